@@ -1,0 +1,108 @@
+"""Pins oracle/im_oracle.py to the UNMODIFIED reference (build container only; skipped on
+the GPU box where /root/reference does not exist — the committed tests/golden fixtures
+cover that side)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from harness import (assert_same, make_delay_mask, random_case, reference_available, run_oracle,
+                     run_reference)
+from marl_for_im_b200 import presets
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not present")
+
+MODES = list(itertools.product([False, True], repeat=3))   # (td, pd, pa)
+
+
+def _legal(kind, td, pd, pa):
+    return not (kind.startswith("MAIM") and (not td) and pa and (not pd))
+
+
+@pytest.mark.parametrize("kind,preset", [("MAIM", "serial4"), ("IM", "serial4"), ("MAIM", "serial8"),
+                                         ("IM", "serial8"), ("MAIM", "serial2"),
+                                         ("MAIM_div", "div1"), ("IM_div", "div1"),
+                                         ("MAIM_div", "div2"), ("IM_div", "div2")])
+@pytest.mark.parametrize("mode", MODES)
+def test_all_obs_modes(kind, preset, mode):
+    td, pd, pa = mode
+    if not _legal(kind, td, pd, pa):
+        pytest.skip("constructor raises 'Not Implemented' (quirk 3)")
+    rng = np.random.default_rng(hash((kind, preset, mode)) % (2 ** 32))
+    for P, mu, amode, indep in [(1, 5, "uniform", False), (3, 15, "uniform", True), (2, 5, "near_eq", False)]:
+        cfg = presets.PRESETS[preset](time_dependency=td, prev_demand=pd, prev_actions=pa, prev_length=P,
+                                      independent=indep)
+        # heterogeneous capacities / targets so that every per-field maximum is distinguishable
+        m = cfg.get("num_nodes", cfg.get("num_stages"))
+        cfg["inv_max"] = np.array([30, 25, 40, 35, 30, 45, 20, 30][:m], dtype=float)
+        cfg["inv_target"] = np.array([0, 3, 5.5, 1, 0, 2, 4, 0][:m], dtype=float)
+        for _ in range(3):
+            demand, actions = random_case(kind, cfg, rng, mu=mu, action_mode=amode)
+            assert_same(run_reference(kind, cfg, demand, actions), run_oracle(kind, cfg, demand, actions),
+                        f"{kind}/{preset}/{mode}/P{P}")
+
+
+@pytest.mark.parametrize("kind,preset", [("MAIM", "serial4"), ("IM", "serial4"), ("IM_div", "div1")])
+def test_non_standardised(kind, preset):
+    rng = np.random.default_rng(7)
+    for td, pd, pa in MODES:
+        if not _legal(kind, td, pd, pa):
+            continue
+        cfg = presets.PRESETS[preset](time_dependency=td, prev_demand=pd, prev_actions=pa, prev_length=2)
+        cfg["standardise_state"] = False
+        cfg["standardise_actions"] = False
+        for mu in (5, 20):
+            demand, actions = random_case(kind, cfg, rng, mu=mu)
+            assert_same(run_reference(kind, cfg, demand, actions), run_oracle(kind, cfg, demand, actions),
+                        f"{kind} raw {td, pd, pa}")
+
+
+@pytest.mark.parametrize("kind,preset", [("MAIM", "serial4"), ("IM", "serial8"), ("MAIM_div", "div2"),
+                                         ("IM_div", "div1")])
+def test_noisy_delay_replayed(kind, preset):
+    rng = np.random.default_rng(11)
+    cfg = presets.PRESETS[preset]()
+    for _ in range(6):
+        demand, actions = random_case(kind, cfg, rng, mu=6, action_mode="near_eq")
+        mask = make_delay_mask(kind, cfg["delay"], cfg["num_periods"], 0.3, rng)
+        assert_same(run_reference(kind, cfg, demand, actions, mask), run_oracle(kind, cfg, demand, actions, mask),
+                    f"{kind} noisy delay")
+
+
+def test_custom_ab_and_order_max():
+    rng = np.random.default_rng(3)
+    cfg = presets.serial4(prev_actions=True)
+    cfg["a"], cfg["b"] = 0, 3
+    cfg["order_max"] = np.array([20., 30., 25., 30.])
+    for kind in ("MAIM", "IM"):
+        T, m = 30, 4
+        demand = rng.poisson(7, T)
+        actions = rng.uniform(-0.2, 3.3, size=(T, m))
+        assert_same(run_reference(kind, cfg, demand, actions), run_oracle(kind, cfg, demand, actions), kind)
+
+
+def test_base_stock_rollout_and_dfo():
+    from scipy.stats import poisson
+    from oracle import im_oracle
+    from oracle.ref_import import load_reference
+    R = load_reference()
+    rng = np.random.default_rng(5)
+    for preset, zs in (("serial4", [25, 25, 25, 25]), ("serial8", [12.5, 20, 31.25, 8, 25, 25, 17, 40])):
+        cfg = presets.PRESETS[preset](time_dependency=False, prev_demand=False, prev_actions=False,
+                                      standardise_state=False, standardise_actions=False)
+        ref_env = R.InvManagement(dict(cfg))
+        ref_env.reset()                      # sets env.dist / dist_param (poisson, mu=5)
+        orc = im_oracle.OracleEnv("IM", cfg)
+        for _ in range(4):
+            demand = rng.poisson(5, 30)
+            z = np.array(zs, dtype=float)
+            want = R.dfo_func(z, ref_env, demand)
+            pmf = poisson.pmf(demand, mu=5)
+            got = im_oracle.dfo_value(orc, z, demand, pmf)
+            assert got == want
+            rewards = im_oracle.base_stock_rollout(orc, z, demand)
+            ref_env.reset(customer_demand=demand)
+            for t in range(30):
+                _, r, _, _ = ref_env.step(R.base_stock_policy(z, ref_env))
+                assert r == rewards[t]
+            np.testing.assert_allclose([im_oracle.poisson_pmf(int(k), 5.0) for k in demand], pmf, rtol=1e-13)
