@@ -1,0 +1,193 @@
+/*
+ * imx_b200.h — C ABI of the B200-native batched inventory-management environment step.
+ *
+ * Drop-in boundary for ONE hot path of MarwanMousa/MARL-for-IM: reset()/step() of
+ *   environments/IM_env.py        InvManagement             (kind IMX_KIND_IM)
+ *   environments/MAIM_env.py      MultiAgentInvManagement   (kind IMX_KIND_MAIM)
+ *   environments/IM_div_env.py    InvManagementDiv          (kind IMX_KIND_IM_DIV)
+ *   environments/MAIM_div_env.py  MultiAgentInvManagementDiv(kind IMX_KIND_MAIM_DIV)
+ * and the rollout loop of base_restock_policy.py.  The reference has no FFI layer (it is
+ * pure Python); each entry point below names the reference method it replaces.  A batch of
+ * N independent environments advances in lock-step (episodes are fixed length, so the
+ * period counter is a scalar of the batch, cf. MAIM_env.py:395-397).
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every `_dev` pointer is caller-owned device memory on the
+ *     env's device (e.g. a torch tensor's data_ptr()), valid until the stream work finishes;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - no entry point synchronises the device or allocates memory after imx_create(), except
+ *     the *_host convenience calls, so reset/step sequences can be captured in CUDA graphs;
+ *   - return value 0 = success, negative = error (imx_last_error() gives the message, thread
+ *     local); nothing throws across the ABI;
+ *   - one handle is not thread-safe; different handles are independent.
+ *
+ * Data layout (row-major, env index slowest unless stated)
+ *   actions  [N][m] float64      reward (MAIM kinds) [N][m] float64, (IM kinds) [N] float64
+ *   obs      [N][m][O] float64   row i of env n = agent i's observation vector
+ *   demand   [N][R][T] int32     replayed customer demand, R = number of retailers (serial: 1)
+ *   mask     [N][T][m] uint8     replayed noisy-delay Bernoulli outcomes (u <= threshold)
+ *   state    int32 structure-of-arrays, see imx_state_field()
+ */
+#ifndef IMX_B200_H
+#define IMX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMX_ABI_VERSION 1
+#define IMX_MAX_NODES 32     /* agents (stages / nodes) per env: one lane each            */
+#define IMX_MAX_CHILDREN 8   /* children per node in a divergent network                  */
+#define IMX_MAX_DELAY 8      /* lead time per stage (shipped configs use <= 4)            */
+#define IMX_MAX_HIST 8       /* prev_length (shipped configs use 1..3)                    */
+
+enum imx_kind { IMX_KIND_IM = 0, IMX_KIND_MAIM = 1, IMX_KIND_IM_DIV = 2, IMX_KIND_MAIM_DIV = 3 };
+enum imx_demand_dist { IMX_DIST_REPLAY_ONLY = 0, IMX_DIST_POISSON = 1, IMX_DIST_UNIFORM = 2 };
+
+/* Per-config constants.  The host mirrors the reference constructors
+ * (IM_env.py:7-162, MAIM_env.py:8-173, IM_div_env.py:9-199, MAIM_div_env.py:9-237): it applies
+ * the per-class defaults and passes explicit vectors; the library derives demand_max, the
+ * depth-based node prices of the divergent envs, the observation length and the state layout. */
+typedef struct imx_config {
+    int32_t kind;                 /* enum imx_kind                                           */
+    int32_t num_nodes;            /* m: num_stages (serial) / num_nodes (divergent)          */
+    int32_t num_periods;          /* T                                                       */
+    int32_t prev_length;          /* P                                                       */
+    int32_t time_dependency;      /* obs carries the lead-time pipeline                      */
+    int32_t prev_demand;          /* obs carries the last P demands                          */
+    int32_t prev_actions;         /* obs carries the last P clipped orders                   */
+    int32_t standardise_state;    /* ignored (treated as 1) for IMX_KIND_MAIM_DIV            */
+    int32_t standardise_actions;  /* ignored (treated as 1) for IMX_KIND_MAIM_DIV            */
+    int32_t independent;          /* MAIM kinds: per-agent profit (1) or shared mean (0)     */
+    int32_t share_network;        /* MAIM_DIV: append the node-id feature                    */
+    int32_t noisy_delay;          /* allocate the carry state; 0 = lead times are exact      */
+    int32_t demand_dist;          /* enum imx_demand_dist: generator used when reset() gets no trace */
+    int32_t uniform_low;          /* IMX_DIST_UNIFORM: integers in [low, high)               */
+    int32_t uniform_high;
+    int32_t device;               /* CUDA device ordinal                                      */
+    double a, b;                  /* rescale interval (IM_DIV: the host passes -1, 1)        */
+    double mu;                    /* IMX_DIST_POISSON mean                                   */
+    double noisy_delay_threshold; /* used when the mask is generated (Philox) instead of replayed */
+    uint64_t seed;                /* Philox key                                               */
+    int64_t num_envs;             /* N: envs in this handle (this rank's shard)              */
+    int64_t env_offset;           /* global index of local env 0 (Philox counter; makes results independent of sharding) */
+    int32_t inv_init[IMX_MAX_NODES];
+    int32_t inv_max[IMX_MAX_NODES];
+    int32_t order_max[IMX_MAX_NODES];
+    int32_t delay[IMX_MAX_NODES];                       /* >= 1, <= IMX_MAX_DELAY            */
+    double inv_target[IMX_MAX_NODES];
+    double stock_cost[IMX_MAX_NODES];
+    double backlog_cost[IMX_MAX_NODES];
+    double price[IMX_MAX_NODES + 1];                    /* serial kinds: price[i] sell, price[i+1] buy */
+    int32_t num_children[IMX_MAX_NODES];                /* divergent kinds                    */
+    int32_t children[IMX_MAX_NODES][IMX_MAX_CHILDREN];  /* in the order listed in `connections` (the split is order dependent) */
+} imx_config;
+
+typedef struct imx_env imx_env;   /* opaque */
+
+/* Optional per-step diagnostics, replacing the `info` dict of step()
+ * (MAIM_env.py:399-409, IM_env.py:345-350).  Any pointer may be NULL. */
+typedef struct imx_info_out {
+    int32_t* demand_dev;       /* [N][m] */
+    int32_t* ship_dev;         /* [N][m] */
+    int32_t* acquisition_dev;  /* [N][m] */
+    int32_t* order_dev;        /* [N][m]  'actual order' */
+    double*  profit_dev;       /* [N][m] */
+} imx_info_out;
+
+/* State fields for imx_state_field(): the persistent per-env state is exactly these int32
+ * arrays; everything else in the reference's [T+1, m] arrays is history. */
+enum imx_field {
+    IMX_F_INV = 0,        /* [N][m]                                                          */
+    IMX_F_BACKLOG = 1,    /* [N][m]                                                          */
+    IMX_F_ORDER_U = 2,    /* [N][m]                                                          */
+    IMX_F_PIPE = 3,       /* [N][L], L = sum(delay); stage i owns delay[i] consecutive slots, slot k arrives in k+1 periods */
+    IMX_F_HIST_D = 4,     /* [N][m][P] last P demands (present iff the obs mode reads them)  */
+    IMX_F_HIST_O = 5,     /* [N][m][P] last P clipped orders (iff prev_actions)              */
+    IMX_F_CARRY = 6,      /* [N][m] goods held back one period by a noisy delay (iff noisy_delay) */
+    IMX_F_BACKLOG_TO = 7, /* [N][NB] signed per-child backlog ledger of the split nodes, NB = sum of their child counts */
+    IMX_F_ERROR = 8,      /* [N] watchdog code of the divergent split (0 = ok, 1..4 = "Infinite Loop k") */
+    IMX_F_DEMAND = 9,     /* [T][R][N] the episode's demand trace as the kernels read it (transposed) */
+    IMX_F_COUNT = 10
+};
+
+const char* imx_last_error(void);
+int imx_abi_version(void);
+int imx_config_size(void);   /* sizeof(imx_config): lets a foreign-language binding verify its struct mirror */
+
+/* Env(config)  —  the constructors cited above.  Allocates all device state (zero further
+ * allocations afterwards) and leaves the batch in the reset state with an all-zero demand trace. */
+int imx_create(const imx_config* cfg, imx_env** out);
+int imx_destroy(imx_env* env);
+
+/* Derived sizes: O (observation length per agent), S (int32 state words per env), R, L, NB. */
+int imx_obs_len(const imx_env* env);
+int imx_state_words(const imx_env* env);
+int imx_num_retailers(const imx_env* env);
+int imx_pipe_words(const imx_env* env);
+int imx_ledger_words(const imx_env* env);
+int imx_retailers(const imx_env* env, int32_t* out /* [R] */);
+int imx_demand_max(const imx_env* env, int32_t* out /* [m] */);
+int imx_node_price(const imx_env* env, double* sell /* [m] */, double* buy /* [m] */);
+
+/* Device pointer + element count of one state field (count 0 = field absent in this config). */
+int imx_state_field(imx_env* env, int field, void** dev_ptr, int64_t* count);
+
+/* Batch period counter (env.period).  Set it only to re-synchronise after replaying a captured graph. */
+int imx_period(const imx_env* env);
+int imx_set_period(imx_env* env, int t);
+
+/* reset(customer_demand=None, noisy_delay=False, ...)  —  IM_env.py:164-229, MAIM_env.py:176-240,
+ * IM_div_env.py:201-302, MAIM_div_env.py:240-341.
+ *   demand_dev      replayed trace [N][R][T] int32, or NULL: draw Poisson/uniform demand from the
+ *                   counter-based Philox stream keyed by (seed; global env, retailer, period, episode)
+ *   delay_mask_dev  [N][T][m] uint8 replayed noisy-delay outcomes, or NULL: drawn from Philox with
+ *                   noisy_delay_threshold when `noisy` is non-zero.  Needs cfg.noisy_delay = 1.
+ *   noisy           0: exact lead times for this episode
+ *   obs_dev         [N][m][O] receives the initial observation (may be NULL)                      */
+int imx_reset(imx_env* env, const int32_t* demand_dev, const uint8_t* delay_mask_dev, int noisy,
+              uint64_t episode, double* obs_dev, void* stream);
+
+/* step(action)  —  IM_env.py:287-360, MAIM_env.py:330-411, IM_div_env.py:361-549,
+ * MAIM_div_env.py:441-630: order clipping, demand propagation, acquisition, shipment (+ split),
+ * backlog / pipeline / inventory update, profit reward, observation build.  One kernel launch.
+ * done = imx_period(env) >= T after the call.  info may be NULL. */
+int imx_step(imx_env* env, const double* actions_dev, double* obs_dev, double* reward_dev,
+             const imx_info_out* info, void* stream);
+
+/* dfo_func's loop  —  base_restock_policy.py:24-45 with base_stock_policy :4-21 fused in: a whole
+ * K = T period episode per env in ONE kernel, state on chip.
+ *   z_dev          base-stock levels, [m] (z_stride = 0) or [N][m] (z_stride = m)
+ *   demand_dev     [N][R][T] replayed trace or NULL (Philox, same stream as imx_reset)
+ *   pmf_dev        optional [N][T] float64 probabilities of the demand trace, or NULL
+ *   return_dev     IM kinds [N], MAIM kinds [N][m]: sum over periods of the step reward
+ *   step_reward_dev optional [T][N] (IM kinds) / [T][N][m] (MAIM kinds) per-period rewards, or NULL
+ *   dfo_dev        optional [N]: -(1/T) * np.sum(pmf * reward)  (needs pmf_dev; IM kinds only)
+ *   write_state    non-zero: leave the final state in the env (period = T), else env is untouched */
+int imx_rollout_basestock(imx_env* env, const double* z_dev, int z_stride, const int32_t* demand_dev,
+                          uint64_t episode, const double* pmf_dev, double* return_dev,
+                          double* step_reward_dev, double* dfo_dev, int write_state, void* stream);
+
+/* Episode statistics for the cross-GPU all-reduce: stats_dev[0..2] = {n, sum, sum of squares} of the
+ * per-env total return, then per agent {sum, sum of squares} (MAIM kinds).  Deterministic order. */
+int imx_return_stats(imx_env* env, const double* return_dev, double* stats_dev /* [3 + 2m] */, void* stream);
+
+/* End-to-end convenience calls on HOST buffers (pinned memory recommended): copy in, launch, copy
+ * out, synchronise.  These are what a per-step Python caller pays for. */
+int imx_reset_host(imx_env* env, const int32_t* demand_host, const uint8_t* delay_mask_host, int noisy,
+                   uint64_t episode, double* obs_host);
+int imx_step_host(imx_env* env, const double* actions_host, double* obs_host, double* reward_host);
+
+/* Poisson CDF table the Philox demand generator inverts (cdf[k] = P(X <= k), last entry a
+ * sentinel > 1).  Returns the table length; copies min(len, cap) entries when out != NULL. */
+int imx_poisson_cdf(const imx_env* env, double* out, int cap);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+int64_t imx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMX_B200_H */

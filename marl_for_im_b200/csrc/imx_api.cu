@@ -1,0 +1,631 @@
+// imx_api.cu — C ABI (include/imx_b200.h) over the sm_100a kernels: handle management, config
+// validation and derivation, kernel dispatch.  No torch, no CPU fallback: every entry point
+// either launches CUDA work or returns an error.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <atomic>
+#include <new>
+#include <vector>
+
+#include "imx_reset.cuh"
+#include "imx_rollout.cuh"
+
+using namespace imx;
+
+// --------------------------------------------------------------------------------------
+// errors
+// --------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define IMX_CUDA(call)                                                                             \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) return fail(-2, "%s failed: %s", #call, cudaGetErrorString(e__));   \
+    } while (0)
+#define IMX_CHECK_LAUNCH(name)                                                                     \
+    do {                                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                                      \
+        if (e__ != cudaSuccess) return fail(-3, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                        \
+    } while (0)
+
+extern "C" const char* imx_last_error(void) { return g_err; }
+extern "C" int imx_abi_version(void) { return IMX_ABI_VERSION; }
+extern "C" int imx_config_size(void) { return (int)sizeof(imx_config); }
+extern "C" int64_t imx_launch_count(void) { return g_launches.load(); }
+
+// --------------------------------------------------------------------------------------
+// handle
+// --------------------------------------------------------------------------------------
+typedef void (*step_fn_t)(const StepArgs);
+typedef void (*reset_fn_t)(const StepArgs, int);
+typedef void (*rollout_fn_t)(const StepArgs, const RolloutArgs);
+
+struct imx_env {
+    imx_config cfg;
+    bool div, multi;
+    int m, T, P, D, O, L, NB, R, maxc;
+    int demand_max[IMX_MAX_NODES];
+    int depth[IMX_MAX_NODES], parent[IMX_MAX_NODES], child_slot[IMX_MAX_NODES];
+    int retailers[IMX_MAX_NODES], retailer_idx[IMX_MAX_NODES];
+    double sell[IMX_MAX_NODES], buy[IMX_MAX_NODES];
+    bool need_hd, need_ho, write_hd, has_carry;
+    int S;                               // int32 state words per env
+    int64_t N;
+    // device memory
+    NodeParams* d_nodes = nullptr;
+    int8_t* d_children = nullptr;
+    int32_t* d_state = nullptr;          // one block holding every state field
+    size_t state_bytes = 0;
+    void* field_ptr[IMX_F_COUNT] = {};
+    int64_t field_cnt[IMX_F_COUNT] = {};
+    int32_t* d_err = nullptr;
+    int32_t* d_demand_T = nullptr;
+    uint8_t* d_mask_T = nullptr;
+    double* d_cdf = nullptr;
+    int cdf_len = 0;
+    // host-call staging (allocated on first use)
+    cudaStream_t hstream = nullptr;
+    double *d_act_h = nullptr, *d_obs_h = nullptr, *d_rew_h = nullptr;
+    int32_t* d_dem_h = nullptr;
+    uint8_t* d_mask_h = nullptr;
+    // episode bookkeeping
+    int t = 0;
+    int noisy_now = 0;
+    uint64_t episode = 0;
+    // kernels
+    step_fn_t step_fn = nullptr;
+    reset_fn_t reset_fn = nullptr;
+    rollout_fn_t rollout_fn = nullptr;
+    int step_grid_cap = 0, rollout_grid_cap = 0;
+    size_t step_smem = 0;
+    int m_pad = 0;
+};
+
+// --------------------------------------------------------------------------------------
+// kernel dispatch tables
+// --------------------------------------------------------------------------------------
+template <int M_PAD, bool DIV>
+static void pick_kernels(imx_env* e) {
+    const bool small = (e->D <= 4 && e->P <= 1);
+    if constexpr (DIV) {
+        const bool few = e->maxc <= 2;
+        if (small && few) { e->step_fn = step_kernel<M_PAD, 4, 1, 2, true>; e->rollout_fn = rollout_kernel<M_PAD, 4, 2, true>; }
+        else if (small)   { e->step_fn = step_kernel<M_PAD, 4, 1, 8, true>; e->rollout_fn = rollout_kernel<M_PAD, 4, 8, true>; }
+        else if (few)     { e->step_fn = step_kernel<M_PAD, 8, 8, 2, true>; e->rollout_fn = rollout_kernel<M_PAD, 8, 2, true>; }
+        else              { e->step_fn = step_kernel<M_PAD, 8, 8, 8, true>; e->rollout_fn = rollout_kernel<M_PAD, 8, 8, true>; }
+    } else {
+        if (small) { e->step_fn = step_kernel<M_PAD, 4, 1, 1, false>; e->rollout_fn = rollout_kernel<M_PAD, 4, 1, false>; }
+        else       { e->step_fn = step_kernel<M_PAD, 8, 8, 1, false>; e->rollout_fn = rollout_kernel<M_PAD, 8, 1, false>; }
+    }
+    e->reset_fn = small ? reset_kernel<4, 1> : reset_kernel<8, 8>;
+    e->m_pad = M_PAD;
+}
+
+static int select_kernels(imx_env* e) {
+    const int m = e->m;
+    if (e->div) {
+        if (m <= 4) pick_kernels<4, true>(e);
+        else if (m <= 8) pick_kernels<8, true>(e);
+        else if (m <= 16) pick_kernels<16, true>(e);
+        else pick_kernels<32, true>(e);
+    } else {
+        if (m <= 2) pick_kernels<2, false>(e);
+        else if (m <= 4) pick_kernels<4, false>(e);
+        else if (m <= 8) pick_kernels<8, false>(e);
+        else if (m <= 16) pick_kernels<16, false>(e);
+        else pick_kernels<32, false>(e);
+    }
+    const int epw = 32 / e->m_pad;
+    const int tile_doubles = (epw * m * e->O + 1) & ~1;
+    e->step_smem = (size_t)(STEP_THREADS / 32) * tile_doubles * sizeof(double);
+    IMX_CUDA(cudaFuncSetAttribute((const void*)e->step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem));
+    int dev_sms = 0, occ = 0;
+    IMX_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e->cfg.device));
+    IMX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e->step_fn, STEP_THREADS, e->step_smem));
+    if (occ < 1) return fail(-4, "step kernel does not fit on an SM (smem %zu B)", e->step_smem);
+    e->step_grid_cap = dev_sms * occ;
+    IMX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e->rollout_fn, ROLLOUT_THREADS, 0));
+    if (occ < 1) return fail(-4, "rollout kernel does not fit on an SM");
+    e->rollout_grid_cap = dev_sms * occ;
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// config validation + derivation (host mirror of the reference constructors)
+// --------------------------------------------------------------------------------------
+static int derive(imx_env* e) {
+    const imx_config& c = e->cfg;
+    if (c.kind < IMX_KIND_IM || c.kind > IMX_KIND_MAIM_DIV) return fail(-1, "unknown kind %d", c.kind);
+    e->div = (c.kind == IMX_KIND_IM_DIV || c.kind == IMX_KIND_MAIM_DIV);
+    e->multi = (c.kind == IMX_KIND_MAIM || c.kind == IMX_KIND_MAIM_DIV);
+    const int m = e->m = c.num_nodes;
+    if (m < 1 || m > IMX_MAX_NODES) return fail(-1, "num_nodes %d outside [1, %d]", m, IMX_MAX_NODES);
+    if (e->div && m < 2) return fail(-1, "a divergent network needs at least 2 nodes");
+    e->T = c.num_periods;
+    if (e->T < 1 || e->T > 65535) return fail(-1, "num_periods %d outside [1, 65535]", e->T);
+    e->P = c.prev_length;
+    const bool uses_hist = c.prev_demand || c.prev_actions;
+    if (uses_hist && (e->P < 1 || e->P > IMX_MAX_HIST)) return fail(-1, "prev_length %d outside [1, %d]", e->P, IMX_MAX_HIST);
+    if (!uses_hist) e->P = (e->P < 1) ? 1 : (e->P > IMX_MAX_HIST ? IMX_MAX_HIST : e->P);
+    e->N = c.num_envs;
+    if (e->N < 1) return fail(-1, "num_envs must be >= 1");
+    if (!(c.b != c.a)) return fail(-1, "rescale interval needs a != b");
+    if (e->multi && !c.time_dependency && c.prev_actions && !c.prev_demand)
+        return fail(-5, "Not Implemented");   // MAIM_env.py:135-136, MAIM_div_env.py:164-165
+
+    e->D = 0;
+    e->L = 0;
+    for (int i = 0; i < m; ++i) {
+        if (c.delay[i] < 1 || c.delay[i] > IMX_MAX_DELAY)
+            return fail(-1, "delay[%d] = %d outside [1, %d]", i, c.delay[i], IMX_MAX_DELAY);
+        if (c.inv_max[i] < 1) return fail(-1, "inv_max[%d] must be >= 1", i);
+        if (c.order_max[i] < 1) return fail(-1, "order_max[%d] must be >= 1", i);
+        if (c.inv_init[i] < 0) return fail(-1, "init_inv[%d] must be >= 0", i);
+        if (c.inv_max[i] > (1 << 28) || c.order_max[i] > (1 << 28)) return fail(-1, "capacities above 2^28 are not supported");
+        e->D = c.delay[i] > e->D ? c.delay[i] : e->D;
+        e->L += c.delay[i];
+    }
+
+    for (int i = 0; i < m; ++i) { e->parent[i] = -1; e->child_slot[i] = -1; e->retailer_idx[i] = -1; e->depth[i] = 0; }
+    e->maxc = 0;
+    e->NB = 0;
+    e->R = 0;
+    if (e->div) {
+        for (int p = 0; p < m; ++p) {
+            const int nc = c.num_children[p];
+            if (nc < 0 || nc > IMX_MAX_CHILDREN) return fail(-1, "node %d has %d children (max %d)", p, nc, IMX_MAX_CHILDREN);
+            e->maxc = nc > e->maxc ? nc : e->maxc;
+            for (int k = 0; k < nc; ++k) {
+                const int ch = c.children[p][k];
+                if (ch <= p || ch >= m)   // utils.py:87-92
+                    return fail(-1, "Downstream node cannot have a smaller index number than upstream node (%d -> %d)", p, ch);
+                if (e->parent[ch] != -1) return fail(-1, "node %d has more than one upstream node", ch);
+                e->parent[ch] = p;
+                e->child_slot[ch] = k;
+            }
+        }
+        for (int i = 1; i < m; ++i) {
+            if (e->parent[i] < 0) return fail(-1, "node %d is not connected to node 0", i);
+            e->depth[i] = e->depth[e->parent[i]] + 1;          // parents have smaller indices
+        }
+        for (int i = 0; i < m; ++i) {
+            if (c.num_children[i] == 0) { e->retailer_idx[i] = e->R; e->retailers[e->R++] = i; }
+            e->sell[i] = (double)(e->depth[i] + 2);            // MAIM_div_env.py:55-61
+            e->buy[i] = (double)(e->depth[i] + 1);
+            int dm = c.inv_max[i], s = 0;                      // MAIM_div_env.py:91-99
+            for (int k = 0; k < c.num_children[i]; ++k) s += c.order_max[c.children[i][k]];
+            e->demand_max[i] = s > dm ? s : dm;
+        }
+        if (c.order_max[0] > c.inv_max[0]) return fail(-1, "order_max[0] must not exceed inv_max[0]");   // MAIM_div_env.py:235
+    } else {
+        e->R = 1;
+        e->retailers[0] = 0;
+        e->retailer_idx[0] = 0;
+        for (int i = 0; i < m; ++i) {
+            if (!(c.price[i] > c.price[i + 1])) return fail(-1, "price must be strictly decreasing (MAIM_env.py:167-168)");
+            e->sell[i] = c.price[i];
+            e->buy[i] = c.price[i + 1];
+            e->demand_max[i] = c.inv_max[i];
+        }
+        if (c.order_max[m - 1] > c.inv_max[m - 1]) return fail(-1, "order_max of the last stage must not exceed its inv_max (MAIM_env.py:171)");
+    }
+
+    const bool std_state = (c.kind == IMX_KIND_MAIM_DIV) ? true : (c.standardise_state != 0);
+    // quirk 2: MAIM kinds in mode (td=F, pd=T, pa=F) never write the demand-history slots
+    e->write_hd = !(e->multi && c.prev_demand && !c.prev_actions && !c.time_dependency);
+    e->need_hd = c.prev_demand && e->write_hd && !(e->multi && !std_state);
+    e->need_ho = c.prev_actions && !(e->multi && !std_state);
+    e->has_carry = c.noisy_delay != 0;
+    e->O = 3 + (c.prev_demand ? e->P : 0) + (c.prev_actions ? e->P : 0) + (c.time_dependency ? e->D : 0)
+         + ((c.kind == IMX_KIND_MAIM_DIV && c.share_network) ? 1 : 0);
+    e->NB = 0;
+    if (e->div)
+        for (int i = 0; i < m; ++i)
+            if (c.num_children[i] > 1) e->NB += c.num_children[i];
+    e->S = 3 * m + e->L + (e->need_hd ? m * e->P : 0) + (e->need_ho ? m * e->P : 0) + (e->has_carry ? m : 0) + e->NB;
+
+    if (c.demand_dist == IMX_DIST_POISSON && !(c.mu > 0.0 && c.mu <= 1000.0)) return fail(-1, "mu must be in (0, 1000]");
+    if (c.demand_dist == IMX_DIST_UNIFORM && !(c.uniform_low < c.uniform_high))
+        return fail(-1, "Lower bound cannot be larger than upper bound");    // MAIM_env.py:215-216
+    if (c.demand_dist < IMX_DIST_REPLAY_ONLY || c.demand_dist > IMX_DIST_UNIFORM)
+        return fail(-1, "Unrecognised, Distribution Not Implemented");        // MAIM_env.py:219
+    return 0;
+}
+
+static void fill_args(const imx_env* e, StepArgs& A) {
+    const imx_config& c = e->cfg;
+    memset(&A, 0, sizeof(A));
+    A.N = e->N; A.m = e->m; A.T = e->T; A.P = e->P; A.D = e->D; A.O = e->O; A.L = e->L; A.NB = e->NB; A.R = e->R;
+    A.t = e->t;
+    A.maxc = e->maxc;
+    A.multi = e->multi;
+    const bool always_std = (c.kind == IMX_KIND_MAIM_DIV);    // quirk 9
+    A.std_state = always_std ? 1 : (c.standardise_state != 0);
+    A.std_actions = always_std ? 1 : (c.standardise_actions != 0);
+    A.cap_backlog = always_std ? 1 : A.std_state;
+    A.independent = c.independent != 0;
+    A.share_network = (c.kind == IMX_KIND_MAIM_DIV && c.share_network);
+    A.td = c.time_dependency != 0; A.pd = c.prev_demand != 0; A.pa = c.prev_actions != 0;
+    A.write_hd = e->write_hd;
+    A.noisy = e->noisy_now;
+    A.has_carry = e->has_carry;
+    A.need_hd = e->need_hd; A.need_ho = e->need_ho;
+    // watchdog thresholds: MAIM_div 2*dm, dm, dm, dm (:504,526,560,574); IM_div 4*dm, 2*dm, 2*dm, 2*dm (:424,449,483,497)
+    A.wd_mult1 = e->multi ? 2 : 4;
+    A.wd_mult = e->multi ? 1 : 2;
+    A.a = c.a; A.b = c.b; A.bma = c.b - c.a;
+    A.nodes = e->d_nodes;
+    A.children = e->d_children;
+    A.inv = (int32_t*)e->field_ptr[IMX_F_INV];
+    A.backlog = (int32_t*)e->field_ptr[IMX_F_BACKLOG];
+    A.order_u = (int32_t*)e->field_ptr[IMX_F_ORDER_U];
+    A.pipe = (int32_t*)e->field_ptr[IMX_F_PIPE];
+    A.hist_d = (int32_t*)e->field_ptr[IMX_F_HIST_D];
+    A.hist_o = (int32_t*)e->field_ptr[IMX_F_HIST_O];
+    A.carry = (int32_t*)e->field_ptr[IMX_F_CARRY];
+    A.bt = (int32_t*)e->field_ptr[IMX_F_BACKLOG_TO];
+    A.err = e->d_err;
+    A.demand_T = e->d_demand_T;
+    A.mask_T = e->d_mask_T;
+}
+
+static std::vector<double> poisson_cdf(double mu) {
+    // cdf[k] = sum_{j<=k} exp(j*log(mu) - lgamma(j+1) - mu); stop once the tail is below 2^-53
+    std::vector<double> cdf;
+    double acc = 0.0;
+    for (int k = 0; k < 8192; ++k) {
+        acc += std::exp(k * std::log(mu) - std::lgamma(k + 1.0) - mu);
+        cdf.push_back(acc);
+        if (k > mu && 1.0 - acc < 1.2e-16) break;
+    }
+    cdf.back() = 2.0;   // sentinel: the search always terminates inside the table
+    return cdf;
+}
+
+extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
+    if (!cfg || !out) return fail(-1, "null argument");
+    *out = nullptr;
+    imx_env* e = new (std::nothrow) imx_env();
+    if (!e) return fail(-1, "out of host memory");
+    e->cfg = *cfg;
+    int rc = derive(e);
+    if (rc) { delete e; return rc; }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        delete e;
+        return fail(-2, "no CUDA device available (%s) — this library has no CPU fallback", cudaGetErrorString(ce));
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { delete e; return fail(-1, "device %d out of range", cfg->device); }
+#define IMX_CREATE_CUDA(call)                                                                      \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            fail(-2, "%s failed: %s", #call, cudaGetErrorString(e__));                              \
+            imx_destroy(e);                                                                        \
+            return -2;                                                                             \
+        }                                                                                          \
+    } while (0)
+    IMX_CREATE_CUDA(cudaSetDevice(cfg->device));
+    rc = select_kernels(e);
+    if (rc) { imx_destroy(e); return rc; }
+
+    const int m = e->m;
+    const int64_t N = e->N;
+    // node table
+    NodeParams h_nodes[IMX_MAX_NODES];
+    int8_t h_children[IMX_MAX_NODES * IMX_MAX_CHILDREN];
+    memset(h_nodes, 0, sizeof(h_nodes));
+    memset(h_children, -1, sizeof(h_children));
+    int pipe_off = 0, bt_off = 0;
+    for (int i = 0; i < m; ++i) {
+        NodeParams& q = h_nodes[i];
+        q.inv_max = cfg->inv_max[i]; q.order_max = cfg->order_max[i]; q.demand_max = e->demand_max[i];
+        q.delay = cfg->delay[i]; q.pipe_off = pipe_off; pipe_off += cfg->delay[i];
+        q.init_inv = cfg->inv_init[i];
+        q.parent = e->parent[i]; q.child_slot = e->child_slot[i];
+        q.nchild = e->div ? cfg->num_children[i] : 0;
+        q.bt_off = -1;
+        if (e->div && cfg->num_children[i] > 1) { q.bt_off = bt_off; bt_off += cfg->num_children[i]; }
+        q.retailer_idx = e->retailer_idx[i];
+        q.p = e->sell[i]; q.c = e->buy[i]; q.h = cfg->stock_cost[i]; q.bc = cfg->backlog_cost[i]; q.target = cfg->inv_target[i];
+        if (e->div)
+            for (int k = 0; k < cfg->num_children[i]; ++k) h_children[i * IMX_MAX_CHILDREN + k] = (int8_t)cfg->children[i][k];
+    }
+    IMX_CREATE_CUDA(cudaMalloc(&e->d_nodes, sizeof(h_nodes)));
+    IMX_CREATE_CUDA(cudaMemcpy(e->d_nodes, h_nodes, sizeof(h_nodes), cudaMemcpyHostToDevice));
+    IMX_CREATE_CUDA(cudaMalloc(&e->d_children, sizeof(h_children)));
+    IMX_CREATE_CUDA(cudaMemcpy(e->d_children, h_children, sizeof(h_children), cudaMemcpyHostToDevice));
+
+    // state block: fields back to back, each 256-byte aligned
+    const int64_t cnt[IMX_F_COUNT] = {
+        N * m, N * m, N * m, N * e->L,
+        e->need_hd ? N * m * e->P : 0, e->need_ho ? N * m * e->P : 0,
+        e->has_carry ? N * m : 0, N * e->NB, 0, 0};
+    size_t off[IMX_F_COUNT] = {};
+    size_t total = 0;
+    for (int f = 0; f <= IMX_F_BACKLOG_TO; ++f) {
+        off[f] = total;
+        total += ((size_t)cnt[f] * sizeof(int32_t) + 255) & ~(size_t)255;
+    }
+    e->state_bytes = total;
+    IMX_CREATE_CUDA(cudaMalloc(&e->d_state, total ? total : 256));
+    for (int f = 0; f <= IMX_F_BACKLOG_TO; ++f) {
+        e->field_cnt[f] = cnt[f];
+        e->field_ptr[f] = cnt[f] ? (void*)((char*)e->d_state + off[f]) : nullptr;
+    }
+    IMX_CREATE_CUDA(cudaMalloc(&e->d_err, (size_t)N * sizeof(int32_t)));
+    e->field_ptr[IMX_F_ERROR] = e->d_err;
+    e->field_cnt[IMX_F_ERROR] = N;
+    const size_t dem_bytes = (size_t)e->T * e->R * N * sizeof(int32_t);
+    IMX_CREATE_CUDA(cudaMalloc(&e->d_demand_T, dem_bytes));
+    e->field_ptr[IMX_F_DEMAND] = e->d_demand_T;
+    e->field_cnt[IMX_F_DEMAND] = (int64_t)e->T * e->R * N;
+    if (e->has_carry) IMX_CREATE_CUDA(cudaMalloc(&e->d_mask_T, (size_t)e->T * N * m));
+    if (cfg->demand_dist == IMX_DIST_POISSON) {
+        std::vector<double> cdf = poisson_cdf(cfg->mu);
+        e->cdf_len = (int)cdf.size();
+        IMX_CREATE_CUDA(cudaMalloc(&e->d_cdf, cdf.size() * sizeof(double)));
+        IMX_CREATE_CUDA(cudaMemcpy(e->d_cdf, cdf.data(), cdf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    // reset state with an all-zero demand trace (the reference constructors end with self.reset())
+    IMX_CREATE_CUDA(cudaMemset(e->d_demand_T, 0, dem_bytes));
+    IMX_CREATE_CUDA(cudaMemset(e->d_state, 0, total ? total : 256));
+    IMX_CREATE_CUDA(cudaMemset(e->d_err, 0, (size_t)N * sizeof(int32_t)));
+    {
+        StepArgs A;
+        fill_args(e, A);
+        A.obs = nullptr;
+        const int64_t cells = N * m;
+        e->reset_fn<<<(unsigned)((cells + 255) / 256), 256>>>(A, e->div ? 1 : 0);
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) { fail(-3, "reset launch failed: %s", cudaGetErrorString(le)); imx_destroy(e); return -3; }
+        g_launches.fetch_add(1);
+        IMX_CREATE_CUDA(cudaDeviceSynchronize());
+    }
+#undef IMX_CREATE_CUDA
+    *out = e;
+    return 0;
+}
+
+extern "C" int imx_destroy(imx_env* e) {
+    if (!e) return 0;
+    cudaSetDevice(e->cfg.device);
+    if (e->hstream) { cudaStreamSynchronize(e->hstream); cudaStreamDestroy(e->hstream); }
+    cudaFree(e->d_nodes); cudaFree(e->d_children); cudaFree(e->d_state); cudaFree(e->d_err);
+    cudaFree(e->d_demand_T); cudaFree(e->d_mask_T); cudaFree(e->d_cdf);
+    cudaFree(e->d_act_h); cudaFree(e->d_obs_h); cudaFree(e->d_rew_h); cudaFree(e->d_dem_h); cudaFree(e->d_mask_h);
+    delete e;
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// getters
+// --------------------------------------------------------------------------------------
+extern "C" int imx_obs_len(const imx_env* e) { return e ? e->O : fail(-1, "null env"); }
+extern "C" int imx_state_words(const imx_env* e) { return e ? e->S : fail(-1, "null env"); }
+extern "C" int imx_num_retailers(const imx_env* e) { return e ? e->R : fail(-1, "null env"); }
+extern "C" int imx_pipe_words(const imx_env* e) { return e ? e->L : fail(-1, "null env"); }
+extern "C" int imx_ledger_words(const imx_env* e) { return e ? e->NB : fail(-1, "null env"); }
+extern "C" int imx_retailers(const imx_env* e, int32_t* out) {
+    if (!e || !out) return fail(-1, "null argument");
+    for (int k = 0; k < e->R; ++k) out[k] = e->retailers[k];
+    return 0;
+}
+extern "C" int imx_demand_max(const imx_env* e, int32_t* out) {
+    if (!e || !out) return fail(-1, "null argument");
+    for (int i = 0; i < e->m; ++i) out[i] = e->demand_max[i];
+    return 0;
+}
+extern "C" int imx_node_price(const imx_env* e, double* sell, double* buy) {
+    if (!e || !sell || !buy) return fail(-1, "null argument");
+    for (int i = 0; i < e->m; ++i) { sell[i] = e->sell[i]; buy[i] = e->buy[i]; }
+    return 0;
+}
+extern "C" int imx_state_field(imx_env* e, int field, void** dev_ptr, int64_t* count) {
+    if (!e || !dev_ptr || !count) return fail(-1, "null argument");
+    if (field < 0 || field >= IMX_F_COUNT) return fail(-1, "unknown field %d", field);
+    *dev_ptr = e->field_ptr[field];
+    *count = e->field_cnt[field];
+    return 0;
+}
+extern "C" int imx_period(const imx_env* e) { return e ? e->t : fail(-1, "null env"); }
+extern "C" int imx_set_period(imx_env* e, int t) {
+    if (!e) return fail(-1, "null env");
+    if (t < 0 || t > e->T) return fail(-1, "period %d outside [0, %d]", t, e->T);
+    e->t = t;
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// reset / step
+// --------------------------------------------------------------------------------------
+static DemandGen make_gen(const imx_env* e, uint64_t episode) {
+    DemandGen g;
+    g.dist = e->cfg.demand_dist; g.low = e->cfg.uniform_low; g.high = e->cfg.uniform_high;
+    g.cdf_len = e->cdf_len; g.cdf = e->d_cdf; g.seed = e->cfg.seed; g.episode = episode; g.env_offset = e->cfg.env_offset;
+    return g;
+}
+
+extern "C" int imx_reset(imx_env* e, const int32_t* demand_dev, const uint8_t* delay_mask_dev, int noisy,
+                         uint64_t episode, double* obs_dev, void* stream) {
+    if (!e) return fail(-1, "null env");
+    cudaStream_t s = (cudaStream_t)stream;
+    IMX_CUDA(cudaSetDevice(e->cfg.device));
+    if ((noisy || delay_mask_dev) && !e->has_carry) return fail(-1, "noisy delay requested but the env was created with noisy_delay = 0");
+    if (!demand_dev && e->cfg.demand_dist == IMX_DIST_REPLAY_ONLY)
+        return fail(-1, "reset() without a demand trace needs demand_dist poisson or uniform");
+    const int64_t N = e->N;
+    const unsigned gb = (unsigned)((N * e->R + 255) / 256);
+    if (demand_dev) {
+        demand_transpose_kernel<<<gb, 256, 0, s>>>(demand_dev, e->d_demand_T, N, e->R, e->T);
+        IMX_CHECK_LAUNCH("demand_transpose_kernel");
+    } else {
+        demand_generate_kernel<<<gb, 256, 0, s>>>(e->d_demand_T, N, e->R, e->T, make_gen(e, episode));
+        IMX_CHECK_LAUNCH("demand_generate_kernel");
+    }
+    e->noisy_now = (noisy || delay_mask_dev) ? 1 : 0;
+    const int64_t cells = N * e->m;
+    const unsigned cb = (unsigned)((cells + 255) / 256);
+    if (e->noisy_now) {
+        if (delay_mask_dev) {
+            mask_transpose_kernel<<<cb, 256, 0, s>>>(delay_mask_dev, e->d_mask_T, N, e->m, e->T);
+            IMX_CHECK_LAUNCH("mask_transpose_kernel");
+        } else {
+            mask_generate_kernel<<<cb, 256, 0, s>>>(e->d_mask_T, N, e->m, e->T, e->cfg.seed, e->cfg.env_offset, episode,
+                                                    e->cfg.noisy_delay_threshold);
+            IMX_CHECK_LAUNCH("mask_generate_kernel");
+        }
+    }
+    IMX_CUDA(cudaMemsetAsync(e->d_state, 0, e->state_bytes, s));
+    IMX_CUDA(cudaMemsetAsync(e->d_err, 0, (size_t)N * sizeof(int32_t), s));
+    e->t = 0;
+    e->episode = episode;
+    StepArgs A;
+    fill_args(e, A);
+    A.obs = obs_dev;
+    e->reset_fn<<<cb, 256, 0, s>>>(A, e->div ? 1 : 0);
+    IMX_CHECK_LAUNCH("reset_kernel");
+    return 0;
+}
+
+static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, double* reward_dev,
+                       const imx_info_out* info, cudaStream_t s) {
+    if (e->t >= e->T) return fail(-6, "step() past the end of the episode (period %d of %d)", e->t, e->T);
+    StepArgs A;
+    fill_args(e, A);
+    A.actions = actions_dev;
+    A.obs = obs_dev;
+    A.reward = reward_dev;
+    if (info) A.info = *info;
+    const int epw = 32 / e->m_pad;
+    const int64_t warp_tiles = (e->N + epw - 1) / epw;
+    const int64_t blocks_needed = (warp_tiles + (STEP_THREADS / 32) - 1) / (STEP_THREADS / 32);
+    const unsigned grid = (unsigned)(blocks_needed < e->step_grid_cap ? blocks_needed : e->step_grid_cap);
+    e->step_fn<<<grid, STEP_THREADS, e->step_smem, s>>>(A);
+    IMX_CHECK_LAUNCH("step_kernel");
+    e->t += 1;
+    return 0;
+}
+
+extern "C" int imx_step(imx_env* e, const double* actions_dev, double* obs_dev, double* reward_dev,
+                        const imx_info_out* info, void* stream) {
+    if (!e || !actions_dev || !reward_dev) return fail(-1, "null argument");
+    IMX_CUDA(cudaSetDevice(e->cfg.device));
+    return launch_step(e, actions_dev, obs_dev, reward_dev, info, (cudaStream_t)stream);
+}
+
+// --------------------------------------------------------------------------------------
+// fused base-stock rollout
+// --------------------------------------------------------------------------------------
+extern "C" int imx_rollout_basestock(imx_env* e, const double* z_dev, int z_stride, const int32_t* demand_dev,
+                                     uint64_t episode, const double* pmf_dev, double* return_dev,
+                                     double* step_reward_dev, double* dfo_dev, int write_state, void* stream) {
+    if (!e || !z_dev || !return_dev) return fail(-1, "null argument");
+    if (z_stride != 0 && z_stride != e->m) return fail(-1, "z_stride must be 0 or m");
+    if (dfo_dev && (!pmf_dev || e->multi)) return fail(-1, "dfo output needs pmf_dev and a single-agent kind");
+    if (!demand_dev && e->cfg.demand_dist == IMX_DIST_REPLAY_ONLY)
+        return fail(-1, "rollout without a demand trace needs demand_dist poisson or uniform");
+    if (e->has_carry) return fail(-1, "the fused rollout does not model noisy delays; create the env with noisy_delay = 0");
+    cudaStream_t s = (cudaStream_t)stream;
+    IMX_CUDA(cudaSetDevice(e->cfg.device));
+    StepArgs A;
+    fill_args(e, A);
+    A.t = 0;
+    RolloutArgs Rg;
+    memset(&Rg, 0, sizeof(Rg));
+    Rg.z = z_dev; Rg.z_stride = z_stride; Rg.demand = demand_dev; Rg.pmf = pmf_dev;
+    Rg.ret = return_dev; Rg.step_reward = step_reward_dev; Rg.dfo = dfo_dev; Rg.write_state = write_state;
+    Rg.gen = make_gen(e, episode);
+    const int epw = 32 / e->m_pad;
+    const int64_t warp_tiles = (e->N + epw - 1) / epw;
+    const int64_t blocks_needed = (warp_tiles + (ROLLOUT_THREADS / 32) - 1) / (ROLLOUT_THREADS / 32);
+    const unsigned grid = (unsigned)(blocks_needed < e->rollout_grid_cap ? blocks_needed : e->rollout_grid_cap);
+    e->rollout_fn<<<grid, ROLLOUT_THREADS, 0, s>>>(A, Rg);
+    IMX_CHECK_LAUNCH("rollout_kernel");
+    if (write_state) { e->t = e->T; e->episode = episode; }
+    return 0;
+}
+
+extern "C" int imx_return_stats(imx_env* e, const double* return_dev, double* stats_dev, void* stream) {
+    if (!e || !return_dev || !stats_dev) return fail(-1, "null argument");
+    IMX_CUDA(cudaSetDevice(e->cfg.device));
+    return_stats_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(return_dev, stats_dev, e->N, e->multi ? e->m : 1, e->multi ? 1 : 0);
+    IMX_CHECK_LAUNCH("return_stats_kernel");
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// host-buffer convenience path (end-to-end: H2D + kernels + D2H + sync)
+// --------------------------------------------------------------------------------------
+static int ensure_host_path(imx_env* e) {
+    if (e->hstream) return 0;
+    IMX_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
+    const size_t cells = (size_t)e->N * e->m;
+    IMX_CUDA(cudaMalloc(&e->d_act_h, cells * sizeof(double)));
+    IMX_CUDA(cudaMalloc(&e->d_obs_h, cells * e->O * sizeof(double)));
+    IMX_CUDA(cudaMalloc(&e->d_rew_h, cells * sizeof(double)));
+    IMX_CUDA(cudaMalloc(&e->d_dem_h, (size_t)e->N * e->R * e->T * sizeof(int32_t)));
+    if (e->has_carry) IMX_CUDA(cudaMalloc(&e->d_mask_h, (size_t)e->N * e->T * e->m));
+    return 0;
+}
+
+extern "C" int imx_reset_host(imx_env* e, const int32_t* demand_host, const uint8_t* delay_mask_host, int noisy,
+                              uint64_t episode, double* obs_host) {
+    if (!e) return fail(-1, "null env");
+    IMX_CUDA(cudaSetDevice(e->cfg.device));
+    int rc = ensure_host_path(e);
+    if (rc) return rc;
+    cudaStream_t s = e->hstream;
+    if (demand_host)
+        IMX_CUDA(cudaMemcpyAsync(e->d_dem_h, demand_host, (size_t)e->N * e->R * e->T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (delay_mask_host) {
+        if (!e->has_carry) return fail(-1, "noisy delay requested but the env was created with noisy_delay = 0");
+        IMX_CUDA(cudaMemcpyAsync(e->d_mask_h, delay_mask_host, (size_t)e->N * e->T * e->m, cudaMemcpyHostToDevice, s));
+    }
+    rc = imx_reset(e, demand_host ? e->d_dem_h : nullptr, delay_mask_host ? e->d_mask_h : nullptr, noisy, episode,
+                   obs_host ? e->d_obs_h : nullptr, s);
+    if (rc) return rc;
+    if (obs_host)
+        IMX_CUDA(cudaMemcpyAsync(obs_host, e->d_obs_h, (size_t)e->N * e->m * e->O * sizeof(double), cudaMemcpyDeviceToHost, s));
+    IMX_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int imx_step_host(imx_env* e, const double* actions_host, double* obs_host, double* reward_host) {
+    if (!e || !actions_host || !reward_host) return fail(-1, "null argument");
+    IMX_CUDA(cudaSetDevice(e->cfg.device));
+    int rc = ensure_host_path(e);
+    if (rc) return rc;
+    cudaStream_t s = e->hstream;
+    const size_t cells = (size_t)e->N * e->m;
+    IMX_CUDA(cudaMemcpyAsync(e->d_act_h, actions_host, cells * sizeof(double), cudaMemcpyHostToDevice, s));
+    rc = launch_step(e, e->d_act_h, obs_host ? e->d_obs_h : nullptr, e->d_rew_h, nullptr, s);
+    if (rc) return rc;
+    if (obs_host) IMX_CUDA(cudaMemcpyAsync(obs_host, e->d_obs_h, cells * e->O * sizeof(double), cudaMemcpyDeviceToHost, s));
+    IMX_CUDA(cudaMemcpyAsync(reward_host, e->d_rew_h, (e->multi ? cells : (size_t)e->N) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    IMX_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int imx_poisson_cdf(const imx_env* e, double* out, int cap) {
+    if (!e) return fail(-1, "null env");
+    if (e->cfg.demand_dist != IMX_DIST_POISSON) return 0;
+    if (out) {
+        std::vector<double> cdf = poisson_cdf(e->cfg.mu);
+        for (int k = 0; k < (int)cdf.size() && k < cap; ++k) out[k] = cdf[k];
+    }
+    return e->cdf_len;
+}

@@ -1,0 +1,226 @@
+// imx_device.cuh — device-side parameter blocks and helpers shared by the step, reset and
+// rollout kernels.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/imx_b200.h"
+
+namespace imx {
+
+// ------------------------------------------------------------------------------------
+// Per-node constants.  Lives in global memory (one small table per env handle); every thread
+// loads the record of ITS stage once at kernel start and keeps it in registers — the
+// thread -> stage mapping is fixed for the whole grid-stride loop (lane % M_PAD).
+// 96 bytes = six 16-byte loads.
+// ------------------------------------------------------------------------------------
+struct __align__(16) NodeParams {
+    int32_t inv_max;
+    int32_t order_max;
+    int32_t demand_max;    // serial: = inv_max (scales backlog / demand history there)
+    int32_t delay;
+    int32_t pipe_off;      // first slot of this node in the ragged pipe[L] record
+    int32_t init_inv;
+    int32_t parent;        // divergent: lane of the parent (-1 for the root / serial)
+    int32_t child_slot;    // divergent: position among the parent's children
+    int32_t nchild;        // divergent: number of children
+    int32_t bt_off;        // divergent: offset of this node's ledger in bt[NB] (-1: not a split node)
+    int32_t retailer_idx;  // row of the demand trace feeding this node (-1: not a retailer)
+    int32_t pad0;
+    double p;              // unit sell price
+    double c;              // unit buy cost
+    double h;              // stock holding cost
+    double bc;             // backlog cost
+    double target;         // inventory target
+    double pad1;
+};
+static_assert(sizeof(NodeParams) == 96, "NodeParams must stay 96 bytes");
+
+// Six 16-byte read-only loads, unpacked field by field so the record stays in registers.
+__device__ __forceinline__ NodeParams load_node(const NodeParams* p) {
+    const int4* s = reinterpret_cast<const int4*>(p);
+    const int4 q0 = __ldg(s), q1 = __ldg(s + 1), q2 = __ldg(s + 2), q3 = __ldg(s + 3), q4 = __ldg(s + 4), q5 = __ldg(s + 5);
+    NodeParams n;
+    n.inv_max = q0.x; n.order_max = q0.y; n.demand_max = q0.z; n.delay = q0.w;
+    n.pipe_off = q1.x; n.init_inv = q1.y; n.parent = q1.z; n.child_slot = q1.w;
+    n.nchild = q2.x; n.bt_off = q2.y; n.retailer_idx = q2.z; n.pad0 = 0;
+    n.p = __hiloint2double(q3.y, q3.x); n.c = __hiloint2double(q3.w, q3.z);
+    n.h = __hiloint2double(q4.y, q4.x); n.bc = __hiloint2double(q4.w, q4.z);
+    n.target = __hiloint2double(q5.y, q5.x); n.pad1 = 0.0;
+    return n;
+}
+
+// Batch-uniform arguments (kernel parameter space → constant bank, broadcast reads).
+struct StepArgs {
+    // sizes
+    int64_t N;
+    int32_t m, T, P, D, O, L, NB, R;
+    int32_t t;                 // period being simulated (0-based)
+    int32_t maxc;              // max children per node (divergent)
+    // mode flags (uniform branches)
+    int32_t multi;             // MAIM kinds
+    int32_t std_state, std_actions, cap_backlog;
+    int32_t independent, share_network;
+    int32_t td, pd, pa;
+    int32_t write_hd;          // demand-history slots are written into obs (false in the MAIM (F,T,F) quirk)
+    int32_t noisy;             // consume the delay mask this episode
+    int32_t has_carry;         // carry field allocated
+    int32_t need_hd, need_ho;  // history state present
+    int32_t wd_mult1, wd_mult;   // watchdog multipliers: LOOP1(A) and the other three
+    double a, b, bma;          // bma = b - a
+    // tables
+    const NodeParams* __restrict__ nodes;   // [m]
+    const int8_t* __restrict__ children;    // [m][IMX_MAX_CHILDREN] lanes of the children (-1 = none)
+    // state (SoA, int32)
+    int32_t* __restrict__ inv;
+    int32_t* __restrict__ backlog;
+    int32_t* __restrict__ order_u;
+    int32_t* __restrict__ pipe;
+    int32_t* __restrict__ hist_d;
+    int32_t* __restrict__ hist_o;
+    int32_t* __restrict__ carry;
+    int32_t* __restrict__ bt;
+    int32_t* __restrict__ err;
+    const int32_t* __restrict__ demand_T;   // [T][R][N]
+    const uint8_t* __restrict__ mask_T;     // [T][N][m]
+    // I/O
+    const double* __restrict__ actions;     // [N][m]
+    double* __restrict__ obs;               // [N][m][O]
+    double* __restrict__ reward;            // [N][m] or [N]
+    imx_info_out info;
+};
+
+// ------------------------------------------------------------------------------------
+// Exact float64 arithmetic.  The explicit _rn intrinsics are never contracted into FMAs, so the
+// result is the same sequence of IEEE-754 roundings numpy performs.
+// ------------------------------------------------------------------------------------
+// rescale(v, 0, vmax, a, b) = a + ((v - 0) * (b - a)) / (vmax - 0)      MAIM_env.py:497-507
+__device__ __forceinline__ double rescale(double v, double vmax, double a, double bma) {
+    return __dadd_rn(a, __ddiv_rn(__dmul_rn(v, bma), vmax));
+}
+// rev_scale(x, 0, vmax, a, b) = ((x - a) * (vmax - 0)) / (b - a) + 0    MAIM_env.py:509-519
+__device__ __forceinline__ double rev_scale(double x, double vmax, double a, double bma) {
+    return __ddiv_rn(__dmul_rn(__dsub_rn(x, a), vmax), bma);
+}
+// order clipping: MAIM kinds round then clip (MAIM_env.py:344-347), IM kinds clip then round
+// (IM_env.py:300-302); rint() is round-half-to-even like np.round.
+__device__ __forceinline__ int decode_order(double x, double om, bool std_actions, bool multi, double a, double bma) {
+    if (std_actions) x = rev_scale(x, om, a, bma);
+    if (multi) x = fmin(fmax(rint(x), 0.0), om);
+    else x = rint(fmin(fmax(x, 0.0), om));
+    return (int)x;
+}
+// profit = p*ship - c*order - h*|inv' - target| - bc*backlog'           MAIM_env.py:421-424
+__device__ __forceinline__ double profit_of(double p, double c, double h, double bc, double target,
+                                            int ship, int order, int inv_new, int backlog_new) {
+    double r = __dsub_rn(__dmul_rn(p, (double)ship), __dmul_rn(c, (double)order));
+    r = __dsub_rn(r, __dmul_rn(h, fabs(__dsub_rn((double)inv_new, target))));
+    return __dsub_rn(r, __dmul_rn(bc, (double)backlog_new));
+}
+
+// ------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), hand-rolled: counter-based, so a draw is a pure
+// function of (seed, global env, index, period, episode) and independent of the sharding.
+// ------------------------------------------------------------------------------------
+struct Philox4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ void philox_mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    const uint64_t p = (uint64_t)a * (uint64_t)b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+}
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(Philox4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        philox_mulhilo(0xD2511F53u, c.x, hi0, lo0);
+        philox_mulhilo(0xCD9E8D57u, c.z, hi1, lo1);
+        Philox4 n;
+        n.x = hi1 ^ c.y ^ k0;
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ k1;
+        n.w = lo0;
+        c = n;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+enum : uint32_t { PHILOX_TAG_DEMAND = 0u, PHILOX_TAG_DELAY = 1u };
+
+// counter = (env_lo, env_hi, tag<<28 | idx<<16 | t, episode_lo), key = (seed_lo, seed_hi ^ episode_hi)
+__host__ __device__ __forceinline__ Philox4 philox_draw(uint64_t seed, uint64_t env_global, uint32_t tag,
+                                                        uint32_t idx, uint32_t t, uint64_t episode) {
+    Philox4 c;
+    c.x = (uint32_t)env_global;
+    c.y = (uint32_t)(env_global >> 32);
+    c.z = (tag << 28) | ((idx & 0xFFFu) << 16) | (t & 0xFFFFu);
+    c.w = (uint32_t)episode;
+    return philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(episode >> 32));
+}
+
+// 53-bit uniform in [0, 1) from two 32-bit words
+__host__ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+    const uint64_t bits = ((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6);
+    return (double)bits * (1.0 / 9007199254740992.0);
+}
+
+// Demand generator description (uniform kernel argument).
+struct DemandGen {
+    int32_t dist;                 // imx_demand_dist
+    int32_t low, high;            // uniform integers in [low, high)
+    int32_t cdf_len;              // Poisson: entries in cdf[]
+    const double* __restrict__ cdf;   // Poisson CDF table, cdf[k] = P(X <= k); inversion: smallest k with u < cdf[k]
+    uint64_t seed;
+    uint64_t episode;
+    int64_t env_offset;
+};
+
+__device__ __forceinline__ int draw_demand(const DemandGen& g, int64_t n_local, int r, int t) {
+    const Philox4 v = philox_draw(g.seed, (uint64_t)(g.env_offset + n_local), PHILOX_TAG_DEMAND, (uint32_t)r,
+                                  (uint32_t)t, g.episode);
+    const double u = u53(v.x, v.y);
+    if (g.dist == IMX_DIST_UNIFORM) {
+        int k = g.low + (int)(u * (double)(g.high - g.low));
+        return k < g.high ? k : g.high - 1;
+    }
+    // Poisson by CDF inversion: binary search for the first entry above u
+    int lo = 0, hi = g.cdf_len - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (u < __ldg(g.cdf + mid)) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ bool draw_delay(uint64_t seed, int64_t env_global, int i, int t, uint64_t episode, double thr) {
+    const Philox4 v = philox_draw(seed, (uint64_t)env_global, PHILOX_TAG_DELAY, (uint32_t)i, (uint32_t)t, episode);
+    return u53(v.x, v.y) <= thr;
+}
+
+// ------------------------------------------------------------------------------------
+// TMA bulk copy shared -> global (SASS: UBLKCP).  One elected lane issues it for a whole warp's
+// contiguous observation tile, so the global write needs no per-lane store instructions.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// wait until the bulk engine has finished READING shared memory (the tile may then be overwritten)
+__device__ __forceinline__ void bulk_wait_read_all() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// streaming global accesses: state and I/O are touched once per launch
+__device__ __forceinline__ int ld_stream(const int32_t* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(int32_t* p, int v) { __stcs(p, v); }
+
+}  // namespace imx

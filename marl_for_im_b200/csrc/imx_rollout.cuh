@@ -1,0 +1,225 @@
+// imx_rollout.cuh — fused K-period base-stock rollout: a whole episode per environment in ONE
+// kernel, state in registers (the lead-time pipeline is a register shift register), demand from
+// the counter-based Philox stream or a replayed trace, the order-up-to policy evaluated in-lane.
+// Restates the loop of dfo_func (base_restock_policy.py:30-45) with base_stock_policy (:4-21) and
+// the env step (same arithmetic as imx_step.cuh) inlined; per-env traffic is the demand trace in
+// and the returns out (≈1 byte per agent-step), so this kernel is issue-bound, not HBM-bound.
+#pragma once
+
+#include "imx_step.cuh"
+
+namespace imx {
+
+constexpr int ROLLOUT_THREADS = 128;
+
+struct RolloutArgs {
+    const double* __restrict__ z;          // base-stock levels [m] or [N][m]
+    int32_t z_stride;                      // 0 or m
+    int32_t write_state;
+    const int32_t* __restrict__ demand;    // replayed [N][R][T] or nullptr → Philox
+    const double* __restrict__ pmf;        // [N][T] or nullptr
+    double* __restrict__ ret;              // [N] (IM kinds) / [N][m] (MAIM kinds)
+    double* __restrict__ step_reward;      // [T][N] / [T][N][m] or nullptr
+    double* __restrict__ dfo;              // [N] or nullptr
+    DemandGen gen;
+};
+
+template <int M_PAD, int DMAX, int MAXC, bool DIV>
+__global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_constant__ StepArgs A,
+                                                                  const __grid_constant__ RolloutArgs Rg) {
+    constexpr int EPW = 32 / M_PAD;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int i = lane % M_PAD;
+    const int sub = lane / M_PAD;
+    const int m = A.m, T = A.T;
+    const bool stage_ok = i < m;
+
+    const NodeParams np = load_node(A.nodes + (stage_ok ? i : 0));
+    int child_lane[MAXC];
+    if constexpr (DIV) {
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k)
+            child_lane[k] = (stage_ok && k < np.nchild) ? (int)A.children[i * IMX_MAX_CHILDREN + k] : -1;
+    }
+    const bool is_last = (i == m - 1);
+    const double om_d = (double)np.order_max;
+    const int full8 = T - (T % 8);
+    const double neg_inv_T = -1.0 / (double)T;        // "-1 / env.num_periods" (base_restock_policy.py:45)
+
+    const int64_t warps_in_grid = (int64_t)gridDim.x * (ROLLOUT_THREADS / 32);
+    const int64_t n_warp_tiles = (A.N + EPW - 1) / EPW;
+    for (int64_t wt = (int64_t)blockIdx.x * (ROLLOUT_THREADS / 32) + warp; wt < n_warp_tiles; wt += warps_in_grid) {
+        const int64_t n = wt * EPW + sub;
+        const bool ok = stage_ok && n < A.N;
+        const int64_t cell = n * m + i;
+
+        // reset state (MAIM_env.py:232-235): inv = init_inv, everything else 0
+        int inv = np.init_inv, backlog = 0, order_u = 0;
+        int pipe[DMAX];
+        int bt[MAXC];
+#pragma unroll
+        for (int k = 0; k < DMAX; ++k) pipe[k] = 0;
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) bt[k] = 0;
+        const double z = ok ? Rg.z[Rg.z_stride ? cell : (int64_t)i] : 0.0;
+        const int32_t* dem_row = (ok && Rg.demand && np.retailer_idx >= 0) ? Rg.demand + (n * A.R + np.retailer_idx) * T : nullptr;
+        double ret = 0.0;                 // "dfo_reward = 0; dfo_reward += r" (inv_management.py:223-231)
+        double acc8[8];                   // np.sum(prob * rewards) accumulators (numpy pairwise order)
+        double dfo_sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc8[j] = 0.0;
+        int err_code = 0;
+
+        for (int t = 0; t < T; ++t) {
+            // base_stock_policy: z - (inv + order_u - backlog), clipped to [0, order_max]  (base_restock_policy.py:12-20)
+            const double inv_ech = __dsub_rn(__dadd_rn((double)inv, (double)order_u), (double)backlog);
+            const double act = fmin(om_d, fmax(__dsub_rn(z, inv_ech), 0.0));
+            const int order = ok ? decode_order(act, om_d, A.std_actions != 0, A.multi != 0, A.a, A.bma) : 0;
+
+            int cust = 0;
+            if (ok && np.retailer_idx >= 0) cust = dem_row ? dem_row[t] : draw_demand(Rg.gen, n, np.retailer_idx, t);
+
+            int demand;
+            int od[MAXC];
+            if constexpr (DIV) {
+                int s = 0;
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) {
+                    od[k] = 0;
+                    if (k < A.maxc) {
+                        const int v = __shfl_sync(0xffffffffu, order, child_lane[k] < 0 ? 0 : child_lane[k], M_PAD);
+                        od[k] = child_lane[k] < 0 ? 0 : v;
+                        s += od[k];
+                    }
+                }
+                demand = (np.retailer_idx >= 0) ? min(cust, np.inv_max) : s;
+            } else {
+                const int down = __shfl_up_sync(0xffffffffu, order, 1, M_PAD);
+                demand = (i == 0) ? min(cust, np.inv_max) : down;
+            }
+
+            const int acq = (t >= np.delay) ? pipe[0] : 0;
+            const int ship = min(backlog + demand, inv + acq);
+            int incoming;
+            if constexpr (DIV) {
+                int st[MAXC];
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) st[k] = 0;
+                if (ok && np.nchild == 1) st[0] = ship;
+                if (ok && np.nchild > 1) {
+                    const int code = split_ship<MAXC>(np.nchild, ship, demand, backlog, np.demand_max, A.wd_mult1, A.wd_mult, od, bt, st);
+                    if (code != 0 && err_code == 0) err_code = code;
+                }
+                incoming = order;
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) {
+                    if (k < A.maxc) {
+                        const int v = __shfl_sync(0xffffffffu, st[k], np.parent < 0 ? 0 : np.parent, M_PAD);
+                        if (np.parent >= 0 && np.child_slot == k) incoming = v;
+                    }
+                }
+            } else {
+                const int up = __shfl_down_sync(0xffffffffu, ship, 1, M_PAD);
+                incoming = is_last ? order : up;
+            }
+
+            int backlog_new = backlog + demand - ship;
+            if (A.cap_backlog) backlog_new = min(backlog_new, np.demand_max);
+            order_u = min(max(order_u + order - acq, 0), np.inv_max);
+            inv = min(max(inv + acq - ship, 0), np.inv_max);
+            backlog = backlog_new;
+#pragma unroll
+            for (int k = 0; k < DMAX - 1; ++k) pipe[k] = pipe[k + 1];
+            pipe[DMAX - 1] = 0;
+#pragma unroll
+            for (int k = 0; k < DMAX; ++k)
+                if (k == np.delay - 1) pipe[k] = incoming;
+
+            const double profit = ok ? profit_of(np.p, np.c, np.h, np.bc, np.target, ship, order, inv, backlog) : 0.0;
+            double r;
+            if (A.multi) r = A.independent ? profit : __ddiv_rn(tile_seq_sum<M_PAD>(profit, m), (double)m);
+            else r = tile_np_sum<M_PAD>(profit, m);
+            ret = __dadd_rn(ret, r);
+            if (ok && Rg.step_reward) {
+                if (A.multi) Rg.step_reward[(int64_t)t * A.N * m + cell] = r;
+                else if (i == 0) Rg.step_reward[(int64_t)t * A.N + n] = r;
+            }
+            if (Rg.dfo && ok && i == 0) {
+                const double v = __dmul_rn(Rg.pmf[n * T + t], r);
+                if (T < 8) dfo_sum = __dadd_rn(dfo_sum, v);
+                else if (t < 8) acc8[t] = v;
+                else if (t < full8) acc8[t & 7] = __dadd_rn(acc8[t & 7], v);
+                else {
+                    if (t == full8)
+                        dfo_sum = __dadd_rn(__dadd_rn(__dadd_rn(acc8[0], acc8[1]), __dadd_rn(acc8[2], acc8[3])),
+                                            __dadd_rn(__dadd_rn(acc8[4], acc8[5]), __dadd_rn(acc8[6], acc8[7])));
+                    dfo_sum = __dadd_rn(dfo_sum, v);
+                }
+            }
+        }
+
+        if (ok) {
+            if (A.multi) Rg.ret[cell] = ret;
+            else if (i == 0) Rg.ret[n] = ret;
+            if (Rg.dfo && i == 0) {
+                if (T >= 8 && full8 == T)
+                    dfo_sum = __dadd_rn(__dadd_rn(__dadd_rn(acc8[0], acc8[1]), __dadd_rn(acc8[2], acc8[3])),
+                                        __dadd_rn(__dadd_rn(acc8[4], acc8[5]), __dadd_rn(acc8[6], acc8[7])));
+                Rg.dfo[n] = __dmul_rn(neg_inv_T, dfo_sum);
+            }
+            if (Rg.write_state) {
+                A.inv[cell] = inv;
+                A.backlog[cell] = backlog;
+                A.order_u[cell] = order_u;
+                int32_t* pp = A.pipe + n * A.L + np.pipe_off;
+#pragma unroll
+                for (int k = 0; k < DMAX; ++k)
+                    if (k < np.delay) pp[k] = pipe[k];
+                if constexpr (DIV) {
+                    if (np.bt_off >= 0) {
+#pragma unroll
+                        for (int k = 0; k < MAXC; ++k)
+                            if (k < np.nchild) A.bt[n * A.NB + np.bt_off + k] = bt[k];
+                    }
+                }
+            }
+            if constexpr (DIV) {
+                if (err_code != 0) A.err[n] = err_code;
+            }
+        }
+    }
+}
+
+// Episode statistics [n, Σ total, Σ total², then per agent (Σ, Σ²)] in a fixed, deterministic
+// order: one block, each thread strides over envs, then a shared-memory tree.  The per-env total
+// of a MAIM kind is the sum over agents in agent order.
+__global__ void __launch_bounds__(1024) return_stats_kernel(const double* __restrict__ ret, double* __restrict__ stats,
+                                                            int64_t N, int cols, int multi) {
+    __shared__ double red[1024];
+    const int nstat = multi ? 2 + 2 * cols : 2;
+    for (int q = 0; q < nstat; ++q) {
+        double acc = 0.0;
+        for (int64_t n = threadIdx.x; n < N; n += blockDim.x) {
+            double v;
+            if (q < 2) {
+                v = 0.0;
+                for (int c = 0; c < cols; ++c) v += ret[n * cols + c];
+            } else {
+                v = ret[n * cols + (q - 2) / 2];
+            }
+            acc += (q & 1) ? v * v : v;
+        }
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) stats[1 + q] = red[0];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) stats[0] = (double)N;
+}
+
+}  // namespace imx

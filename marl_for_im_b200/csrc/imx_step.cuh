@@ -1,0 +1,440 @@
+// imx_step.cuh — the single-period environment step kernel (serial and divergent networks).
+//
+// Mapping: lanes = stages.  A warp is cut into tiles of M_PAD lanes (M_PAD = m rounded up to a
+// power of two); one tile simulates one environment, lane i of the tile owns stage / node i.
+// The only cross-stage dependencies of a period are resolved with warp shuffles inside the tile:
+//   serial     demand_i = order_{i-1}   (shfl_up)     pipeline input_i = ship_{i+1}  (shfl_down)
+//   divergent  demand_i = sum of the children's orders (gather)   pipeline input_i = ship_to[parent -> i] (scatter)
+// Restates: MAIM_env.py:330-436 + :242-328, IM_env.py:231-374, MAIM_div_env.py:441-655 + :343-439,
+// IM_div_env.py:304-563 (see SURVEY.md appendix A for the state-machine form).
+//
+// Memory: state is int32 structure-of-arrays [N][m] per field (the tile's lanes read consecutive
+// words → every warp-level request is one contiguous 128-byte line), the ragged pipeline record
+// is [N][L].  Observations ([N][m][O] float64, 60 % of all traffic) are staged per warp in shared
+// memory and leave the SM as ONE TMA bulk copy per warp (cp.async.bulk shared→global).
+#pragma once
+
+#include "imx_device.cuh"
+
+namespace imx {
+
+constexpr int STEP_THREADS = 256;
+
+// np.sum order for the IM kinds' scalar reward (numpy pairwise_sum: sequential below 8 elements,
+// eight running accumulators from 8 to 128) — IM_env.py:372, IM_div_env.py:561.
+template <int M_PAD>
+__device__ __forceinline__ double tile_np_sum(double v, int m) {
+    if constexpr (M_PAD < 8) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < M_PAD; ++j) {
+            const double x = __shfl_sync(0xffffffffu, v, j, M_PAD);
+            if (j < m) s = __dadd_rn(s, x);
+        }
+        return s;
+    } else {
+        if (m < 8) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double x = __shfl_sync(0xffffffffu, v, j, M_PAD);
+                if (j < m) s = __dadd_rn(s, x);
+            }
+            return s;
+        }
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __shfl_sync(0xffffffffu, v, j, M_PAD);
+        const int full = m - (m % 8);
+#pragma unroll
+        for (int base = 8; base < M_PAD; base += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double x = __shfl_sync(0xffffffffu, v, base + j, M_PAD);
+                if (base + j < full) r[j] = __dadd_rn(r[j], x);
+            }
+        }
+        double s = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                             __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+#pragma unroll
+        for (int j = 8; j < M_PAD; ++j) {
+            const double x = __shfl_sync(0xffffffffu, v, j, M_PAD);
+            if (j >= full && j < m) s = __dadd_rn(s, x);
+        }
+        return s;
+    }
+}
+
+// MAIM shared reward: reward_sum starts at integer 0 and adds the profits in stage order
+// (MAIM_env.py:418-426), then / num_stages (:434).
+template <int M_PAD>
+__device__ __forceinline__ double tile_seq_sum(double v, int m) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < M_PAD; ++j) {
+        const double x = __shfl_sync(0xffffffffu, v, j, M_PAD);
+        if (j < m) s = __dadd_rn(s, x);
+    }
+    return s;
+}
+
+// One period of the divergent split for a node with > 1 child — MAIM_div_env.py:483-579 /
+// IM_div_env.py:403-502, pass for pass (whole round-robin passes: the shipped amount may go
+// negative inside a pass, the ledger may go negative; both are the reference's behaviour).
+// Returns the watchdog code (0 ok; 1..4 = the reference's "Infinite Loop k").
+template <int MAXC>
+__device__ __forceinline__ int split_ship(int nchild, int ship, int demand, int backlog, int demand_max, int mult1,
+                                          int mult, const int (&od)[MAXC], int (&bt)[MAXC], int (&st)[MAXC]) {
+    int amt = ship;
+    int code = 0;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) st[k] = 0;
+
+    auto loop1 = [&](int limit, int which) {
+        int cnt = 0;
+        while (true) {
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) sum += (k < nchild) ? bt[k] : 0;
+            if (!(sum > 0 && amt > 0)) break;
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) {
+                if (k < nchild && bt[k] > 0) { st[k] += 1; bt[k] -= 1; amt -= 1; }
+            }
+            if (++cnt > limit) { code = which; break; }
+        }
+    };
+
+    if (ship >= demand) {
+        if (backlog > 0) {
+            loop1(demand_max * mult1, 1);
+            if (code == 0 && amt > 0 && demand > 0) {
+                int out[MAXC];
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) out[k] = (k < nchild) ? od[k] : 0;
+                int cnt = 0;
+                while (true) {
+                    int sum = 0;
+#pragma unroll
+                    for (int k = 0; k < MAXC; ++k) sum += out[k];
+                    if (!(amt > 0 && sum > 0)) break;
+#pragma unroll
+                    for (int k = 0; k < MAXC; ++k) {
+                        if (out[k] > 0) { st[k] += 1; out[k] -= 1; amt -= 1; }
+                    }
+                    if (++cnt > demand_max * mult) { code = 2; break; }
+                }
+                if (code == 0) {
+#pragma unroll
+                    for (int k = 0; k < MAXC; ++k) bt[k] += out[k];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) st[k] += (k < nchild) ? od[k] : 0;
+        }
+    } else {
+        if (backlog > 0) {
+            loop1(demand_max * mult, 3);
+        } else {
+            int cnt = 0;
+            while (amt > 0) {
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) {
+                    if (k < nchild && st[k] < od[k] + bt[k]) { st[k] += 1; amt -= 1; }
+                }
+                if (++cnt > demand_max * mult) { code = 4; break; }
+            }
+        }
+        if (code == 0) {
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) {
+                if (k < nchild) bt[k] += od[k] - st[k];
+            }
+        }
+    }
+    return code;
+}
+
+// Writes one agent's observation vector (O doubles) — the field order and per-field maxima of
+// SURVEY.md table A.5.  `row` points into the warp's shared-memory staging tile.
+template <int DMAX, int PMAX>
+__device__ __forceinline__ void write_obs_row(double* row, const StepArgs& A, const NodeParams& np, int node_idx,
+                                              int inv, int backlog, int order_u, const int (&pipe)[DMAX],
+                                              const int (&hd)[PMAX], const int (&ho)[PMAX], bool div) {
+    const double a = A.a, bma = A.bma;
+    const double inv_max = (double)np.inv_max, order_max = (double)np.order_max;
+    const double dem_max = (double)np.demand_max;
+    const double ou_max = A.multi ? order_max : inv_max;   // MAIM_env.py:300 vs IM_env.py:265
+    if (A.std_state) {
+        row[0] = rescale((double)inv, inv_max, a, bma);
+        row[1] = rescale((double)backlog, dem_max, a, bma);
+        row[2] = rescale((double)order_u, ou_max, a, bma);
+    } else {
+        row[0] = (double)inv;
+        row[1] = (double)backlog;
+        row[2] = (double)order_u;
+    }
+    if (A.multi && !A.std_state) {
+        // MAIM_env.py:319-324 (quirk 13): raw pipeline at [3:3+D] whatever the history offsets, rest stays 0
+        for (int k = 3; k < A.O; ++k) row[k] = 0.0;
+        if (A.td) {
+#pragma unroll
+            for (int k = 0; k < DMAX; ++k)
+                if (k < A.D) row[3 + k] = (double)pipe[k];
+        }
+        return;
+    }
+    int k0 = 3;
+    if (A.pd) {
+#pragma unroll
+        for (int j = 0; j < PMAX; ++j)
+            if (j < A.P) row[k0 + j] = A.write_hd ? rescale((double)hd[j], dem_max, a, bma) : 0.0;   // quirk 2
+        k0 += A.P;
+    }
+    if (A.pa) {
+#pragma unroll
+        for (int j = 0; j < PMAX; ++j)
+            if (j < A.P) row[k0 + j] = rescale((double)ho[j], order_max, a, bma);
+        k0 += A.P;
+    }
+    if (A.td) {
+#pragma unroll
+        for (int k = 0; k < DMAX; ++k) {
+            if (k < A.D) {
+                double v;
+                if (!A.std_state) v = (double)pipe[k];                                    // IM kinds, raw
+                else if (div && A.multi) v = rescale((double)min(pipe[k], 2 * np.inv_max), 2.0 * inv_max, a, bma);   // MAIM_div_env.py:408-411
+                else v = rescale((double)pipe[k], inv_max, a, bma);
+                row[k0 + k] = v;
+            }
+        }
+        k0 += A.D;
+    }
+    if (A.share_network) row[k0] = rescale((double)node_idx, (double)A.m, a, bma);       // MAIM_div_env.py:434-435
+}
+
+// Flushes a warp's staged observation tile (`doubles` contiguous float64 values) to global memory.
+__device__ __forceinline__ void flush_obs_tile(double* gdst, const double* stile, int doubles, int lane) {
+    const uint32_t bytes = (uint32_t)doubles * 8u;
+    const bool bulk_ok = ((bytes & 15u) == 0u) && ((reinterpret_cast<uintptr_t>(gdst) & 15u) == 0u);
+    __syncwarp();
+    if (bulk_ok) {
+        if (lane == 0) {
+            fence_proxy_async_smem();
+            bulk_store_s2g(gdst, stile, bytes);
+        }
+    } else {
+        for (int k = lane; k < doubles; k += 32) gdst[k] = stile[k];
+    }
+}
+
+template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV>
+__global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constant__ StepArgs A) {
+    extern __shared__ __align__(16) double smem_obs[];
+    constexpr int EPW = 32 / M_PAD;                 // envs per warp
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int i = lane % M_PAD;                     // stage / node owned by this lane
+    const int sub = lane / M_PAD;                   // env slot inside the warp
+    const bool stage_ok = i < A.m;
+    const int m = A.m, O = A.O;
+
+    const NodeParams np = load_node(A.nodes + (stage_ok ? i : 0));
+    int child_lane[MAXC];
+    if constexpr (DIV) {
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k)
+            child_lane[k] = (stage_ok && k < np.nchild) ? (int)A.children[i * IMX_MAX_CHILDREN + k] : -1;
+    }
+    const bool is_last = (i == m - 1);
+    const double om_d = (double)np.order_max;
+
+    const int tile_doubles = (EPW * m * O + 1) & ~1;             // keep every warp's tile 16-byte aligned
+    double* wtile = smem_obs + (size_t)warp * tile_doubles;
+    bool tile_in_flight = false;
+
+    const int64_t warps_in_grid = (int64_t)gridDim.x * (STEP_THREADS / 32);
+    const int64_t n_warp_tiles = (A.N + EPW - 1) / EPW;
+    for (int64_t wt = (int64_t)blockIdx.x * (STEP_THREADS / 32) + warp; wt < n_warp_tiles; wt += warps_in_grid) {
+        const int64_t n = wt * EPW + sub;
+        const bool ok = stage_ok && n < A.N;
+        const int64_t cell = n * m + i;
+
+        // ---- loads (all issued before the first use) --------------------------------------
+        double act = 0.0;
+        int inv = 0, backlog = 0, order_u = 0, carry = 0, cust = 0;
+        int pipe[DMAX], hd[PMAX], ho[PMAX];
+        int bt[MAXC];
+        bool delayed = false;
+#pragma unroll
+        for (int k = 0; k < DMAX; ++k) pipe[k] = 0;
+#pragma unroll
+        for (int j = 0; j < PMAX; ++j) { hd[j] = 0; ho[j] = 0; }
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) bt[k] = 0;
+        if (ok) {
+            act = A.actions[cell];
+            inv = A.inv[cell];
+            backlog = A.backlog[cell];
+            order_u = A.order_u[cell];
+            const int32_t* pp = A.pipe + n * A.L + np.pipe_off;
+#pragma unroll
+            for (int k = 0; k < DMAX; ++k)
+                if (k < np.delay) pipe[k] = pp[k];
+            if (A.need_hd) {
+#pragma unroll
+                for (int j = 0; j < PMAX; ++j)
+                    if (j < A.P) hd[j] = A.hist_d[cell * A.P + j];
+            }
+            if (A.need_ho) {
+#pragma unroll
+                for (int j = 0; j < PMAX; ++j)
+                    if (j < A.P) ho[j] = A.hist_o[cell * A.P + j];
+            }
+            if (np.retailer_idx >= 0) cust = A.demand_T[((int64_t)A.t * A.R + np.retailer_idx) * A.N + n];
+            if (A.has_carry) carry = A.carry[cell];
+            if (A.noisy) delayed = A.mask_T[((int64_t)A.t * A.N + n) * m + i] != 0;
+            if constexpr (DIV) {
+                if (np.bt_off >= 0) {
+#pragma unroll
+                    for (int k = 0; k < MAXC; ++k)
+                        if (k < np.nchild) bt[k] = A.bt[n * A.NB + np.bt_off + k];
+                }
+            }
+        }
+
+        // ---- order clipping ---------------------------------------------------------------
+        const int order = ok ? decode_order(act, om_d, A.std_actions != 0, A.multi != 0, A.a, A.bma) : 0;
+
+        // ---- demand propagation -----------------------------------------------------------
+        int demand;
+        int od[MAXC];
+        if constexpr (DIV) {
+            int s = 0;
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) {
+                od[k] = 0;
+                if (k < A.maxc) {
+                    const int v = __shfl_sync(0xffffffffu, order, child_lane[k] < 0 ? 0 : child_lane[k], M_PAD);
+                    od[k] = child_lane[k] < 0 ? 0 : v;
+                    s += od[k];
+                }
+            }
+            demand = (np.retailer_idx >= 0) ? min(cust, np.inv_max) : s;
+        } else {
+            const int down = __shfl_up_sync(0xffffffffu, order, 1, M_PAD);
+            demand = (i == 0) ? min(cust, np.inv_max) : down;
+        }
+
+        // ---- acquisition: head of the lead-time pipeline (+ replayed noisy delay) ----------
+        int acq = carry;
+        int carry_new = 0;
+        if (A.t >= np.delay) {
+            acq += pipe[0];
+            if (delayed && A.t < A.T - 1) { carry_new = acq; acq = 0; }
+        }
+
+        // ---- shipment and state update ----------------------------------------------------
+        const int ship = min(backlog + demand, inv + acq);
+        int incoming;
+        int err_code = 0;
+        if constexpr (DIV) {
+            int st[MAXC];
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) st[k] = 0;
+            if (ok && np.nchild == 1) st[0] = ship;
+            if (ok && np.nchild > 1)
+                err_code = split_ship<MAXC>(np.nchild, ship, demand, backlog, np.demand_max, A.wd_mult1, A.wd_mult, od, bt, st);
+            incoming = order;                                   // root: its own production order
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) {
+                if (k < A.maxc) {
+                    const int v = __shfl_sync(0xffffffffu, st[k], np.parent < 0 ? 0 : np.parent, M_PAD);
+                    if (np.parent >= 0 && np.child_slot == k) incoming = v;
+                }
+            }
+        } else {
+            const int up = __shfl_down_sync(0xffffffffu, ship, 1, M_PAD);
+            incoming = is_last ? order : up;
+        }
+
+        int backlog_new = backlog + demand - ship;
+        if (A.cap_backlog) backlog_new = min(backlog_new, np.demand_max);
+        const int order_u_new = min(max(order_u + order - acq, 0), np.inv_max);
+        const int inv_new = min(max(inv + acq - ship, 0), np.inv_max);
+#pragma unroll
+        for (int k = 0; k < DMAX - 1; ++k) pipe[k] = pipe[k + 1];
+        pipe[DMAX - 1] = 0;
+#pragma unroll
+        for (int k = 0; k < DMAX; ++k)
+            if (k == np.delay - 1) pipe[k] = incoming;
+#pragma unroll
+        for (int j = PMAX - 1; j > 0; --j) { hd[j] = hd[j - 1]; ho[j] = ho[j - 1]; }
+        hd[0] = demand;
+        ho[0] = order;
+
+        // ---- reward -----------------------------------------------------------------------
+        const double profit = ok ? profit_of(np.p, np.c, np.h, np.bc, np.target, ship, order, inv_new, backlog_new) : 0.0;
+        double reward_out;
+        if (A.multi) {
+            if (A.independent) reward_out = profit;
+            else reward_out = __ddiv_rn(tile_seq_sum<M_PAD>(profit, m), (double)m);
+        } else {
+            reward_out = tile_np_sum<M_PAD>(profit, m);
+        }
+
+        // ---- stores -----------------------------------------------------------------------
+        if (tile_in_flight) {                       // the previous iteration's bulk copy must have read the tile
+            if (lane == 0) bulk_wait_read_all();
+            __syncwarp();
+            tile_in_flight = false;
+        }
+        if (ok) {
+            A.inv[cell] = inv_new;
+            A.backlog[cell] = backlog_new;
+            A.order_u[cell] = order_u_new;
+            int32_t* pp = A.pipe + n * A.L + np.pipe_off;
+#pragma unroll
+            for (int k = 0; k < DMAX; ++k)
+                if (k < np.delay) pp[k] = pipe[k];
+            if (A.need_hd) {
+#pragma unroll
+                for (int j = 0; j < PMAX; ++j)
+                    if (j < A.P) A.hist_d[cell * A.P + j] = hd[j];
+            }
+            if (A.need_ho) {
+#pragma unroll
+                for (int j = 0; j < PMAX; ++j)
+                    if (j < A.P) A.hist_o[cell * A.P + j] = ho[j];
+            }
+            if (A.has_carry) A.carry[cell] = carry_new;
+            if constexpr (DIV) {
+                if (np.bt_off >= 0) {
+#pragma unroll
+                    for (int k = 0; k < MAXC; ++k)
+                        if (k < np.nchild) A.bt[n * A.NB + np.bt_off + k] = bt[k];
+                }
+                if (err_code != 0) A.err[n] = err_code;
+            }
+            if (A.multi) A.reward[cell] = reward_out;
+            else if (i == 0) A.reward[n] = reward_out;
+            if (A.info.demand_dev) A.info.demand_dev[cell] = demand;
+            if (A.info.ship_dev) A.info.ship_dev[cell] = ship;
+            if (A.info.acquisition_dev) A.info.acquisition_dev[cell] = acq;
+            if (A.info.order_dev) A.info.order_dev[cell] = order;
+            if (A.info.profit_dev) A.info.profit_dev[cell] = profit;
+            if (A.obs) write_obs_row<DMAX, PMAX>(wtile + (size_t)(sub * m + i) * O, A, np, i, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
+        }
+        if (A.obs) {
+            const int64_t first = wt * EPW;
+            const int envs_here = (int)min((int64_t)EPW, A.N - first);
+            flush_obs_tile(A.obs + first * m * O, wtile, envs_here * m * O, lane);
+            tile_in_flight = true;
+        }
+    }
+    // shared memory must stay valid until the bulk engine has read it
+    if (tile_in_flight && lane == 0) bulk_wait_read_all();
+}
+
+}  // namespace imx

@@ -1,0 +1,86 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/imx_b200.h declares,
+the ctypes struct mirror matches, and the product refuses to run without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from harness import ROOT
+from marl_for_im_b200 import _lib
+
+HEADER = os.path.join(ROOT, "include", "imx_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(imx_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "run python __graft_entry__.py first"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in imx_b200.h but not exported"
+    assert set(names) == set(_lib.SYMBOLS), "ctypes binding table and header disagree"
+
+
+def test_struct_mirror_and_version():
+    lib = _lib.load()
+    assert lib.imx_config_size() == ctypes.sizeof(_lib.ImxConfig)
+    assert lib.imx_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from marl_for_im_b200 import presets
+    from marl_for_im_b200.envs import MultiAgentInvManagement
+    with pytest.raises(_lib.ImxError):
+        MultiAgentInvManagement(presets.serial4())
+    # the raw ABI refuses too
+    c = _lib.ImxConfig()
+    c.kind, c.num_nodes, c.num_periods, c.prev_length, c.num_envs = 1, 2, 5, 1, 4
+    c.a, c.b = -1.0, 1.0
+    for i in range(2):
+        c.inv_max[i], c.order_max[i], c.delay[i] = 10, 10, 1
+    c.price[0], c.price[1], c.price[2] = 3, 2, 1
+    h = ctypes.c_void_p()
+    rc = _lib.load().imx_create(ctypes.byref(c), ctypes.byref(h))
+    assert rc < 0 and b"no CUDA device" in _lib.load().imx_last_error()
+
+
+def test_config_validation_messages():
+    lib = _lib.load()
+    c = _lib.ImxConfig()
+    c.kind, c.num_nodes, c.num_periods, c.prev_length, c.num_envs = 1, 2, 5, 1, 4
+    c.a, c.b = -1.0, 1.0
+    for i in range(2):
+        c.inv_max[i], c.order_max[i], c.delay[i] = 10, 10, 0          # delay 0 is rejected
+    c.price[0], c.price[1], c.price[2] = 3, 2, 1
+    h = ctypes.c_void_p()
+    assert lib.imx_create(ctypes.byref(c), ctypes.byref(h)) < 0
+    assert b"delay" in lib.imx_last_error()
+    c.delay[0] = c.delay[1] = 1
+    c.time_dependency, c.prev_actions, c.prev_demand = 0, 1, 0           # quirk 3
+    assert lib.imx_create(ctypes.byref(c), ctypes.byref(h)) == -5
+    assert b"Not Implemented" in lib.imx_last_error()
+
+
+def test_host_helpers():
+    import numpy as np
+    from marl_for_im_b200 import topology
+    from marl_for_im_b200.spaces import Box
+    conn = {0: [1], 1: [2, 3], 2: [4, 5], 3: [], 4: [], 5: []}
+    topology.check_connections(conn)
+    net = topology.create_network(conn)
+    assert topology.get_retailers(net) == [3, 4, 5]
+    assert [topology.get_stage(i, net) for i in range(6)] == [0, 1, 2, 2, 3, 3]
+    with pytest.raises(Exception):
+        topology.check_connections({0: [1], 1: [0]})
+    b = Box(low=np.ones(3) * -1, high=np.ones(3), dtype=np.float64, shape=(np.int8(3),))
+    assert b.shape == (3,) and isinstance(b.shape[0], int) and b.contains(np.zeros(3))

@@ -1,0 +1,171 @@
+"""CUDA path vs the oracle / the reference-generated golden fixtures — serial chains.
+Every call goes through the C ABI (ctypes → libimx_b200.so); bit-exact on all fields."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+from harness import golden_names, load_golden, random_case, run_oracle, make_delay_mask
+from marl_for_im_b200 import presets
+
+pytestmark = pytest.mark.gpu
+
+
+def run_cuda(kind, cfg, demand, actions, delay_mask=None, n_copies=1):
+    """Runs one episode on the GPU in batched mode (the same trace replicated ``n_copies`` times)
+    and returns the harness dict for env 0 plus the raw batched tensors."""
+    from marl_for_im_b200.envs import ENV_CLASSES
+    from harness import copy_config
+    c = copy_config(cfg)
+    c.update(num_envs=n_copies, device="cuda:0", return_info=True)
+    env = ENV_CLASSES[kind](c)
+    m, T = env.num_nodes, env.num_periods
+    multi = kind.startswith("MAIM")
+    dm = None
+    if delay_mask is not None:
+        dm = np.broadcast_to(np.asarray(delay_mask)[None], (n_copies,) + np.asarray(delay_mask).shape)
+    d = np.asarray(demand)
+    d = np.broadcast_to(d[None], (n_copies,) + d.shape)
+    o = env.reset(customer_demand=d, delay_mask=dm)
+
+    def pack(o):
+        return (torch.stack([o[n] for n in env.agent_names], dim=1) if multi else o).cpu().numpy()
+
+    obs = [pack(o)]
+    out = {k: np.zeros((T, n_copies, m)) for k in ("reward", "demand", "ship", "acq", "order", "profit")}
+    st = {k: [env.state_dict()[k].cpu().numpy().astype(np.int64)] for k in ("inv", "backlog", "order_u")}
+    for t in range(T):
+        a = torch.as_tensor(np.broadcast_to(actions[t][None], (n_copies, m)).copy(), device="cuda:0")
+        if multi:
+            a = {n: a[:, i] for i, n in enumerate(env.agent_names)}
+        o, r, done, info = env.step(a)
+        obs.append(pack(o))
+        if multi:
+            out["reward"][t] = torch.stack([r[n] for n in env.agent_names], dim=1).cpu().numpy()
+            for i, n in enumerate(env.agent_names):
+                out["demand"][t, :, i] = info[n]["demand"].cpu().numpy()
+                out["ship"][t, :, i] = info[n]["ship"].cpu().numpy()
+                out["acq"][t, :, i] = info[n]["acquisition"].cpu().numpy()
+                out["order"][t, :, i] = info[n]["actual order"].cpu().numpy()
+                out["profit"][t, :, i] = info[n]["profit"].cpu().numpy()
+            assert done["__all__"] == (t == T - 1)
+        else:
+            out["reward"][t, :, 0] = r.cpu().numpy()
+            out["demand"][t] = info["demand"].cpu().numpy()
+            out["ship"][t] = info["ship"].cpu().numpy()
+            out["acq"][t] = info["acquisition"].cpu().numpy()
+            out["order"][t] = info["actual order"].cpu().numpy()
+            out["profit"][t] = info["profit"].cpu().numpy()
+            assert done == (t == T - 1)
+        for k in st:
+            st[k].append(env.state_dict()[k].cpu().numpy().astype(np.int64))
+    assert int(env.error_flags.abs().sum()) == 0
+    res = {k: v[:, 0] for k, v in out.items()}
+    res["obs"] = np.stack(obs)[:, 0]
+    for k in st:
+        res[k] = np.stack(st[k])[:, 0]
+    # every replica must agree with env 0
+    full_obs = np.stack(obs)
+    assert np.array_equal(full_obs, np.broadcast_to(full_obs[:, :1], full_obs.shape))
+    return res
+
+
+def assert_same(a, b, what=""):
+    for k in ("inv", "backlog", "order_u", "demand", "ship", "acq", "order", "profit", "reward", "obs"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=f"{what}: {k}")
+
+
+SERIAL_GOLDEN = [n for n in golden_names() if not ("div" in n)]
+
+
+@pytest.mark.parametrize("name", SERIAL_GOLDEN)
+def test_cuda_matches_golden_serial(name):
+    g = load_golden(name)
+    got = run_cuda(g["kind"], g["config"], g["demand_trace"], g["actions"], g["delay_mask"], n_copies=3)
+    assert_same(g["ref"], got, name)
+
+
+MODES = list(itertools.product([False, True], repeat=3))
+
+
+@pytest.mark.parametrize("kind,preset", [("MAIM", "serial4"), ("IM", "serial4"), ("MAIM", "serial8"), ("IM", "serial8"),
+                                         ("MAIM", "serial2")])
+def test_cuda_matches_oracle_all_modes(kind, preset):
+    rng = np.random.default_rng(99)
+    for td, pd, pa in MODES:
+        if kind == "MAIM" and (not td) and pa and (not pd):
+            continue
+        for P, mu, indep in [(1, 5, False), (3, 15, True)]:
+            cfg = presets.PRESETS[preset](time_dependency=td, prev_demand=pd, prev_actions=pa, prev_length=P, independent=indep)
+            m = cfg["num_stages"]
+            cfg["inv_max"] = np.array([30, 25, 40, 35, 30, 45, 20, 30][:m], dtype=float)
+            cfg["inv_target"] = np.array([0, 3, 5.5, 1, 0, 2, 4, 0][:m], dtype=float)
+            demand, actions = random_case(kind, cfg, rng, mu=mu)
+            assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=5),
+                        f"{kind}/{preset}/{(td, pd, pa)}/P{P}")
+
+
+@pytest.mark.parametrize("kind", ["MAIM", "IM"])
+def test_cuda_non_standardised_and_noisy(kind):
+    rng = np.random.default_rng(5)
+    for td, pd, pa in MODES:
+        if kind == "MAIM" and (not td) and pa and (not pd):
+            continue
+        cfg = presets.serial4(time_dependency=td, prev_demand=pd, prev_actions=pa, prev_length=2,
+                              standardise_state=False, standardise_actions=False)
+        demand, actions = random_case(kind, cfg, rng, mu=12)
+        assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=2), "raw")
+    cfg = presets.serial8()
+    for _ in range(3):
+        demand, actions = random_case(kind, cfg, rng, mu=6, action_mode="near_eq")
+        mask = make_delay_mask(kind, cfg["delay"], 30, 0.3, rng)
+        assert_same(run_oracle(kind, cfg, demand, actions, mask), run_cuda(kind, cfg, demand, actions, mask, n_copies=9), "noisy")
+
+
+def test_cuda_wide_chain_and_tail_sizes():
+    """m not a power of two, m up to 32 (one warp per env), N not a multiple of the warp tile."""
+    rng = np.random.default_rng(17)
+    for m in (3, 5, 11, 16, 23, 32):
+        cfg = {
+            "num_stages": m, "num_periods": 12, "init_inv": np.ones(m) * 8, "inv_target": np.ones(m) * 2,
+            "inv_max": rng.integers(15, 40, m).astype(float), "price": np.arange(m + 1, 0, -1).astype(float),
+            "stock_cost": rng.uniform(0.1, 0.5, m), "backlog_cost": rng.uniform(0.3, 0.9, m),
+            "delay": rng.integers(1, 6, m), "time_dependency": True, "prev_demand": True, "prev_actions": True,
+            "prev_length": 2, "independent": False,
+        }
+        for kind in ("MAIM", "IM"):
+            demand = rng.poisson(6, 12)
+            actions = rng.uniform(-1.1, 1.1, (12, m))
+            assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=7), f"m={m}")
+
+
+def test_cuda_batch_of_distinct_envs():
+    """4096 envs with distinct traces, compared env by env on a sample and through shard invariance."""
+    from marl_for_im_b200.envs import MultiAgentInvManagement
+    cfg = presets.serial4()
+    N, T, m = 4096 + 3, 30, 4
+    rng = np.random.default_rng(420)
+    demand = rng.poisson(5, size=(N, T)).astype(np.int32)
+    actions = np.random.default_rng(0).uniform(-1, 1, size=(T, N, m))
+    env = MultiAgentInvManagement(dict(cfg, num_envs=N))
+    o = env.reset(customer_demand=demand)
+    obs, rew = [], []
+    a_dev = torch.as_tensor(actions, device="cuda:0")
+    for t in range(T):
+        o, r, done, _ = env.step(a_dev[t])
+        obs.append(torch.stack([o[n] for n in env.agent_names], dim=1).cpu().numpy())
+        rew.append(torch.stack([r[n] for n in env.agent_names], dim=1).cpu().numpy())
+    obs, rew = np.stack(obs), np.stack(rew)
+    for n in list(range(0, N, 97)) + [N - 1]:
+        want = run_oracle("MAIM", cfg, demand[n], actions[:, n])
+        np.testing.assert_array_equal(want["obs"][1:], obs[:, n])
+        np.testing.assert_array_equal(want["reward"], rew[:, n])
+    # shard invariance: the same envs split over two handles give the same bytes
+    half = N // 2
+    for lo, hi in ((0, half), (half, N)):
+        e2 = MultiAgentInvManagement(dict(cfg, num_envs=hi - lo, env_offset=lo))
+        e2.reset(customer_demand=demand[lo:hi])
+        for t in range(T):
+            o2, r2, _, _ = e2.step(a_dev[t, lo:hi])
+        np.testing.assert_array_equal(torch.stack([o2[n] for n in e2.agent_names], dim=1).cpu().numpy(), obs[-1, lo:hi])
