@@ -75,6 +75,8 @@ struct imx_env {
     uint8_t* d_mask_T = nullptr;
     double* d_cdf = nullptr;
     int cdf_len = 0;
+    double* d_tab = nullptr;             // [m][4][TL] rescale tables
+    int TL = 0;
     // host-call staging (allocated on first use)
     cudaStream_t hstream = nullptr;
     double *d_act_h = nullptr, *d_obs_h = nullptr, *d_rew_h = nullptr;
@@ -266,6 +268,14 @@ static void fill_args(const imx_env* e, StepArgs& A) {
     A.wd_mult1 = e->multi ? 2 : 4;
     A.wd_mult = e->multi ? 1 : 2;
     A.a = c.a; A.b = c.b; A.bma = c.b - c.a;
+    {
+        int ex = 0;
+        const double fr = std::frexp(A.bma, &ex);          // power of two <=> mantissa exactly 0.5
+        A.inv_bma = (fr == 0.5 && ex > -1000 && ex < 1000) ? 1.0 / A.bma : 0.0;
+        A.inv_m = ((e->m & (e->m - 1)) == 0) ? 1.0 / (double)e->m : 0.0;
+    }
+    A.TL = e->TL;
+    A.tab = e->d_tab;
     A.nodes = e->d_nodes;
     A.children = e->d_children;
     A.inv = (int32_t*)e->field_ptr[IMX_F_INV];
@@ -279,6 +289,37 @@ static void fill_args(const imx_env* e, StepArgs& A) {
     A.err = e->d_err;
     A.demand_T = e->d_demand_T;
     A.mask_T = e->d_mask_T;
+}
+
+// Exact rescale tables: tab[i][k][v] = a + (v*(b-a))/max_k(i), evaluated with the same three IEEE
+// double operations as MAIM_env.py:505 (this translation unit is compiled with -ffp-contract=off
+// semantics: product, quotient and sum are separate roundings).  Row k: 0 scale inv_max, 1 order_max,
+// 2 demand_max, 3 MAIM_div pipeline min(v, 2*inv_max)/(2*inv_max).
+static std::vector<double> build_tables(const imx_env* e, int* TL_out) {
+    const imx_config& c = e->cfg;
+    int maxv = 1;
+    for (int i = 0; i < e->m; ++i) {
+        maxv = c.inv_max[i] > maxv ? c.inv_max[i] : maxv;
+        maxv = c.order_max[i] > maxv ? c.order_max[i] : maxv;
+        maxv = e->demand_max[i] > maxv ? e->demand_max[i] : maxv;
+    }
+    const int64_t TL = 2 * (int64_t)maxv + IMX_MAX_CHILDREN + 8 + 1;   // covers every reachable value
+    if (TL * 4 * e->m * (int64_t)sizeof(double) > (int64_t)8 << 20) { *TL_out = 0; return {}; }
+    std::vector<double> tab((size_t)e->m * 4 * TL);
+    const volatile double a = c.a, bma = c.b - c.a;
+    for (int i = 0; i < e->m; ++i) {
+        const double mx[4] = {(double)c.inv_max[i], (double)c.order_max[i], (double)e->demand_max[i], 2.0 * (double)c.inv_max[i]};
+        for (int k = 0; k < 4; ++k)
+            for (int64_t v = 0; v < TL; ++v) {
+                double x = (double)v;
+                if (k == 3 && v > 2 * (int64_t)c.inv_max[i]) x = 2.0 * (double)c.inv_max[i];
+                volatile double prod = x * bma;
+                volatile double quot = prod / mx[k];
+                tab[((size_t)i * 4 + k) * TL + v] = a + quot;
+            }
+    }
+    *TL_out = (int)TL;
+    return tab;
 }
 
 static std::vector<double> poisson_cdf(double mu) {
@@ -380,6 +421,13 @@ extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
         IMX_CREATE_CUDA(cudaMalloc(&e->d_cdf, cdf.size() * sizeof(double)));
         IMX_CREATE_CUDA(cudaMemcpy(e->d_cdf, cdf.data(), cdf.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
+    {
+        std::vector<double> tab = build_tables(e, &e->TL);
+        if (e->TL > 0) {
+            IMX_CREATE_CUDA(cudaMalloc(&e->d_tab, tab.size() * sizeof(double)));
+            IMX_CREATE_CUDA(cudaMemcpy(e->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
     // reset state with an all-zero demand trace (the reference constructors end with self.reset())
     IMX_CREATE_CUDA(cudaMemset(e->d_demand_T, 0, dem_bytes));
     IMX_CREATE_CUDA(cudaMemset(e->d_state, 0, total ? total : 256));
@@ -405,7 +453,7 @@ extern "C" int imx_destroy(imx_env* e) {
     cudaSetDevice(e->cfg.device);
     if (e->hstream) { cudaStreamSynchronize(e->hstream); cudaStreamDestroy(e->hstream); }
     cudaFree(e->d_nodes); cudaFree(e->d_children); cudaFree(e->d_state); cudaFree(e->d_err);
-    cudaFree(e->d_demand_T); cudaFree(e->d_mask_T); cudaFree(e->d_cdf);
+    cudaFree(e->d_demand_T); cudaFree(e->d_mask_T); cudaFree(e->d_cdf); cudaFree(e->d_tab);
     cudaFree(e->d_act_h); cudaFree(e->d_obs_h); cudaFree(e->d_rew_h); cudaFree(e->d_dem_h); cudaFree(e->d_mask_h);
     delete e;
     return 0;

@@ -69,7 +69,12 @@ struct StepArgs {
     int32_t need_hd, need_ho;  // history state present
     int32_t wd_mult1, wd_mult;   // watchdog multipliers: LOOP1(A) and the other three
     double a, b, bma;          // bma = b - a
+    double inv_bma;            // 1/(b-a) when b-a is a power of two (the division is then an exact scaling), else 0
+    double inv_m;              // 1/m when m is a power of two, else 0 (shared-reward mean)
     // tables
+    int32_t TL;                // entries per rescale table row (0: no tables, compute)
+    int32_t pad_tl;
+    const double* __restrict__ tab;         // [m][4][TL] exact rescale results, see build_tables() in imx_api.cu
     const NodeParams* __restrict__ nodes;   // [m]
     const int8_t* __restrict__ children;    // [m][IMX_MAX_CHILDREN] lanes of the children (-1 = none)
     // state (SoA, int32)
@@ -105,11 +110,30 @@ __device__ __forceinline__ double rev_scale(double x, double vmax, double a, dou
 }
 // order clipping: MAIM kinds round then clip (MAIM_env.py:344-347), IM kinds clip then round
 // (IM_env.py:300-302); rint() is round-half-to-even like np.round.
-__device__ __forceinline__ int decode_order(double x, double om, bool std_actions, bool multi, double a, double bma) {
-    if (std_actions) x = rev_scale(x, om, a, bma);
+__device__ __forceinline__ int decode_order(double x, double om, bool std_actions, bool multi, double a, double bma,
+                                            double inv_bma) {
+    if (std_actions) {
+        // dividing by a power of two is an exact exponent shift, so the multiply gives the same bits
+        if (inv_bma != 0.0) x = __dmul_rn(__dmul_rn(__dsub_rn(x, a), om), inv_bma);
+        else x = rev_scale(x, om, a, bma);
+    }
     if (multi) x = fmin(fmax(rint(x), 0.0), om);
     else x = rint(fmin(fmax(x, 0.0), om));
     return (int)x;
+}
+// Rescaled observation value.  The integer domain of every scaled field is bounded (inventory and
+// unfulfilled orders by inv_max, capped backlog and demand by demand_max, pipeline entries by
+// 2*max(demand_max) + children), so the host precomputes a + (v*(b-a))/max for every v with the same
+// IEEE operations and the kernel replaces an FP64 division by one cached 8-byte load.
+enum : int { TAB_INV = 0, TAB_ORD = 1, TAB_DEM = 2, TAB_PIPE2 = 3 };
+__device__ __forceinline__ double scaled(const double* __restrict__ tabrow, int TL, int which, int v, double vmax,
+                                         double a, double bma) {
+    if (tabrow) return __ldg(tabrow + which * TL + (int)min((unsigned)v, (unsigned)(TL - 1)));
+    return rescale((double)v, vmax, a, bma);
+}
+// mean of the shared reward: reward_sum / num_stages (MAIM_env.py:434)
+__device__ __forceinline__ double div_by_m(double s, int m, double inv_m) {
+    return inv_m != 0.0 ? __dmul_rn(s, inv_m) : __ddiv_rn(s, (double)m);
 }
 // profit = p*ship - c*order - h*|inv' - target| - bc*backlog'           MAIM_env.py:421-424
 __device__ __forceinline__ double profit_of(double p, double c, double h, double bc, double target,

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
             child_lane[k] = (stage_ok && k < np.nchild) ? (int)A.children[i * IMX_MAX_CHILDREN + k] : -1;
     }
     const bool is_last = (i == m - 1);
+    const int delay_m1 = np.delay - 1;
     const double om_d = (double)np.order_max;
     const int full8 = T - (T % 8);
     const double neg_inv_T = -1.0 / (double)T;        // "-1 / env.num_periods" (base_restock_policy.py:45)
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
             // base_stock_policy: z - (inv + order_u - backlog), clipped to [0, order_max]  (base_restock_policy.py:12-20)
             const double inv_ech = __dsub_rn(__dadd_rn((double)inv, (double)order_u), (double)backlog);
             const double act = fmin(om_d, fmax(__dsub_rn(z, inv_ech), 0.0));
-            const int order = ok ? decode_order(act, om_d, A.std_actions != 0, A.multi != 0, A.a, A.bma) : 0;
+            const int order = ok ? decode_order(act, om_d, A.std_actions != 0, A.multi != 0, A.a, A.bma, A.inv_bma) : 0;
 
             int cust = 0;
             if (ok && np.retailer_idx >= 0) cust = dem_row ? dem_row[t] : draw_demand(Rg.gen, n, np.retailer_idx, t);
@@ -130,15 +131,14 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
             inv = min(max(inv + acq - ship, 0), np.inv_max);
             backlog = backlog_new;
 #pragma unroll
-            for (int k = 0; k < DMAX - 1; ++k) pipe[k] = pipe[k + 1];
-            pipe[DMAX - 1] = 0;
-#pragma unroll
-            for (int k = 0; k < DMAX; ++k)
-                if (k == np.delay - 1) pipe[k] = incoming;
+            for (int k = 0; k < DMAX; ++k) {
+                const int nxt = (k + 1 < DMAX) ? pipe[k + 1] : 0;
+                pipe[k] = (k == delay_m1) ? incoming : nxt;
+            }
 
             const double profit = ok ? profit_of(np.p, np.c, np.h, np.bc, np.target, ship, order, inv, backlog) : 0.0;
             double r;
-            if (A.multi) r = A.independent ? profit : __ddiv_rn(tile_seq_sum<M_PAD>(profit, m), (double)m);
+            if (A.multi) r = A.independent ? profit : div_by_m(tile_seq_sum<M_PAD>(profit, m), m, A.inv_m);
             else r = tile_np_sum<M_PAD>(profit, m);
             ret = __dadd_rn(ret, r);
             if (ok && Rg.step_reward) {

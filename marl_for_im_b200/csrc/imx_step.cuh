@@ -160,16 +160,17 @@ __device__ __forceinline__ int split_ship(int nchild, int ship, int demand, int 
 // SURVEY.md table A.5.  `row` points into the warp's shared-memory staging tile.
 template <int DMAX, int PMAX>
 __device__ __forceinline__ void write_obs_row(double* row, const StepArgs& A, const NodeParams& np, int node_idx,
-                                              int inv, int backlog, int order_u, const int (&pipe)[DMAX],
-                                              const int (&hd)[PMAX], const int (&ho)[PMAX], bool div) {
+                                              const double* __restrict__ tabrow, int inv, int backlog, int order_u,
+                                              const int (&pipe)[DMAX], const int (&hd)[PMAX], const int (&ho)[PMAX], bool div) {
     const double a = A.a, bma = A.bma;
+    const int TL = A.TL;
     const double inv_max = (double)np.inv_max, order_max = (double)np.order_max;
     const double dem_max = (double)np.demand_max;
     const double ou_max = A.multi ? order_max : inv_max;   // MAIM_env.py:300 vs IM_env.py:265
     if (A.std_state) {
-        row[0] = rescale((double)inv, inv_max, a, bma);
-        row[1] = rescale((double)backlog, dem_max, a, bma);
-        row[2] = rescale((double)order_u, ou_max, a, bma);
+        row[0] = scaled(tabrow, TL, TAB_INV, inv, inv_max, a, bma);
+        row[1] = scaled(tabrow, TL, TAB_DEM, backlog, dem_max, a, bma);
+        row[2] = scaled(tabrow, TL, A.multi ? TAB_ORD : TAB_INV, order_u, ou_max, a, bma);
     } else {
         row[0] = (double)inv;
         row[1] = (double)backlog;
@@ -189,13 +190,13 @@ __device__ __forceinline__ void write_obs_row(double* row, const StepArgs& A, co
     if (A.pd) {
 #pragma unroll
         for (int j = 0; j < PMAX; ++j)
-            if (j < A.P) row[k0 + j] = A.write_hd ? rescale((double)hd[j], dem_max, a, bma) : 0.0;   // quirk 2
+            if (j < A.P) row[k0 + j] = A.write_hd ? scaled(tabrow, TL, TAB_DEM, hd[j], dem_max, a, bma) : 0.0;   // quirk 2
         k0 += A.P;
     }
     if (A.pa) {
 #pragma unroll
         for (int j = 0; j < PMAX; ++j)
-            if (j < A.P) row[k0 + j] = rescale((double)ho[j], order_max, a, bma);
+            if (j < A.P) row[k0 + j] = scaled(tabrow, TL, TAB_ORD, ho[j], order_max, a, bma);
         k0 += A.P;
     }
     if (A.td) {
@@ -204,8 +205,8 @@ __device__ __forceinline__ void write_obs_row(double* row, const StepArgs& A, co
             if (k < A.D) {
                 double v;
                 if (!A.std_state) v = (double)pipe[k];                                    // IM kinds, raw
-                else if (div && A.multi) v = rescale((double)min(pipe[k], 2 * np.inv_max), 2.0 * inv_max, a, bma);   // MAIM_div_env.py:408-411
-                else v = rescale((double)pipe[k], inv_max, a, bma);
+                else if (div && A.multi) v = scaled(tabrow, TL, TAB_PIPE2, min(pipe[k], 2 * np.inv_max), 2.0 * inv_max, a, bma);   // MAIM_div_env.py:408-411
+                else v = scaled(tabrow, TL, TAB_INV, pipe[k], inv_max, a, bma);
                 row[k0 + k] = v;
             }
         }
@@ -248,7 +249,9 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
             child_lane[k] = (stage_ok && k < np.nchild) ? (int)A.children[i * IMX_MAX_CHILDREN + k] : -1;
     }
     const bool is_last = (i == m - 1);
+    const int delay_m1 = np.delay - 1;
     const double om_d = (double)np.order_max;
+    const double* __restrict__ tabrow = A.tab ? A.tab + (size_t)(stage_ok ? i : 0) * 4 * A.TL : nullptr;
 
     const int tile_doubles = (EPW * m * O + 1) & ~1;             // keep every warp's tile 16-byte aligned
     double* wtile = smem_obs + (size_t)warp * tile_doubles;
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
         }
 
         // ---- order clipping ---------------------------------------------------------------
-        const int order = ok ? decode_order(act, om_d, A.std_actions != 0, A.multi != 0, A.a, A.bma) : 0;
+        const int order = ok ? decode_order(act, om_d, A.std_actions != 0, A.multi != 0, A.a, A.bma, A.inv_bma) : 0;
 
         // ---- demand propagation -----------------------------------------------------------
         int demand;
@@ -363,12 +366,13 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
         if (A.cap_backlog) backlog_new = min(backlog_new, np.demand_max);
         const int order_u_new = min(max(order_u + order - acq, 0), np.inv_max);
         const int inv_new = min(max(inv + acq - ship, 0), np.inv_max);
+        // shift the lead-time register by one period and insert this period's shipment at slot delay-1
+        // (selects, not indexed stores: the array must stay in registers)
 #pragma unroll
-        for (int k = 0; k < DMAX - 1; ++k) pipe[k] = pipe[k + 1];
-        pipe[DMAX - 1] = 0;
-#pragma unroll
-        for (int k = 0; k < DMAX; ++k)
-            if (k == np.delay - 1) pipe[k] = incoming;
+        for (int k = 0; k < DMAX; ++k) {
+            const int nxt = (k + 1 < DMAX) ? pipe[k + 1] : 0;
+            pipe[k] = (k == delay_m1) ? incoming : nxt;
+        }
 #pragma unroll
         for (int j = PMAX - 1; j > 0; --j) { hd[j] = hd[j - 1]; ho[j] = ho[j - 1]; }
         hd[0] = demand;
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
         double reward_out;
         if (A.multi) {
             if (A.independent) reward_out = profit;
-            else reward_out = __ddiv_rn(tile_seq_sum<M_PAD>(profit, m), (double)m);
+            else reward_out = div_by_m(tile_seq_sum<M_PAD>(profit, m), m, A.inv_m);
         } else {
             reward_out = tile_np_sum<M_PAD>(profit, m);
         }
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
             if (A.info.acquisition_dev) A.info.acquisition_dev[cell] = acq;
             if (A.info.order_dev) A.info.order_dev[cell] = order;
             if (A.info.profit_dev) A.info.profit_dev[cell] = profit;
-            if (A.obs) write_obs_row<DMAX, PMAX>(wtile + (size_t)(sub * m + i) * O, A, np, i, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
+            if (A.obs) write_obs_row<DMAX, PMAX>(wtile + (size_t)(sub * m + i) * O, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
         }
         if (A.obs) {
             const int64_t first = wt * EPW;
