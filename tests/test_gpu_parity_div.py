@@ -1,0 +1,94 @@
+"""CUDA path vs the oracle / golden fixtures — divergent networks (pass-exact split, signed ledger)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from cuda_harness import assert_same, run_cuda
+from harness import golden_names, load_golden, make_delay_mask, random_case, run_oracle
+from marl_for_im_b200 import presets
+
+pytestmark = pytest.mark.gpu
+
+DIV_GOLDEN = [n for n in golden_names() if "div" in n]
+MODES = list(itertools.product([False, True], repeat=3))
+
+
+@pytest.mark.parametrize("name", DIV_GOLDEN)
+def test_cuda_matches_golden_div(name):
+    g = load_golden(name)
+    got = run_cuda(g["kind"], g["config"], g["demand_trace"], g["actions"], g["delay_mask"], n_copies=3)
+    assert_same(g["ref"], got, name)
+
+
+@pytest.mark.parametrize("kind,preset", [("MAIM_div", "div1"), ("IM_div", "div1"), ("MAIM_div", "div2"), ("IM_div", "div2")])
+def test_cuda_matches_oracle_div_modes(kind, preset):
+    rng = np.random.default_rng(123)
+    for td, pd, pa in MODES:
+        if kind == "MAIM_div" and (not td) and pa and (not pd):
+            continue
+        for P, mu, amode, indep in [(1, 5, "uniform", False), (2, 9, "near_eq", True)]:
+            cfg = presets.PRESETS[preset](time_dependency=td, prev_demand=pd, prev_actions=pa, prev_length=P, independent=indep)
+            m = cfg["num_nodes"]
+            cfg["inv_max"] = np.array([30, 25, 40, 35, 30, 45][:m], dtype=float)
+            cfg["inv_target"] = np.array([0, 3, 5.5, 1, 0, 2][:m], dtype=float)
+            if kind == "MAIM_div":
+                cfg["share_network"] = bool(P == 2)
+            demand, actions = random_case(kind, cfg, rng, mu=mu, action_mode=amode)
+            assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=5),
+                        f"{kind}/{preset}/{(td, pd, pa)}/P{P}")
+
+
+@pytest.mark.parametrize("kind", ["MAIM_div", "IM_div"])
+def test_cuda_div_noisy_and_raw(kind):
+    rng = np.random.default_rng(8)
+    cfg = presets.div2()
+    for _ in range(4):
+        demand, actions = random_case(kind, cfg, rng, mu=7, action_mode="near_eq")
+        mask = make_delay_mask(kind, cfg["delay"], 30, 0.3, rng)
+        assert_same(run_oracle(kind, cfg, demand, actions, mask), run_cuda(kind, cfg, demand, actions, mask, n_copies=4), "noisy")
+    if kind == "IM_div":
+        cfg = presets.div1(prev_actions=True)
+        cfg["standardise_state"] = False
+        cfg["standardise_actions"] = False
+        demand, actions = random_case(kind, cfg, rng, mu=12)
+        assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=2), "raw")
+
+
+def test_cuda_wide_tree():
+    """A bushier tree: 11 nodes, one node with 4 children, depth 3, heterogeneous lead times."""
+    rng = np.random.default_rng(31)
+    conn = {0: [1, 2], 1: [3, 4, 5, 6], 2: [7], 3: [], 4: [8, 9, 10], 5: [], 6: [], 7: [], 8: [], 9: [], 10: []}
+    m = 11
+    cfg = {"num_nodes": m, "num_periods": 20, "connections": conn, "init_inv": np.ones(m) * 12, "inv_target": np.ones(m) * 1,
+           "inv_max": rng.integers(20, 45, m).astype(float), "stock_cost": rng.uniform(0.1, 0.5, m),
+           "backlog_cost": rng.uniform(0.3, 0.9, m), "delay": rng.integers(1, 4, m), "time_dependency": True,
+           "prev_demand": True, "prev_actions": True, "prev_length": 2, "independent": False, "share_network": True}
+    for kind in ("MAIM_div", "IM_div"):
+        for amode in ("uniform", "near_eq"):
+            demand, actions = random_case(kind, cfg, rng, mu=4, action_mode=amode)
+            assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=3), f"tree {kind}")
+
+
+def test_cuda_div_batch_distinct_envs():
+    import torch
+    from marl_for_im_b200.envs import MultiAgentInvManagementDiv
+    cfg = presets.div2()
+    N, T, m, R = 2048 + 5, 30, 6, 3
+    rng = np.random.default_rng(420)
+    demand = rng.poisson(5, size=(N, R, T)).astype(np.int32)
+    actions = np.clip(rng.normal(-0.6, 0.5, size=(T, N, m)), -1, 1)
+    env = MultiAgentInvManagementDiv(dict(cfg, num_envs=N))
+    env.reset(customer_demand=demand)
+    a_dev = torch.as_tensor(actions, device="cuda:0")
+    obs, rew = [], []
+    for t in range(T):
+        o, r, done, _ = env.step(a_dev[t])
+        obs.append(torch.stack([o[n] for n in env.agent_names], dim=1).cpu().numpy())
+        rew.append(torch.stack([r[n] for n in env.agent_names], dim=1).cpu().numpy())
+    obs, rew = np.stack(obs), np.stack(rew)
+    assert int(env.error_flags.abs().sum()) == 0
+    for n in list(range(0, N, 61)) + [N - 1]:
+        want = run_oracle("MAIM_div", cfg, demand[n], actions[:, n])
+        np.testing.assert_array_equal(want["obs"][1:], obs[:, n])
+        np.testing.assert_array_equal(want["reward"], rew[:, n])
