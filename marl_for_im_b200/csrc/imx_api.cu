@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "imx_reset.cuh"
+#include "imx_step_tma.cuh"
 #include "imx_rollout.cuh"
 
 using namespace imx;
@@ -49,6 +50,7 @@ extern "C" int64_t imx_launch_count(void) { return g_launches.load(); }
 // handle
 // --------------------------------------------------------------------------------------
 typedef void (*step_fn_t)(const StepArgs);
+typedef void (*tma_fn_t)(const StepArgs, const TileLayout);
 typedef void (*reset_fn_t)(const StepArgs, int);
 typedef void (*rollout_fn_t)(const StepArgs, const RolloutArgs);
 
@@ -88,6 +90,9 @@ struct imx_env {
     uint64_t episode = 0;
     // kernels
     step_fn_t step_fn = nullptr;
+    tma_fn_t tma_fn = nullptr;
+    TileLayout tile = {};
+    int step_path = 0;                   // 0 auto, 1 direct only, 2 TMA wherever legal (IMX_STEP_PATH)
     reset_fn_t reset_fn = nullptr;
     rollout_fn_t rollout_fn = nullptr;
     int step_grid_cap = 0, rollout_grid_cap = 0;
@@ -103,11 +108,16 @@ static void pick_kernels(imx_env* e) {
     const bool small = (e->D <= 4 && e->P <= 1);
     if constexpr (DIV) {
         const bool few = e->maxc <= 2;
+        if (small && few) e->tma_fn = step_kernel_tma<M_PAD, 4, 1, 2, true>;
+        else if (small) e->tma_fn = step_kernel_tma<M_PAD, 4, 1, 8, true>;
+        else if (few) e->tma_fn = step_kernel_tma<M_PAD, 8, 8, 2, true>;
+        else e->tma_fn = step_kernel_tma<M_PAD, 8, 8, 8, true>;
         if (small && few) { e->step_fn = step_kernel<M_PAD, 4, 1, 2, true>; e->rollout_fn = rollout_kernel<M_PAD, 4, 2, true>; }
         else if (small)   { e->step_fn = step_kernel<M_PAD, 4, 1, 8, true>; e->rollout_fn = rollout_kernel<M_PAD, 4, 8, true>; }
         else if (few)     { e->step_fn = step_kernel<M_PAD, 8, 8, 2, true>; e->rollout_fn = rollout_kernel<M_PAD, 8, 2, true>; }
         else              { e->step_fn = step_kernel<M_PAD, 8, 8, 8, true>; e->rollout_fn = rollout_kernel<M_PAD, 8, 8, true>; }
     } else {
+        e->tma_fn = small ? step_kernel_tma<M_PAD, 4, 1, 1, false> : step_kernel_tma<M_PAD, 8, 8, 1, false>;
         if (small) { e->step_fn = step_kernel<M_PAD, 4, 1, 1, false>; e->rollout_fn = rollout_kernel<M_PAD, 4, 1, false>; }
         else       { e->step_fn = step_kernel<M_PAD, 8, 8, 1, false>; e->rollout_fn = rollout_kernel<M_PAD, 8, 1, false>; }
     }
@@ -138,6 +148,32 @@ static int select_kernels(imx_env* e) {
     IMX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e->step_fn, STEP_THREADS, e->step_smem));
     if (occ < 1) return fail(-4, "step kernel does not fit on an SM (smem %zu B)", e->step_smem);
     e->step_grid_cap = dev_sms * occ;
+    {   // shared-memory tile layout of the TMA kernel (regions 128-byte aligned)
+        TileLayout& L = e->tile;
+        const int E = STEP_THREADS / e->m_pad;
+        int off = 0;
+        auto take = [&](int bytes) { const int o = off; off += (bytes + 127) & ~127; return o; };
+        L.E = E;
+        L.off_act = take(E * m * 8);
+        L.off_inv = take(E * m * 4);
+        L.off_bl = take(E * m * 4);
+        L.off_ou = take(E * m * 4);
+        L.off_pipe = take(E * e->L * 4);
+        L.off_hd = take(e->need_hd ? E * m * e->P * 4 : 0);
+        L.off_ho = take(e->need_ho ? E * m * e->P * 4 : 0);
+        L.off_carry = take(e->has_carry ? E * m * 4 : 0);
+        L.off_bt = take(E * e->NB * 4);
+        L.off_dem = take(e->R * E * 4);
+        L.off_obs = take(E * m * e->O * 8);
+        L.off_rew = take(E * m * 8);
+        L.total = off;
+        if (L.total <= 200 * 1024)
+            IMX_CUDA(cudaFuncSetAttribute((const void*)e->tma_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        else
+            e->tma_fn = nullptr;
+        const char* pth = getenv("IMX_STEP_PATH");
+        e->step_path = (pth && !strcmp(pth, "direct")) ? 1 : (pth && !strcmp(pth, "tma")) ? 2 : 0;
+    }
     IMX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e->rollout_fn, ROLLOUT_THREADS, 0));
     if (occ < 1) return fail(-4, "rollout kernel does not fit on an SM");
     e->rollout_grid_cap = dev_sms * occ;
@@ -558,12 +594,27 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
     A.obs = obs_dev;
     A.reward = reward_dev;
     if (info) A.info = *info;
-    const int epw = 32 / e->m_pad;
-    const int64_t warp_tiles = (e->N + epw - 1) / epw;
-    const int64_t blocks_needed = (warp_tiles + (STEP_THREADS / 32) - 1) / (STEP_THREADS / 32);
-    const unsigned grid = (unsigned)(blocks_needed < e->step_grid_cap ? blocks_needed : e->step_grid_cap);
-    e->step_fn<<<grid, STEP_THREADS, e->step_smem, s>>>(A);
-    IMX_CHECK_LAUNCH("step_kernel");
+    // fast path: whole tiles of E envs through the TMA-staged kernel; the tail (and configurations the
+    // bulk copies cannot address: unaligned caller buffers, N not a multiple of 4) through the direct kernel
+    int64_t n_tma = 0;
+    const auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    if (e->tma_fn && e->step_path != 1 && (e->N % 4) == 0 && aligned16(actions_dev) && aligned16(obs_dev) && aligned16(reward_dev)) {
+        n_tma = (e->N / e->tile.E) * e->tile.E;
+        if (e->step_path == 0 && n_tma < e->tile.E) n_tma = 0;
+    }
+    if (n_tma > 0) {
+        e->tma_fn<<<(unsigned)(n_tma / e->tile.E), STEP_THREADS, e->tile.total, s>>>(A, e->tile);
+        IMX_CHECK_LAUNCH("step_kernel_tma");
+    }
+    if (n_tma < e->N) {
+        A.n_begin = n_tma;
+        const int epw = 32 / e->m_pad;
+        const int64_t warp_tiles = (e->N - n_tma + epw - 1) / epw;
+        const int64_t blocks_needed = (warp_tiles + (STEP_THREADS / 32) - 1) / (STEP_THREADS / 32);
+        const unsigned grid = (unsigned)(blocks_needed < e->step_grid_cap ? blocks_needed : e->step_grid_cap);
+        e->step_fn<<<grid, STEP_THREADS, e->step_smem, s>>>(A);
+        IMX_CHECK_LAUNCH("step_kernel");
+    }
     e->t += 1;
     return 0;
 }

@@ -55,6 +55,7 @@ __device__ __forceinline__ NodeParams load_node(const NodeParams* p) {
 struct StepArgs {
     // sizes
     int64_t N;
+    int64_t n_begin;           // first env this launch handles (direct kernel; the TMA kernel covers [0, n_begin))
     int32_t m, T, P, D, O, L, NB, R;
     int32_t t;                 // period being simulated (0-based)
     int32_t maxc;              // max children per node (divergent)

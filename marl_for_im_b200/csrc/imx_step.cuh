@@ -219,12 +219,10 @@ __device__ __forceinline__ void write_obs_row(double* row, const StepArgs& A, co
 __device__ __forceinline__ void flush_obs_tile(double* gdst, const double* stile, int doubles, int lane) {
     const uint32_t bytes = (uint32_t)doubles * 8u;
     const bool bulk_ok = ((bytes & 15u) == 0u) && ((reinterpret_cast<uintptr_t>(gdst) & 15u) == 0u);
+    if (bulk_ok) fence_proxy_async_smem();      // every writer orders its stores before the async-proxy read
     __syncwarp();
     if (bulk_ok) {
-        if (lane == 0) {
-            fence_proxy_async_smem();
-            bulk_store_s2g(gdst, stile, bytes);
-        }
+        if (lane == 0) bulk_store_s2g(gdst, stile, bytes);
     } else {
         for (int k = lane; k < doubles; k += 32) gdst[k] = stile[k];
     }
@@ -259,7 +257,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
 
     const int64_t warps_in_grid = (int64_t)gridDim.x * (STEP_THREADS / 32);
     const int64_t n_warp_tiles = (A.N + EPW - 1) / EPW;
-    for (int64_t wt = (int64_t)blockIdx.x * (STEP_THREADS / 32) + warp; wt < n_warp_tiles; wt += warps_in_grid) {
+    for (int64_t wt = A.n_begin / EPW + (int64_t)blockIdx.x * (STEP_THREADS / 32) + warp; wt < n_warp_tiles; wt += warps_in_grid) {
         const int64_t n = wt * EPW + sub;
         const bool ok = stage_ok && n < A.N;
         const int64_t cell = n * m + i;

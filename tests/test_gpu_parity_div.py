@@ -17,7 +17,7 @@ MODES = list(itertools.product([False, True], repeat=3))
 @pytest.mark.parametrize("name", DIV_GOLDEN)
 def test_cuda_matches_golden_div(name):
     g = load_golden(name)
-    got = run_cuda(g["kind"], g["config"], g["demand_trace"], g["actions"], g["delay_mask"], n_copies=3)
+    got = run_cuda(g["kind"], g["config"], g["demand_trace"], g["actions"], g["delay_mask"], n_copies=72)
     assert_same(g["ref"], got, name)
 
 
@@ -35,7 +35,7 @@ def test_cuda_matches_oracle_div_modes(kind, preset):
             if kind == "MAIM_div":
                 cfg["share_network"] = bool(P == 2)
             demand, actions = random_case(kind, cfg, rng, mu=mu, action_mode=amode)
-            assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=5),
+            assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=72),
                         f"{kind}/{preset}/{(td, pd, pa)}/P{P}")
 
 
@@ -46,13 +46,13 @@ def test_cuda_div_noisy_and_raw(kind):
     for _ in range(4):
         demand, actions = random_case(kind, cfg, rng, mu=7, action_mode="near_eq")
         mask = make_delay_mask(kind, cfg["delay"], 30, 0.3, rng)
-        assert_same(run_oracle(kind, cfg, demand, actions, mask), run_cuda(kind, cfg, demand, actions, mask, n_copies=4), "noisy")
+        assert_same(run_oracle(kind, cfg, demand, actions, mask), run_cuda(kind, cfg, demand, actions, mask, n_copies=72), "noisy")
     if kind == "IM_div":
         cfg = presets.div1(prev_actions=True)
         cfg["standardise_state"] = False
         cfg["standardise_actions"] = False
         demand, actions = random_case(kind, cfg, rng, mu=12)
-        assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=2), "raw")
+        assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=72), "raw")
 
 
 def test_cuda_wide_tree():
@@ -67,14 +67,14 @@ def test_cuda_wide_tree():
     for kind in ("MAIM_div", "IM_div"):
         for amode in ("uniform", "near_eq"):
             demand, actions = random_case(kind, cfg, rng, mu=4, action_mode=amode)
-            assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=3), f"tree {kind}")
+            assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=72), f"tree {kind}")
 
 
 def test_cuda_div_batch_distinct_envs():
     import torch
     from marl_for_im_b200.envs import MultiAgentInvManagementDiv
     cfg = presets.div2()
-    N, T, m, R = 2048 + 5, 30, 6, 3
+    N, T, m, R = 2048 + 8, 30, 6, 3
     rng = np.random.default_rng(420)
     demand = rng.poisson(5, size=(N, R, T)).astype(np.int32)
     actions = np.clip(rng.normal(-0.6, 0.5, size=(T, N, m)), -1, 1)

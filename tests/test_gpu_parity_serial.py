@@ -21,7 +21,7 @@ SERIAL_GOLDEN = [n for n in golden_names() if not ("div" in n)]
 @pytest.mark.parametrize("name", SERIAL_GOLDEN)
 def test_cuda_matches_golden_serial(name):
     g = load_golden(name)
-    got = run_cuda(g["kind"], g["config"], g["demand_trace"], g["actions"], g["delay_mask"], n_copies=3)
+    got = run_cuda(g["kind"], g["config"], g["demand_trace"], g["actions"], g["delay_mask"], n_copies=72)
     assert_same(g["ref"], got, name)
 
 
@@ -41,7 +41,7 @@ def test_cuda_matches_oracle_all_modes(kind, preset):
             cfg["inv_max"] = np.array([30, 25, 40, 35, 30, 45, 20, 30][:m], dtype=float)
             cfg["inv_target"] = np.array([0, 3, 5.5, 1, 0, 2, 4, 0][:m], dtype=float)
             demand, actions = random_case(kind, cfg, rng, mu=mu)
-            assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=5),
+            assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=72),
                         f"{kind}/{preset}/{(td, pd, pa)}/P{P}")
 
 
@@ -54,12 +54,12 @@ def test_cuda_non_standardised_and_noisy(kind):
         cfg = presets.serial4(time_dependency=td, prev_demand=pd, prev_actions=pa, prev_length=2,
                               standardise_state=False, standardise_actions=False)
         demand, actions = random_case(kind, cfg, rng, mu=12)
-        assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=2), "raw")
+        assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=72), "raw")
     cfg = presets.serial8()
     for _ in range(3):
         demand, actions = random_case(kind, cfg, rng, mu=6, action_mode="near_eq")
         mask = make_delay_mask(kind, cfg["delay"], 30, 0.3, rng)
-        assert_same(run_oracle(kind, cfg, demand, actions, mask), run_cuda(kind, cfg, demand, actions, mask, n_copies=9), "noisy")
+        assert_same(run_oracle(kind, cfg, demand, actions, mask), run_cuda(kind, cfg, demand, actions, mask, n_copies=72), "noisy")
 
 
 def test_cuda_wide_chain_and_tail_sizes():
@@ -76,14 +76,14 @@ def test_cuda_wide_chain_and_tail_sizes():
         for kind in ("MAIM", "IM"):
             demand = rng.poisson(6, 12)
             actions = rng.uniform(-1.1, 1.1, (12, m))
-            assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=7), f"m={m}")
+            assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=72), f"m={m}")
 
 
 def test_cuda_batch_of_distinct_envs():
     """4096 envs with distinct traces, compared env by env on a sample and through shard invariance."""
     from marl_for_im_b200.envs import MultiAgentInvManagement
     cfg = presets.serial4()
-    N, T, m = 4096 + 3, 30, 4
+    N, T, m = 4096 + 8, 30, 4
     rng = np.random.default_rng(420)
     demand = rng.poisson(5, size=(N, T)).astype(np.int32)
     actions = np.random.default_rng(0).uniform(-1, 1, size=(T, N, m))
@@ -108,3 +108,19 @@ def test_cuda_batch_of_distinct_envs():
         for t in range(T):
             o2, r2, _, _ = e2.step(a_dev[t, lo:hi])
         np.testing.assert_array_equal(torch.stack([o2[n] for n in e2.agent_names], dim=1).cpu().numpy(), obs[-1, lo:hi])
+
+
+def test_both_step_paths_agree(monkeypatch):
+    """The TMA-staged kernel and the direct kernel are two implementations of the same step: force
+    each one (IMX_STEP_PATH is read when a handle is created) and compare bytes, including an N that
+    is not a multiple of 4 (TMA illegal → the auto path must fall back to the direct kernel)."""
+    rng = np.random.default_rng(77)
+    cfg = presets.serial8(prev_actions=True, prev_length=2)
+    demand, actions = random_case("MAIM", cfg, rng, mu=7)
+    want = run_oracle("MAIM", cfg, demand, actions)
+    for path, n in (("direct", 96), ("tma", 96), ("auto", 96), ("auto", 97), ("tma", 32)):
+        if path == "auto":
+            monkeypatch.delenv("IMX_STEP_PATH", raising=False)
+        else:
+            monkeypatch.setenv("IMX_STEP_PATH", path)
+        assert_same(want, run_cuda("MAIM", cfg, demand, actions, n_copies=n), f"path={path} N={n}")
