@@ -31,7 +31,9 @@
 #ifndef IMX_B200_H
 #define IMX_B200_H
 
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -113,6 +115,7 @@ enum imx_field {
     IMX_F_COUNT = 10
 };
 
+#ifndef __CUDACC_RTC__   /* the device-side (NVRTC) build only needs the types above */
 const char* imx_last_error(void);
 int imx_abi_version(void);
 int imx_config_size(void);   /* sizeof(imx_config): lets a foreign-language binding verify its struct mirror */
@@ -184,8 +187,18 @@ int imx_step_host(imx_env* env, const double* actions_host, double* obs_host, do
  * sentinel > 1).  Returns the table length; copies min(len, cap) entries when out != NULL. */
 int imx_poisson_cdf(const imx_env* env, double* out, int cap);
 
+/* Which kernel served the last step()/rollout of this handle: 0 ahead-of-time direct kernel,
+ * 1 ahead-of-time TMA-staged kernel, 2 runtime-specialised (NVRTC, same sources, flags as literals). */
+int imx_kernel_variant(const imx_env* env);
+/* Last message of the runtime-specialisation layer (why it is unavailable, or a compile log). */
+const char* imx_jit_log(void);
+/* Compiles the specialised kernels for `cfg` with NVRTC for sm_100a WITHOUT a GPU (build check).
+ * Returns the cubin size in bytes, or a negative error; `log` receives the compiler log. */
+int imx_jit_compile_check(const imx_config* cfg, char* log, int cap);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 int64_t imx_launch_count(void);
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,7 @@
 #include "imx_reset.cuh"
 #include "imx_step_tma.cuh"
 #include "imx_rollout.cuh"
+#include "imx_jit.cuh"
 
 using namespace imx;
 
@@ -93,6 +94,10 @@ struct imx_env {
     tma_fn_t tma_fn = nullptr;
     TileLayout tile = {};
     int step_path = 0;                   // 0 auto, 1 direct only, 2 TMA wherever legal (IMX_STEP_PATH)
+    int jit_policy = 0;                  // 0 auto (large batches), 1 always, -1 never (IMX_JIT)
+    int jit_state = 0;                   // 0 not tried, 1 specialised kernels loaded, -1 unavailable
+    const imxjit::Kernels* jit = nullptr;
+    int last_variant = 0;                // 0 AOT direct, 1 AOT TMA, 2 runtime-specialised TMA
     reset_fn_t reset_fn = nullptr;
     rollout_fn_t rollout_fn = nullptr;
     int step_grid_cap = 0, rollout_grid_cap = 0;
@@ -125,6 +130,81 @@ static void pick_kernels(imx_env* e) {
     e->m_pad = M_PAD;
 }
 
+static int m_pad_of(const imx_env* e) {
+    const int m = e->m;
+    if (e->div) return m <= 4 ? 4 : m <= 8 ? 8 : m <= 16 ? 16 : 32;
+    return m <= 2 ? 2 : m <= 4 ? 4 : m <= 8 ? 8 : m <= 16 ? 16 : 32;
+}
+
+// shared-memory tile layout of the TMA kernel (regions 128-byte aligned); pure host arithmetic
+static void compute_tile(imx_env* e) {
+    TileLayout& L = e->tile;
+    const int m = e->m;
+    const int E = STEP_THREADS / m_pad_of(e);
+    int off = 0;
+    auto take = [&](int bytes) { const int o = off; off += (bytes + 127) & ~127; return o; };
+    L.E = E;
+    L.off_act = take(E * m * 8);
+    L.off_inv = take(E * m * 4);
+    L.off_bl = take(E * m * 4);
+    L.off_ou = take(E * m * 4);
+    L.off_pipe = take(E * e->L * 4);
+    L.off_hd = take(e->need_hd ? E * m * e->P * 4 : 0);
+    L.off_ho = take(e->need_ho ? E * m * e->P * 4 : 0);
+    L.off_carry = take(e->has_carry ? E * m * 4 : 0);
+    L.off_bt = take(E * e->NB * 4);
+    L.off_dem = take(e->R * E * 4);
+    L.off_obs = take(E * m * e->O * 8);
+    L.off_rew = take(E * m * 8);
+    L.total = off;
+}
+
+// -D options and template instantiations of the runtime-specialised build (imx_jit.cuh)
+static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, std::string& step_name, std::string& rollout_name) {
+    const imx_config& c = e->cfg;
+    const bool always_std = (c.kind == IMX_KIND_MAIM_DIV);
+    const int std_state = always_std ? 1 : (c.standardise_state != 0);
+    auto add = [&](const char* k, long long v) { defs.push_back(std::string("IMX_K_") + k + "=" + std::to_string(v)); };
+    add("m", e->m); add("T", e->T); add("P", e->P); add("D", e->D); add("O", e->O); add("L", e->L); add("NB", e->NB);
+    add("R", e->R); add("maxc", e->maxc); add("multi", e->multi); add("std_state", std_state);
+    add("std_actions", always_std ? 1 : (c.standardise_actions != 0)); add("cap_backlog", always_std ? 1 : std_state);
+    add("independent", c.independent != 0); add("share_network", (c.kind == IMX_KIND_MAIM_DIV && c.share_network) ? 1 : 0);
+    add("td", c.time_dependency != 0); add("pd", c.prev_demand != 0); add("pa", c.prev_actions != 0);
+    add("write_hd", e->write_hd); add("noisy", 0); add("has_carry", e->has_carry); add("need_hd", e->need_hd);
+    add("need_ho", e->need_ho); add("wd_mult1", e->multi ? 2 : 4); add("wd_mult", e->multi ? 1 : 2); add("TL", TL);
+    add("has_info", 0); add("has_obs", 1); add("has_tab", TL > 0);
+    int ex = 0;
+    const double fr = std::frexp(c.b - c.a, &ex);
+    add("bma_pow2", (fr == 0.5 && ex > -1000 && ex < 1000) ? 1 : 0);
+    add("m_pow2", ((e->m & (e->m - 1)) == 0) ? 1 : 0);
+    const TileLayout& L = e->tile;
+    auto addt = [&](const char* k, long long v) { defs.push_back(std::string("IMX_KT_") + k + "=" + std::to_string(v)); };
+    addt("E", L.E); addt("off_act", L.off_act); addt("off_inv", L.off_inv); addt("off_bl", L.off_bl); addt("off_ou", L.off_ou);
+    addt("off_pipe", L.off_pipe); addt("off_hd", L.off_hd); addt("off_ho", L.off_ho); addt("off_carry", L.off_carry);
+    addt("off_bt", L.off_bt); addt("off_dem", L.off_dem); addt("off_obs", L.off_obs); addt("off_rew", L.off_rew); addt("total", L.total);
+    const int mp = m_pad_of(e);
+    const int pmax = (e->need_hd || e->need_ho) ? e->P : 1;
+    const int maxc = e->maxc > 1 ? e->maxc : 1;
+    const std::string dv = e->div ? "true" : "false";
+    step_name = "imx::step_kernel_tma<" + std::to_string(mp) + ", " + std::to_string(e->D) + ", " + std::to_string(pmax) + ", " +
+                std::to_string(e->div ? maxc : 1) + ", " + dv + ">";
+    rollout_name = "imx::rollout_kernel<" + std::to_string(mp) + ", " + std::to_string(e->D) + ", " + std::to_string(e->div ? maxc : 1) +
+                   ", " + dv + ">";
+}
+
+// Loads the specialised kernels for this handle on first use (large batches, or IMX_JIT=1).
+static void ensure_jit(imx_env* e) {
+    if (e->jit_state != 0) return;
+    e->jit_state = -1;
+    if (e->jit_policy < 0 || !e->tma_fn) return;
+    if (e->jit_policy == 0 && e->N < 4096) return;
+    std::vector<std::string> defs;
+    std::string sn, rn;
+    jit_spec(e, e->TL, defs, sn, rn);
+    e->jit = imxjit::get(defs, sn, rn, e->tile.total);
+    if (e->jit) e->jit_state = 1;
+}
+
 static int select_kernels(imx_env* e) {
     const int m = e->m;
     if (e->div) {
@@ -148,31 +228,16 @@ static int select_kernels(imx_env* e) {
     IMX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e->step_fn, STEP_THREADS, e->step_smem));
     if (occ < 1) return fail(-4, "step kernel does not fit on an SM (smem %zu B)", e->step_smem);
     e->step_grid_cap = dev_sms * occ;
-    {   // shared-memory tile layout of the TMA kernel (regions 128-byte aligned)
-        TileLayout& L = e->tile;
-        const int E = STEP_THREADS / e->m_pad;
-        int off = 0;
-        auto take = [&](int bytes) { const int o = off; off += (bytes + 127) & ~127; return o; };
-        L.E = E;
-        L.off_act = take(E * m * 8);
-        L.off_inv = take(E * m * 4);
-        L.off_bl = take(E * m * 4);
-        L.off_ou = take(E * m * 4);
-        L.off_pipe = take(E * e->L * 4);
-        L.off_hd = take(e->need_hd ? E * m * e->P * 4 : 0);
-        L.off_ho = take(e->need_ho ? E * m * e->P * 4 : 0);
-        L.off_carry = take(e->has_carry ? E * m * 4 : 0);
-        L.off_bt = take(E * e->NB * 4);
-        L.off_dem = take(e->R * E * 4);
-        L.off_obs = take(E * m * e->O * 8);
-        L.off_rew = take(E * m * 8);
-        L.total = off;
-        if (L.total <= 200 * 1024)
-            IMX_CUDA(cudaFuncSetAttribute((const void*)e->tma_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        else
-            e->tma_fn = nullptr;
+    compute_tile(e);
+    if (e->tile.total <= 200 * 1024)
+        IMX_CUDA(cudaFuncSetAttribute((const void*)e->tma_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->tile.total));
+    else
+        e->tma_fn = nullptr;
+    {
         const char* pth = getenv("IMX_STEP_PATH");
         e->step_path = (pth && !strcmp(pth, "direct")) ? 1 : (pth && !strcmp(pth, "tma")) ? 2 : 0;
+        const char* jp = getenv("IMX_JIT");
+        e->jit_policy = (jp && !strcmp(jp, "1")) ? 1 : (jp && !strcmp(jp, "0")) ? -1 : 0;
     }
     IMX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e->rollout_fn, ROLLOUT_THREADS, 0));
     if (occ < 1) return fail(-4, "rollout kernel does not fit on an SM");
@@ -593,7 +658,10 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
     A.actions = actions_dev;
     A.obs = obs_dev;
     A.reward = reward_dev;
-    if (info) A.info = *info;
+    if (info) {
+        A.info = *info;
+        A.has_info = (info->demand_dev || info->ship_dev || info->acquisition_dev || info->order_dev || info->profit_dev) ? 1 : 0;
+    }
     // fast path: whole tiles of E envs through the TMA-staged kernel; the tail (and configurations the
     // bulk copies cannot address: unaligned caller buffers, N not a multiple of 4) through the direct kernel
     int64_t n_tma = 0;
@@ -602,9 +670,26 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
         n_tma = (e->N / e->tile.E) * e->tile.E;
         if (e->step_path == 0 && n_tma < e->tile.E) n_tma = 0;
     }
+    e->last_variant = 0;
     if (n_tma > 0) {
-        e->tma_fn<<<(unsigned)(n_tma / e->tile.E), STEP_THREADS, e->tile.total, s>>>(A, e->tile);
-        IMX_CHECK_LAUNCH("step_kernel_tma");
+        bool launched = false;
+        if (obs_dev && !A.has_info && !A.noisy) {
+            ensure_jit(e);
+            if (e->jit_state == 1) {
+                void* params[] = {(void*)&A, (void*)&e->tile};
+                const CUresult cr = imxjit::g_api.LaunchKernel(e->jit->step, (unsigned)(n_tma / e->tile.E), 1, 1, STEP_THREADS, 1, 1,
+                                                               (unsigned)e->tile.total, (CUstream)s, params, nullptr);
+                if (cr != CUDA_SUCCESS) return fail(-3, "launch of the specialised step kernel failed (CUresult %d)", (int)cr);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+                launched = true;
+                e->last_variant = 2;
+            }
+        }
+        if (!launched) {
+            e->tma_fn<<<(unsigned)(n_tma / e->tile.E), STEP_THREADS, e->tile.total, s>>>(A, e->tile);
+            IMX_CHECK_LAUNCH("step_kernel_tma");
+            e->last_variant = 1;
+        }
     }
     if (n_tma < e->N) {
         A.n_begin = n_tma;
@@ -652,8 +737,20 @@ extern "C" int imx_rollout_basestock(imx_env* e, const double* z_dev, int z_stri
     const int64_t warp_tiles = (e->N + epw - 1) / epw;
     const int64_t blocks_needed = (warp_tiles + (ROLLOUT_THREADS / 32) - 1) / (ROLLOUT_THREADS / 32);
     const unsigned grid = (unsigned)(blocks_needed < e->rollout_grid_cap ? blocks_needed : e->rollout_grid_cap);
-    e->rollout_fn<<<grid, ROLLOUT_THREADS, 0, s>>>(A, Rg);
-    IMX_CHECK_LAUNCH("rollout_kernel");
+    ensure_jit(e);
+    if (e->jit_state == 1) {
+        void* params[] = {(void*)&A, (void*)&Rg};
+        int occ_blocks = e->rollout_grid_cap;
+        const unsigned g2 = (unsigned)(blocks_needed < (int64_t)occ_blocks * 4 ? blocks_needed : (int64_t)occ_blocks * 4);
+        const CUresult cr = imxjit::g_api.LaunchKernel(e->jit->rollout, g2, 1, 1, ROLLOUT_THREADS, 1, 1, 0, (CUstream)s, params, nullptr);
+        if (cr != CUDA_SUCCESS) return fail(-3, "launch of the specialised rollout kernel failed (CUresult %d)", (int)cr);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e->last_variant = 2;
+    } else {
+        e->rollout_fn<<<grid, ROLLOUT_THREADS, 0, s>>>(A, Rg);
+        IMX_CHECK_LAUNCH("rollout_kernel");
+        e->last_variant = 0;
+    }
     if (write_state) { e->t = e->T; e->episode = episode; }
     return 0;
 }
@@ -727,4 +824,33 @@ extern "C" int imx_poisson_cdf(const imx_env* e, double* out, int cap) {
         for (int k = 0; k < (int)cdf.size() && k < cap; ++k) out[k] = cdf[k];
     }
     return e->cdf_len;
+}
+
+// --------------------------------------------------------------------------------------
+// kernel-variant introspection and the CPU-side check of the runtime-specialised build
+// --------------------------------------------------------------------------------------
+extern "C" int imx_kernel_variant(const imx_env* e) { return e ? e->last_variant : fail(-1, "null env"); }
+extern "C" const char* imx_jit_log(void) { return imxjit::g_last_log.c_str(); }
+
+extern "C" int imx_jit_compile_check(const imx_config* cfg, char* log, int cap) {
+    if (!cfg) return fail(-1, "null argument");
+    imx_env tmp;
+    tmp.cfg = *cfg;
+    const int rc = derive(&tmp);
+    if (rc) return rc;
+    compute_tile(&tmp);
+    int TL = 0;
+    build_tables(&tmp, &TL);
+    std::vector<std::string> defs;
+    std::string sn, rn, lg;
+    jit_spec(&tmp, TL, defs, sn, rn);
+    std::vector<char> cubin;
+    const size_t n = imxjit::compile_only(defs, sn, rn, lg, &cubin);
+    if (n > 0 && getenv("IMX_JIT_DUMP")) {              // for cuobjdump -sass inspection
+        FILE* f = fopen(getenv("IMX_JIT_DUMP"), "wb");
+        if (f) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }
+    }
+    if (log && cap > 0) { strncpy(log, lg.c_str(), (size_t)cap - 1); log[cap - 1] = 0; }
+    if (n == 0) return fail(-7, "runtime specialisation did not compile: %s", lg.substr(0, 300).c_str());
+    return (int)n;
 }

@@ -2,10 +2,37 @@
 // rollout kernels.  sm_100a only.
 #pragma once
 
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#else   // NVRTC has no system headers: the fixed-width types this code uses
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long uintptr_t;
+#endif
 
 #include "../../include/imx_b200.h"
+
+// Mode flags and sizes.  Ahead-of-time kernels read them from the kernel arguments (uniform
+// branches); the runtime-specialised build (imx_jit.cuh, NVRTC) defines IMX_JIT and injects every
+// one of them as a literal, so the compiler folds the branches and unrolls to the exact config.
+#ifdef IMX_JIT
+#define KF(name) (IMX_K_##name)
+#define KT(name) (IMX_KT_##name)
+#define KHAS(ptr) (IMX_K_has_##ptr)
+#define KBMA_POW2 (IMX_K_bma_pow2)
+#define KM_POW2 (IMX_K_m_pow2)
+#else
+#define KF(name) (A.name)
+#define KT(name) (TLY.name)
+#define KHAS(ptr) (A.ptr != nullptr)
+#define KBMA_POW2 (A.inv_bma != 0.0)
+#define KM_POW2 (A.inv_m != 0.0)
+#endif
 
 namespace imx {
 
@@ -68,6 +95,7 @@ struct StepArgs {
     int32_t noisy;             // consume the delay mask this episode
     int32_t has_carry;         // carry field allocated
     int32_t need_hd, need_ho;  // history state present
+    int32_t has_info;          // any imx_info_out pointer set
     int32_t wd_mult1, wd_mult;   // watchdog multipliers: LOOP1(A) and the other three
     double a, b, bma;          // bma = b - a
     double inv_bma;            // 1/(b-a) when b-a is a power of two (the division is then an exact scaling), else 0
@@ -112,10 +140,10 @@ __device__ __forceinline__ double rev_scale(double x, double vmax, double a, dou
 // order clipping: MAIM kinds round then clip (MAIM_env.py:344-347), IM kinds clip then round
 // (IM_env.py:300-302); rint() is round-half-to-even like np.round.
 __device__ __forceinline__ int decode_order(double x, double om, bool std_actions, bool multi, double a, double bma,
-                                            double inv_bma) {
+                                            double inv_bma, bool bma_pow2) {
     if (std_actions) {
         // dividing by a power of two is an exact exponent shift, so the multiply gives the same bits
-        if (inv_bma != 0.0) x = __dmul_rn(__dmul_rn(__dsub_rn(x, a), om), inv_bma);
+        if (bma_pow2) x = __dmul_rn(__dmul_rn(__dsub_rn(x, a), om), inv_bma);
         else x = rev_scale(x, om, a, bma);
     }
     if (multi) x = fmin(fmax(rint(x), 0.0), om);
@@ -127,14 +155,14 @@ __device__ __forceinline__ int decode_order(double x, double om, bool std_action
 // 2*max(demand_max) + children), so the host precomputes a + (v*(b-a))/max for every v with the same
 // IEEE operations and the kernel replaces an FP64 division by one cached 8-byte load.
 enum : int { TAB_INV = 0, TAB_ORD = 1, TAB_DEM = 2, TAB_PIPE2 = 3 };
-__device__ __forceinline__ double scaled(const double* __restrict__ tabrow, int TL, int which, int v, double vmax,
-                                         double a, double bma) {
-    if (tabrow) return __ldg(tabrow + which * TL + (int)min((unsigned)v, (unsigned)(TL - 1)));
+__device__ __forceinline__ double scaled(bool has_tab, const double* __restrict__ tabrow, int TL, int which, int v,
+                                         double vmax, double a, double bma) {
+    if (has_tab) return __ldg(tabrow + which * TL + (int)min((unsigned)v, (unsigned)(TL - 1)));
     return rescale((double)v, vmax, a, bma);
 }
 // mean of the shared reward: reward_sum / num_stages (MAIM_env.py:434)
-__device__ __forceinline__ double div_by_m(double s, int m, double inv_m) {
-    return inv_m != 0.0 ? __dmul_rn(s, inv_m) : __ddiv_rn(s, (double)m);
+__device__ __forceinline__ double div_by_m(double s, int m, double inv_m, bool m_pow2) {
+    return m_pow2 ? __dmul_rn(s, inv_m) : __ddiv_rn(s, (double)m);
 }
 // profit = p*ship - c*order - h*|inv' - target| - bc*backlog'           MAIM_env.py:421-424
 __device__ __forceinline__ double profit_of(double p, double c, double h, double bc, double target,

@@ -14,17 +14,17 @@ namespace imx {
 template <int DMAX, int PMAX>
 __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ StepArgs A, int div) {
     const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= A.N * A.m) return;
-    const int i = (int)(cell % A.m);
+    if (cell >= A.N * KF(m)) return;
+    const int i = (int)(cell % KF(m));
     const NodeParams np = load_node(A.nodes + i);
     A.inv[cell] = np.init_inv;
-    if (A.obs) {
+    if (KHAS(obs)) {
         int pipe[DMAX], hd[PMAX], ho[PMAX];
 #pragma unroll
         for (int k = 0; k < DMAX; ++k) pipe[k] = 0;
 #pragma unroll
         for (int j = 0; j < PMAX; ++j) { hd[j] = 0; ho[j] = 0; }
-        write_obs_row<DMAX, PMAX>(A.obs + cell * A.O, A, np, i, A.tab ? A.tab + (size_t)i * 4 * A.TL : nullptr, np.init_inv, 0, 0, pipe, hd, ho, div != 0);
+        write_obs_row<DMAX, PMAX>(A.obs + cell * KF(O), A, np, i, KHAS(tab) ? A.tab + (size_t)i * 4 * KF(TL) : nullptr, np.init_inv, 0, 0, pipe, hd, ho, div != 0);
     }
 }
 

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
     const int warp = threadIdx.x >> 5;
     const int i = lane % M_PAD;
     const int sub = lane / M_PAD;
-    const int m = A.m, T = A.T;
+    const int m = KF(m), T = KF(T);
     const bool stage_ok = i < m;
 
     const NodeParams np = load_node(A.nodes + (stage_ok ? i : 0));
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) bt[k] = 0;
         const double z = ok ? Rg.z[Rg.z_stride ? cell : (int64_t)i] : 0.0;
-        const int32_t* dem_row = (ok && Rg.demand && np.retailer_idx >= 0) ? Rg.demand + (n * A.R + np.retailer_idx) * T : nullptr;
+        const int32_t* dem_row = (ok && Rg.demand && np.retailer_idx >= 0) ? Rg.demand + (n * KF(R) + np.retailer_idx) * T : nullptr;
         double ret = 0.0;                 // "dfo_reward = 0; dfo_reward += r" (inv_management.py:223-231)
         double acc8[8];                   // np.sum(prob * rewards) accumulators (numpy pairwise order)
         double dfo_sum = 0.0;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
             // base_stock_policy: z - (inv + order_u - backlog), clipped to [0, order_max]  (base_restock_policy.py:12-20)
             const double inv_ech = __dsub_rn(__dadd_rn((double)inv, (double)order_u), (double)backlog);
             const double act = fmin(om_d, fmax(__dsub_rn(z, inv_ech), 0.0));
-            const int order = ok ? decode_order(act, om_d, A.std_actions != 0, A.multi != 0, A.a, A.bma, A.inv_bma) : 0;
+            const int order = ok ? decode_order(act, om_d, KF(std_actions) != 0, KF(multi) != 0, A.a, A.bma, A.inv_bma, KBMA_POW2) : 0;
 
             int cust = 0;
             if (ok && np.retailer_idx >= 0) cust = dem_row ? dem_row[t] : draw_demand(Rg.gen, n, np.retailer_idx, t);
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
 #pragma unroll
                 for (int k = 0; k < MAXC; ++k) {
                     od[k] = 0;
-                    if (k < A.maxc) {
+                    if (k < KF(maxc)) {
                         const int v = __shfl_sync(0xffffffffu, order, child_lane[k] < 0 ? 0 : child_lane[k], M_PAD);
                         od[k] = child_lane[k] < 0 ? 0 : v;
                         s += od[k];
@@ -109,13 +109,13 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
                 for (int k = 0; k < MAXC; ++k) st[k] = 0;
                 if (ok && np.nchild == 1) st[0] = ship;
                 if (ok && np.nchild > 1) {
-                    const int code = split_ship<MAXC>(np.nchild, ship, demand, backlog, np.demand_max, A.wd_mult1, A.wd_mult, od, bt, st);
+                    const int code = split_ship<MAXC>(np.nchild, ship, demand, backlog, np.demand_max, KF(wd_mult1), KF(wd_mult), od, bt, st);
                     if (code != 0 && err_code == 0) err_code = code;
                 }
                 incoming = order;
 #pragma unroll
                 for (int k = 0; k < MAXC; ++k) {
-                    if (k < A.maxc) {
+                    if (k < KF(maxc)) {
                         const int v = __shfl_sync(0xffffffffu, st[k], np.parent < 0 ? 0 : np.parent, M_PAD);
                         if (np.parent >= 0 && np.child_slot == k) incoming = v;
                     }
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
             }
 
             int backlog_new = backlog + demand - ship;
-            if (A.cap_backlog) backlog_new = min(backlog_new, np.demand_max);
+            if (KF(cap_backlog)) backlog_new = min(backlog_new, np.demand_max);
             order_u = min(max(order_u + order - acq, 0), np.inv_max);
             inv = min(max(inv + acq - ship, 0), np.inv_max);
             backlog = backlog_new;
@@ -138,11 +138,11 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
 
             const double profit = ok ? profit_of(np.p, np.c, np.h, np.bc, np.target, ship, order, inv, backlog) : 0.0;
             double r;
-            if (A.multi) r = A.independent ? profit : div_by_m(tile_seq_sum<M_PAD>(profit, m), m, A.inv_m);
+            if (KF(multi)) r = KF(independent) ? profit : div_by_m(tile_seq_sum<M_PAD>(profit, m), m, A.inv_m, KM_POW2);
             else r = tile_np_sum<M_PAD>(profit, m);
             ret = __dadd_rn(ret, r);
             if (ok && Rg.step_reward) {
-                if (A.multi) Rg.step_reward[(int64_t)t * A.N * m + cell] = r;
+                if (KF(multi)) Rg.step_reward[(int64_t)t * A.N * m + cell] = r;
                 else if (i == 0) Rg.step_reward[(int64_t)t * A.N + n] = r;
             }
             if (Rg.dfo && ok && i == 0) {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
         }
 
         if (ok) {
-            if (A.multi) Rg.ret[cell] = ret;
+            if (KF(multi)) Rg.ret[cell] = ret;
             else if (i == 0) Rg.ret[n] = ret;
             if (Rg.dfo && i == 0) {
                 if (T >= 8 && full8 == T)
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
                 A.inv[cell] = inv;
                 A.backlog[cell] = backlog;
                 A.order_u[cell] = order_u;
-                int32_t* pp = A.pipe + n * A.L + np.pipe_off;
+                int32_t* pp = A.pipe + n * KF(L) + np.pipe_off;
 #pragma unroll
                 for (int k = 0; k < DMAX; ++k)
                     if (k < np.delay) pp[k] = pipe[k];
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
                     if (np.bt_off >= 0) {
 #pragma unroll
                         for (int k = 0; k < MAXC; ++k)
-                            if (k < np.nchild) A.bt[n * A.NB + np.bt_off + k] = bt[k];
+                            if (k < np.nchild) A.bt[n * KF(NB) + np.bt_off + k] = bt[k];
                     }
                 }
             }

@@ -163,56 +163,56 @@ __device__ __forceinline__ void write_obs_row(double* row, const StepArgs& A, co
                                               const double* __restrict__ tabrow, int inv, int backlog, int order_u,
                                               const int (&pipe)[DMAX], const int (&hd)[PMAX], const int (&ho)[PMAX], bool div) {
     const double a = A.a, bma = A.bma;
-    const int TL = A.TL;
+    const int TL = KF(TL);
     const double inv_max = (double)np.inv_max, order_max = (double)np.order_max;
     const double dem_max = (double)np.demand_max;
-    const double ou_max = A.multi ? order_max : inv_max;   // MAIM_env.py:300 vs IM_env.py:265
-    if (A.std_state) {
-        row[0] = scaled(tabrow, TL, TAB_INV, inv, inv_max, a, bma);
-        row[1] = scaled(tabrow, TL, TAB_DEM, backlog, dem_max, a, bma);
-        row[2] = scaled(tabrow, TL, A.multi ? TAB_ORD : TAB_INV, order_u, ou_max, a, bma);
+    const double ou_max = KF(multi) ? order_max : inv_max;   // MAIM_env.py:300 vs IM_env.py:265
+    if (KF(std_state)) {
+        row[0] = scaled(KHAS(tab), tabrow, TL, TAB_INV, inv, inv_max, a, bma);
+        row[1] = scaled(KHAS(tab), tabrow, TL, TAB_DEM, backlog, dem_max, a, bma);
+        row[2] = scaled(KHAS(tab), tabrow, TL, KF(multi) ? TAB_ORD : TAB_INV, order_u, ou_max, a, bma);
     } else {
         row[0] = (double)inv;
         row[1] = (double)backlog;
         row[2] = (double)order_u;
     }
-    if (A.multi && !A.std_state) {
+    if (KF(multi) && !KF(std_state)) {
         // MAIM_env.py:319-324 (quirk 13): raw pipeline at [3:3+D] whatever the history offsets, rest stays 0
-        for (int k = 3; k < A.O; ++k) row[k] = 0.0;
-        if (A.td) {
+        for (int k = 3; k < KF(O); ++k) row[k] = 0.0;
+        if (KF(td)) {
 #pragma unroll
             for (int k = 0; k < DMAX; ++k)
-                if (k < A.D) row[3 + k] = (double)pipe[k];
+                if (k < KF(D)) row[3 + k] = (double)pipe[k];
         }
         return;
     }
     int k0 = 3;
-    if (A.pd) {
+    if (KF(pd)) {
 #pragma unroll
         for (int j = 0; j < PMAX; ++j)
-            if (j < A.P) row[k0 + j] = A.write_hd ? scaled(tabrow, TL, TAB_DEM, hd[j], dem_max, a, bma) : 0.0;   // quirk 2
-        k0 += A.P;
+            if (j < KF(P)) row[k0 + j] = KF(write_hd) ? scaled(KHAS(tab), tabrow, TL, TAB_DEM, hd[j], dem_max, a, bma) : 0.0;   // quirk 2
+        k0 += KF(P);
     }
-    if (A.pa) {
+    if (KF(pa)) {
 #pragma unroll
         for (int j = 0; j < PMAX; ++j)
-            if (j < A.P) row[k0 + j] = scaled(tabrow, TL, TAB_ORD, ho[j], order_max, a, bma);
-        k0 += A.P;
+            if (j < KF(P)) row[k0 + j] = scaled(KHAS(tab), tabrow, TL, TAB_ORD, ho[j], order_max, a, bma);
+        k0 += KF(P);
     }
-    if (A.td) {
+    if (KF(td)) {
 #pragma unroll
         for (int k = 0; k < DMAX; ++k) {
-            if (k < A.D) {
+            if (k < KF(D)) {
                 double v;
-                if (!A.std_state) v = (double)pipe[k];                                    // IM kinds, raw
-                else if (div && A.multi) v = scaled(tabrow, TL, TAB_PIPE2, min(pipe[k], 2 * np.inv_max), 2.0 * inv_max, a, bma);   // MAIM_div_env.py:408-411
-                else v = scaled(tabrow, TL, TAB_INV, pipe[k], inv_max, a, bma);
+                if (!KF(std_state)) v = (double)pipe[k];                                    // IM kinds, raw
+                else if (div && KF(multi)) v = scaled(KHAS(tab), tabrow, TL, TAB_PIPE2, min(pipe[k], 2 * np.inv_max), 2.0 * inv_max, a, bma);   // MAIM_div_env.py:408-411
+                else v = scaled(KHAS(tab), tabrow, TL, TAB_INV, pipe[k], inv_max, a, bma);
                 row[k0 + k] = v;
             }
         }
-        k0 += A.D;
+        k0 += KF(D);
     }
-    if (A.share_network) row[k0] = rescale((double)node_idx, (double)A.m, a, bma);       // MAIM_div_env.py:434-435
+    if (KF(share_network)) row[k0] = rescale((double)node_idx, (double)KF(m), a, bma);       // MAIM_div_env.py:434-435
 }
 
 // Flushes a warp's staged observation tile (`doubles` contiguous float64 values) to global memory.
@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
     const int warp = threadIdx.x >> 5;
     const int i = lane % M_PAD;                     // stage / node owned by this lane
     const int sub = lane / M_PAD;                   // env slot inside the warp
-    const bool stage_ok = i < A.m;
-    const int m = A.m, O = A.O;
+    const bool stage_ok = i < KF(m);
+    const int m = KF(m), O = KF(O);
 
     const NodeParams np = load_node(A.nodes + (stage_ok ? i : 0));
     int child_lane[MAXC];
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
     const bool is_last = (i == m - 1);
     const int delay_m1 = np.delay - 1;
     const double om_d = (double)np.order_max;
-    const double* __restrict__ tabrow = A.tab ? A.tab + (size_t)(stage_ok ? i : 0) * 4 * A.TL : nullptr;
+    const double* __restrict__ tabrow = KHAS(tab) ? A.tab + (size_t)(stage_ok ? i : 0) * 4 * KF(TL) : nullptr;
 
     const int tile_doubles = (EPW * m * O + 1) & ~1;             // keep every warp's tile 16-byte aligned
     double* wtile = smem_obs + (size_t)warp * tile_doubles;
@@ -279,34 +279,34 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
             inv = A.inv[cell];
             backlog = A.backlog[cell];
             order_u = A.order_u[cell];
-            const int32_t* pp = A.pipe + n * A.L + np.pipe_off;
+            const int32_t* pp = A.pipe + n * KF(L) + np.pipe_off;
 #pragma unroll
             for (int k = 0; k < DMAX; ++k)
                 if (k < np.delay) pipe[k] = pp[k];
-            if (A.need_hd) {
+            if (KF(need_hd)) {
 #pragma unroll
                 for (int j = 0; j < PMAX; ++j)
-                    if (j < A.P) hd[j] = A.hist_d[cell * A.P + j];
+                    if (j < KF(P)) hd[j] = A.hist_d[cell * KF(P) + j];
             }
-            if (A.need_ho) {
+            if (KF(need_ho)) {
 #pragma unroll
                 for (int j = 0; j < PMAX; ++j)
-                    if (j < A.P) ho[j] = A.hist_o[cell * A.P + j];
+                    if (j < KF(P)) ho[j] = A.hist_o[cell * KF(P) + j];
             }
-            if (np.retailer_idx >= 0) cust = A.demand_T[((int64_t)A.t * A.R + np.retailer_idx) * A.N + n];
-            if (A.has_carry) carry = A.carry[cell];
-            if (A.noisy) delayed = A.mask_T[((int64_t)A.t * A.N + n) * m + i] != 0;
+            if (np.retailer_idx >= 0) cust = A.demand_T[((int64_t)A.t * KF(R) + np.retailer_idx) * A.N + n];
+            if (KF(has_carry)) carry = A.carry[cell];
+            if (KF(noisy)) delayed = A.mask_T[((int64_t)A.t * A.N + n) * m + i] != 0;
             if constexpr (DIV) {
                 if (np.bt_off >= 0) {
 #pragma unroll
                     for (int k = 0; k < MAXC; ++k)
-                        if (k < np.nchild) bt[k] = A.bt[n * A.NB + np.bt_off + k];
+                        if (k < np.nchild) bt[k] = A.bt[n * KF(NB) + np.bt_off + k];
                 }
             }
         }
 
         // ---- order clipping ---------------------------------------------------------------
-        const int order = ok ? decode_order(act, om_d, A.std_actions != 0, A.multi != 0, A.a, A.bma, A.inv_bma) : 0;
+        const int order = ok ? decode_order(act, om_d, KF(std_actions) != 0, KF(multi) != 0, A.a, A.bma, A.inv_bma, KBMA_POW2) : 0;
 
         // ---- demand propagation -----------------------------------------------------------
         int demand;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
 #pragma unroll
             for (int k = 0; k < MAXC; ++k) {
                 od[k] = 0;
-                if (k < A.maxc) {
+                if (k < KF(maxc)) {
                     const int v = __shfl_sync(0xffffffffu, order, child_lane[k] < 0 ? 0 : child_lane[k], M_PAD);
                     od[k] = child_lane[k] < 0 ? 0 : v;
                     s += od[k];
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
         int carry_new = 0;
         if (A.t >= np.delay) {
             acq += pipe[0];
-            if (delayed && A.t < A.T - 1) { carry_new = acq; acq = 0; }
+            if (delayed && A.t < KF(T) - 1) { carry_new = acq; acq = 0; }
         }
 
         // ---- shipment and state update ----------------------------------------------------
@@ -346,11 +346,11 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
             for (int k = 0; k < MAXC; ++k) st[k] = 0;
             if (ok && np.nchild == 1) st[0] = ship;
             if (ok && np.nchild > 1)
-                err_code = split_ship<MAXC>(np.nchild, ship, demand, backlog, np.demand_max, A.wd_mult1, A.wd_mult, od, bt, st);
+                err_code = split_ship<MAXC>(np.nchild, ship, demand, backlog, np.demand_max, KF(wd_mult1), KF(wd_mult), od, bt, st);
             incoming = order;                                   // root: its own production order
 #pragma unroll
             for (int k = 0; k < MAXC; ++k) {
-                if (k < A.maxc) {
+                if (k < KF(maxc)) {
                     const int v = __shfl_sync(0xffffffffu, st[k], np.parent < 0 ? 0 : np.parent, M_PAD);
                     if (np.parent >= 0 && np.child_slot == k) incoming = v;
                 }
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
         }
 
         int backlog_new = backlog + demand - ship;
-        if (A.cap_backlog) backlog_new = min(backlog_new, np.demand_max);
+        if (KF(cap_backlog)) backlog_new = min(backlog_new, np.demand_max);
         const int order_u_new = min(max(order_u + order - acq, 0), np.inv_max);
         const int inv_new = min(max(inv + acq - ship, 0), np.inv_max);
         // shift the lead-time register by one period and insert this period's shipment at slot delay-1
@@ -379,9 +379,9 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
         // ---- reward -----------------------------------------------------------------------
         const double profit = ok ? profit_of(np.p, np.c, np.h, np.bc, np.target, ship, order, inv_new, backlog_new) : 0.0;
         double reward_out;
-        if (A.multi) {
-            if (A.independent) reward_out = profit;
-            else reward_out = div_by_m(tile_seq_sum<M_PAD>(profit, m), m, A.inv_m);
+        if (KF(multi)) {
+            if (KF(independent)) reward_out = profit;
+            else reward_out = div_by_m(tile_seq_sum<M_PAD>(profit, m), m, A.inv_m, KM_POW2);
         } else {
             reward_out = tile_np_sum<M_PAD>(profit, m);
         }
@@ -396,39 +396,41 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
             A.inv[cell] = inv_new;
             A.backlog[cell] = backlog_new;
             A.order_u[cell] = order_u_new;
-            int32_t* pp = A.pipe + n * A.L + np.pipe_off;
+            int32_t* pp = A.pipe + n * KF(L) + np.pipe_off;
 #pragma unroll
             for (int k = 0; k < DMAX; ++k)
                 if (k < np.delay) pp[k] = pipe[k];
-            if (A.need_hd) {
+            if (KF(need_hd)) {
 #pragma unroll
                 for (int j = 0; j < PMAX; ++j)
-                    if (j < A.P) A.hist_d[cell * A.P + j] = hd[j];
+                    if (j < KF(P)) A.hist_d[cell * KF(P) + j] = hd[j];
             }
-            if (A.need_ho) {
+            if (KF(need_ho)) {
 #pragma unroll
                 for (int j = 0; j < PMAX; ++j)
-                    if (j < A.P) A.hist_o[cell * A.P + j] = ho[j];
+                    if (j < KF(P)) A.hist_o[cell * KF(P) + j] = ho[j];
             }
-            if (A.has_carry) A.carry[cell] = carry_new;
+            if (KF(has_carry)) A.carry[cell] = carry_new;
             if constexpr (DIV) {
                 if (np.bt_off >= 0) {
 #pragma unroll
                     for (int k = 0; k < MAXC; ++k)
-                        if (k < np.nchild) A.bt[n * A.NB + np.bt_off + k] = bt[k];
+                        if (k < np.nchild) A.bt[n * KF(NB) + np.bt_off + k] = bt[k];
                 }
                 if (err_code != 0) A.err[n] = err_code;
             }
-            if (A.multi) A.reward[cell] = reward_out;
+            if (KF(multi)) A.reward[cell] = reward_out;
             else if (i == 0) A.reward[n] = reward_out;
-            if (A.info.demand_dev) A.info.demand_dev[cell] = demand;
-            if (A.info.ship_dev) A.info.ship_dev[cell] = ship;
-            if (A.info.acquisition_dev) A.info.acquisition_dev[cell] = acq;
-            if (A.info.order_dev) A.info.order_dev[cell] = order;
-            if (A.info.profit_dev) A.info.profit_dev[cell] = profit;
-            if (A.obs) write_obs_row<DMAX, PMAX>(wtile + (size_t)(sub * m + i) * O, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
+            if (KF(has_info)) {
+                if (A.info.demand_dev) A.info.demand_dev[cell] = demand;
+                if (A.info.ship_dev) A.info.ship_dev[cell] = ship;
+                if (A.info.acquisition_dev) A.info.acquisition_dev[cell] = acq;
+                if (A.info.order_dev) A.info.order_dev[cell] = order;
+                if (A.info.profit_dev) A.info.profit_dev[cell] = profit;
+            }
+            if (KHAS(obs)) write_obs_row<DMAX, PMAX>(wtile + (size_t)(sub * m + i) * O, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
         }
-        if (A.obs) {
+        if (KHAS(obs)) {
             const int64_t first = wt * EPW;
             const int envs_here = (int)min((int64_t)EPW, A.N - first);
             flush_obs_tile(A.obs + first * m * O, wtile, envs_here * m * O, lane);

@@ -68,48 +68,48 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_con
     const int lane = tid & 31;
     const int i = lane % M_PAD;                      // stage / node of this lane
     const int e_loc = tid / M_PAD;                   // env inside the tile
-    const int m = A.m, O = A.O, E = TLY.E;
+    const int m = KF(m), O = KF(O), E = KT(E);
     const bool ok = i < m;                            // full tiles only: every env slot is live
     const int cell = e_loc * m + i;                  // index inside a [E][m] tile
     const int64_t n0 = (int64_t)blockIdx.x * E;      // first env of the tile
 
-    double* s_act = reinterpret_cast<double*>(smem + TLY.off_act);
-    int32_t* s_inv = reinterpret_cast<int32_t*>(smem + TLY.off_inv);
-    int32_t* s_bl = reinterpret_cast<int32_t*>(smem + TLY.off_bl);
-    int32_t* s_ou = reinterpret_cast<int32_t*>(smem + TLY.off_ou);
-    int32_t* s_pipe = reinterpret_cast<int32_t*>(smem + TLY.off_pipe);
-    int32_t* s_hd = reinterpret_cast<int32_t*>(smem + TLY.off_hd);
-    int32_t* s_ho = reinterpret_cast<int32_t*>(smem + TLY.off_ho);
-    int32_t* s_carry = reinterpret_cast<int32_t*>(smem + TLY.off_carry);
-    int32_t* s_bt = reinterpret_cast<int32_t*>(smem + TLY.off_bt);
-    int32_t* s_dem = reinterpret_cast<int32_t*>(smem + TLY.off_dem);
-    double* s_obs = reinterpret_cast<double*>(smem + TLY.off_obs);
-    double* s_rew = reinterpret_cast<double*>(smem + TLY.off_rew);
+    double* s_act = reinterpret_cast<double*>(smem + KT(off_act));
+    int32_t* s_inv = reinterpret_cast<int32_t*>(smem + KT(off_inv));
+    int32_t* s_bl = reinterpret_cast<int32_t*>(smem + KT(off_bl));
+    int32_t* s_ou = reinterpret_cast<int32_t*>(smem + KT(off_ou));
+    int32_t* s_pipe = reinterpret_cast<int32_t*>(smem + KT(off_pipe));
+    int32_t* s_hd = reinterpret_cast<int32_t*>(smem + KT(off_hd));
+    int32_t* s_ho = reinterpret_cast<int32_t*>(smem + KT(off_ho));
+    int32_t* s_carry = reinterpret_cast<int32_t*>(smem + KT(off_carry));
+    int32_t* s_bt = reinterpret_cast<int32_t*>(smem + KT(off_bt));
+    int32_t* s_dem = reinterpret_cast<int32_t*>(smem + KT(off_dem));
+    double* s_obs = reinterpret_cast<double*>(smem + KT(off_obs));
+    double* s_rew = reinterpret_cast<double*>(smem + KT(off_rew));
 
     const uint32_t b_cell4 = (uint32_t)E * m * 4u, b_cell8 = (uint32_t)E * m * 8u;
-    const uint32_t b_pipe = (uint32_t)E * A.L * 4u, b_hist = b_cell4 * (uint32_t)A.P;
-    const uint32_t b_bt = (uint32_t)E * A.NB * 4u, b_dem = (uint32_t)E * 4u;
+    const uint32_t b_pipe = (uint32_t)E * KF(L) * 4u, b_hist = b_cell4 * (uint32_t)KF(P);
+    const uint32_t b_bt = (uint32_t)E * KF(NB) * 4u, b_dem = (uint32_t)E * 4u;
 
     if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (tid == 0) {
-        uint32_t bytes = b_cell8 + 3u * b_cell4 + b_pipe + (uint32_t)A.R * b_dem;
-        if (A.need_hd) bytes += b_hist;
-        if (A.need_ho) bytes += b_hist;
-        if (A.has_carry) bytes += b_cell4;
-        if (DIV && A.NB > 0) bytes += b_bt;
+        uint32_t bytes = b_cell8 + 3u * b_cell4 + b_pipe + (uint32_t)KF(R) * b_dem;
+        if (KF(need_hd)) bytes += b_hist;
+        if (KF(need_ho)) bytes += b_hist;
+        if (KF(has_carry)) bytes += b_cell4;
+        if (DIV && KF(NB) > 0) bytes += b_bt;
         mbar_expect_tx(&bar, bytes);
         bulk_load_g2s(s_act, A.actions + n0 * m, b_cell8, &bar);
         bulk_load_g2s(s_inv, A.inv + n0 * m, b_cell4, &bar);
         bulk_load_g2s(s_bl, A.backlog + n0 * m, b_cell4, &bar);
         bulk_load_g2s(s_ou, A.order_u + n0 * m, b_cell4, &bar);
-        bulk_load_g2s(s_pipe, A.pipe + n0 * A.L, b_pipe, &bar);
-        if (A.need_hd) bulk_load_g2s(s_hd, A.hist_d + n0 * m * A.P, b_hist, &bar);
-        if (A.need_ho) bulk_load_g2s(s_ho, A.hist_o + n0 * m * A.P, b_hist, &bar);
-        if (A.has_carry) bulk_load_g2s(s_carry, A.carry + n0 * m, b_cell4, &bar);
-        if (DIV && A.NB > 0) bulk_load_g2s(s_bt, A.bt + n0 * A.NB, b_bt, &bar);
-        for (int r = 0; r < A.R; ++r)
-            bulk_load_g2s(s_dem + r * E, A.demand_T + ((int64_t)A.t * A.R + r) * A.N + n0, b_dem, &bar);
+        bulk_load_g2s(s_pipe, A.pipe + n0 * KF(L), b_pipe, &bar);
+        if (KF(need_hd)) bulk_load_g2s(s_hd, A.hist_d + n0 * m * KF(P), b_hist, &bar);
+        if (KF(need_ho)) bulk_load_g2s(s_ho, A.hist_o + n0 * m * KF(P), b_hist, &bar);
+        if (KF(has_carry)) bulk_load_g2s(s_carry, A.carry + n0 * m, b_cell4, &bar);
+        if (DIV && KF(NB) > 0) bulk_load_g2s(s_bt, A.bt + n0 * KF(NB), b_bt, &bar);
+        for (int r = 0; r < KF(R); ++r)
+            bulk_load_g2s(s_dem + r * E, A.demand_T + ((int64_t)A.t * KF(R) + r) * A.N + n0, b_dem, &bar);
     }
 
     // per-lane constants (overlaps the bulk loads)
@@ -123,9 +123,9 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_con
     const bool is_last = (i == m - 1);
     const int delay_m1 = np.delay - 1;
     const double om_d = (double)np.order_max;
-    const double* __restrict__ tabrow = A.tab ? A.tab + (size_t)(ok ? i : 0) * 4 * A.TL : nullptr;
+    const double* __restrict__ tabrow = KHAS(tab) ? A.tab + (size_t)(ok ? i : 0) * 4 * KF(TL) : nullptr;
     bool delayed = false;
-    if (A.noisy && ok) delayed = A.mask_T[((int64_t)A.t * A.N + n0 + e_loc) * m + i] != 0;
+    if (KF(noisy) && ok) delayed = A.mask_T[((int64_t)A.t * A.N + n0 + e_loc) * m + i] != 0;
 
     mbar_wait(&bar, 0);
 
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_con
     for (int j = 0; j < PMAX; ++j) { hd[j] = 0; ho[j] = 0; }
 #pragma unroll
     for (int k = 0; k < MAXC; ++k) bt[k] = 0;
-    int32_t* my_pipe = s_pipe + e_loc * A.L + np.pipe_off;
+    int32_t* my_pipe = s_pipe + e_loc * KF(L) + np.pipe_off;
     if (ok) {
         act = s_act[cell];
         inv = s_inv[cell];
@@ -148,29 +148,29 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_con
 #pragma unroll
         for (int k = 0; k < DMAX; ++k)
             if (k < np.delay) pipe[k] = my_pipe[k];
-        if (A.need_hd) {
+        if (KF(need_hd)) {
 #pragma unroll
             for (int j = 0; j < PMAX; ++j)
-                if (j < A.P) hd[j] = s_hd[cell * A.P + j];
+                if (j < KF(P)) hd[j] = s_hd[cell * KF(P) + j];
         }
-        if (A.need_ho) {
+        if (KF(need_ho)) {
 #pragma unroll
             for (int j = 0; j < PMAX; ++j)
-                if (j < A.P) ho[j] = s_ho[cell * A.P + j];
+                if (j < KF(P)) ho[j] = s_ho[cell * KF(P) + j];
         }
         if (np.retailer_idx >= 0) cust = s_dem[np.retailer_idx * E + e_loc];
-        if (A.has_carry) carry = s_carry[cell];
+        if (KF(has_carry)) carry = s_carry[cell];
         if constexpr (DIV) {
             if (np.bt_off >= 0) {
 #pragma unroll
                 for (int k = 0; k < MAXC; ++k)
-                    if (k < np.nchild) bt[k] = s_bt[e_loc * A.NB + np.bt_off + k];
+                    if (k < np.nchild) bt[k] = s_bt[e_loc * KF(NB) + np.bt_off + k];
             }
         }
     }
 
     // ---- one period (identical arithmetic to step_kernel) --------------------------------------
-    const int order = ok ? decode_order(act, om_d, A.std_actions != 0, A.multi != 0, A.a, A.bma, A.inv_bma) : 0;
+    const int order = ok ? decode_order(act, om_d, KF(std_actions) != 0, KF(multi) != 0, A.a, A.bma, A.inv_bma, KBMA_POW2) : 0;
     int demand;
     int od[MAXC];
     if constexpr (DIV) {
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_con
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
             od[k] = 0;
-            if (k < A.maxc) {
+            if (k < KF(maxc)) {
                 const int v = __shfl_sync(0xffffffffu, order, child_lane[k] < 0 ? 0 : child_lane[k], M_PAD);
                 od[k] = child_lane[k] < 0 ? 0 : v;
                 s += od[k];
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_con
     int carry_new = 0;
     if (A.t >= np.delay) {
         acq += pipe[0];
-        if (delayed && A.t < A.T - 1) { carry_new = acq; acq = 0; }
+        if (delayed && A.t < KF(T) - 1) { carry_new = acq; acq = 0; }
     }
     const int ship = min(backlog + demand, inv + acq);
     int incoming;
@@ -204,11 +204,11 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_con
         for (int k = 0; k < MAXC; ++k) st[k] = 0;
         if (ok && np.nchild == 1) st[0] = ship;
         if (ok && np.nchild > 1)
-            err_code = split_ship<MAXC>(np.nchild, ship, demand, backlog, np.demand_max, A.wd_mult1, A.wd_mult, od, bt, st);
+            err_code = split_ship<MAXC>(np.nchild, ship, demand, backlog, np.demand_max, KF(wd_mult1), KF(wd_mult), od, bt, st);
         incoming = order;
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
-            if (k < A.maxc) {
+            if (k < KF(maxc)) {
                 const int v = __shfl_sync(0xffffffffu, st[k], np.parent < 0 ? 0 : np.parent, M_PAD);
                 if (np.parent >= 0 && np.child_slot == k) incoming = v;
             }
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_con
         incoming = is_last ? order : up;
     }
     int backlog_new = backlog + demand - ship;
-    if (A.cap_backlog) backlog_new = min(backlog_new, np.demand_max);
+    if (KF(cap_backlog)) backlog_new = min(backlog_new, np.demand_max);
     const int order_u_new = min(max(order_u + order - acq, 0), np.inv_max);
     const int inv_new = min(max(inv + acq - ship, 0), np.inv_max);
 #pragma unroll
@@ -233,9 +233,9 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_con
 
     const double profit = ok ? profit_of(np.p, np.c, np.h, np.bc, np.target, ship, order, inv_new, backlog_new) : 0.0;
     double reward_out;
-    if (A.multi) {
-        if (A.independent) reward_out = profit;
-        else reward_out = div_by_m(tile_seq_sum<M_PAD>(profit, m), m, A.inv_m);
+    if (KF(multi)) {
+        if (KF(independent)) reward_out = profit;
+        else reward_out = div_by_m(tile_seq_sum<M_PAD>(profit, m), m, A.inv_m, KM_POW2);
     } else {
         reward_out = tile_np_sum<M_PAD>(profit, m);
     }
@@ -248,35 +248,37 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_con
 #pragma unroll
         for (int k = 0; k < DMAX; ++k)
             if (k < np.delay) my_pipe[k] = pipe[k];
-        if (A.need_hd) {
+        if (KF(need_hd)) {
 #pragma unroll
             for (int j = 0; j < PMAX; ++j)
-                if (j < A.P) s_hd[cell * A.P + j] = hd[j];
+                if (j < KF(P)) s_hd[cell * KF(P) + j] = hd[j];
         }
-        if (A.need_ho) {
+        if (KF(need_ho)) {
 #pragma unroll
             for (int j = 0; j < PMAX; ++j)
-                if (j < A.P) s_ho[cell * A.P + j] = ho[j];
+                if (j < KF(P)) s_ho[cell * KF(P) + j] = ho[j];
         }
-        if (A.has_carry) s_carry[cell] = carry_new;
+        if (KF(has_carry)) s_carry[cell] = carry_new;
         if constexpr (DIV) {
             if (np.bt_off >= 0) {
 #pragma unroll
                 for (int k = 0; k < MAXC; ++k)
-                    if (k < np.nchild) s_bt[e_loc * A.NB + np.bt_off + k] = bt[k];
+                    if (k < np.nchild) s_bt[e_loc * KF(NB) + np.bt_off + k] = bt[k];
             }
             if (err_code != 0) A.err[n0 + e_loc] = err_code;
         }
-        if (A.multi) s_rew[cell] = reward_out;
+        if (KF(multi)) s_rew[cell] = reward_out;
         else if (i == 0) s_rew[e_loc] = reward_out;
-        if (A.obs) write_obs_row<DMAX, PMAX>(s_obs + (size_t)cell * O, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
+        if (KHAS(obs)) write_obs_row<DMAX, PMAX>(s_obs + (size_t)cell * O, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
         // optional diagnostics go straight to global memory (off the fast path)
+        if (KF(has_info)) {
         const int64_t gcell = (n0 + e_loc) * m + i;
         if (A.info.demand_dev) A.info.demand_dev[gcell] = demand;
         if (A.info.ship_dev) A.info.ship_dev[gcell] = ship;
         if (A.info.acquisition_dev) A.info.acquisition_dev[gcell] = acq;
         if (A.info.order_dev) A.info.order_dev[gcell] = order;
         if (A.info.profit_dev) A.info.profit_dev[gcell] = profit;
+        }
     }
     fence_proxy_async_smem();          // every writer orders its generic-proxy stores before the bulk copies
     __syncthreads();
@@ -284,13 +286,13 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_con
         bulk_store_only(A.inv + n0 * m, s_inv, b_cell4);
         bulk_store_only(A.backlog + n0 * m, s_bl, b_cell4);
         bulk_store_only(A.order_u + n0 * m, s_ou, b_cell4);
-        bulk_store_only(A.pipe + n0 * A.L, s_pipe, b_pipe);
-        if (A.need_hd) bulk_store_only(A.hist_d + n0 * m * A.P, s_hd, b_hist);
-        if (A.need_ho) bulk_store_only(A.hist_o + n0 * m * A.P, s_ho, b_hist);
-        if (A.has_carry) bulk_store_only(A.carry + n0 * m, s_carry, b_cell4);
-        if (DIV && A.NB > 0) bulk_store_only(A.bt + n0 * A.NB, s_bt, b_bt);
-        if (A.obs) bulk_store_only(A.obs + n0 * m * O, s_obs, b_cell8 * (uint32_t)O);
-        bulk_store_only(A.reward + (A.multi ? n0 * m : n0), s_rew, A.multi ? b_cell8 : (uint32_t)E * 8u);
+        bulk_store_only(A.pipe + n0 * KF(L), s_pipe, b_pipe);
+        if (KF(need_hd)) bulk_store_only(A.hist_d + n0 * m * KF(P), s_hd, b_hist);
+        if (KF(need_ho)) bulk_store_only(A.hist_o + n0 * m * KF(P), s_ho, b_hist);
+        if (KF(has_carry)) bulk_store_only(A.carry + n0 * m, s_carry, b_cell4);
+        if (DIV && KF(NB) > 0) bulk_store_only(A.bt + n0 * KF(NB), s_bt, b_bt);
+        if (KHAS(obs)) bulk_store_only(A.obs + n0 * m * O, s_obs, b_cell8 * (uint32_t)O);
+        bulk_store_only(A.reward + (KF(multi) ? n0 * m : n0), s_rew, KF(multi) ? b_cell8 : (uint32_t)E * 8u);
         bulk_commit();
         bulk_wait_read_all();            // shared memory must outlive the bulk engine's reads
     }

@@ -84,3 +84,38 @@ def test_host_helpers():
         topology.check_connections({0: [1], 1: [0]})
     b = Box(low=np.ones(3) * -1, high=np.ones(3), dtype=np.float64, shape=(np.int8(3),))
     assert b.shape == (3,) and isinstance(b.shape[0], int) and b.contains(np.zeros(3))
+
+
+def _raw_config(kind, cfg, N=65536):
+    import numpy as np
+    c = _lib.ImxConfig()
+    div = kind.endswith("div")
+    m = cfg.get("num_nodes", cfg.get("num_stages"))
+    c.kind, c.num_nodes, c.num_periods, c.prev_length = _lib.KIND[kind], m, 30, cfg["prev_length"]
+    c.time_dependency, c.prev_demand, c.prev_actions = int(cfg["time_dependency"]), int(cfg["prev_demand"]), int(cfg["prev_actions"])
+    c.standardise_state, c.standardise_actions = int(cfg.get("standardise_state", True)), int(cfg.get("standardise_actions", True))
+    c.independent, c.a, c.b, c.num_envs, c.demand_dist, c.mu = int(cfg.get("independent", False)), -1.0, 1.0, N, 1, 5.0
+    for i in range(m):
+        c.inv_init[i], c.inv_max[i], c.order_max[i], c.delay[i] = 10, 30, 30, int(cfg["delay"][i])
+        c.stock_cost[i], c.backlog_cost[i] = float(cfg["stock_cost"][i]), float(cfg["backlog_cost"][i])
+    if div:
+        for p, ch in cfg["connections"].items():
+            c.num_children[p] = len(ch)
+            for k, v in enumerate(ch):
+                c.children[p][k] = v
+    else:
+        for i in range(m + 1):
+            c.price[i] = float(cfg["price"][i])
+    return c
+
+
+def test_runtime_specialisation_compiles_for_sm100a_without_gpu():
+    """NVRTC builds the specialised kernels from csrc/*.cuh for sm_100a on the CPU box (no launch)."""
+    from marl_for_im_b200 import presets
+    lib = _lib.load()
+    for kind, cfg in (("MAIM", presets.serial4()), ("MAIM", presets.serial8()), ("IM", presets.serial4_dfo()),
+                      ("MAIM_div", presets.div1()), ("IM_div", presets.div2(prev_actions=True, prev_length=2))):
+        c = _raw_config(kind, cfg)
+        buf = ctypes.create_string_buffer(8192)
+        n = lib.imx_jit_compile_check(ctypes.byref(c), buf, 8192)
+        assert n > 10000, (kind, n, buf.value.decode()[:500], lib.imx_last_error())

@@ -124,3 +124,39 @@ def test_both_step_paths_agree(monkeypatch):
         else:
             monkeypatch.setenv("IMX_STEP_PATH", path)
         assert_same(want, run_cuda("MAIM", cfg, demand, actions, n_copies=n), f"path={path} N={n}")
+
+
+def test_runtime_specialised_kernels_match(monkeypatch):
+    """IMX_JIT=1 forces the NVRTC-specialised build of the same kernel sources; it must be the one
+    that runs (kernel variant 2) and give the same bytes as the oracle."""
+    from marl_for_im_b200.envs import ENV_CLASSES
+    from harness import copy_config
+    monkeypatch.setenv("IMX_JIT", "1")
+    rng = np.random.default_rng(2024)
+    cases = [("MAIM", presets.serial4()), ("MAIM", presets.serial8(prev_actions=True, prev_length=3, independent=True)),
+             ("IM", presets.serial4(time_dependency=False, prev_actions=True)), ("MAIM", presets.serial2()),
+             ("IM", presets.serial4_dfo()), ("MAIM_div", presets.div1()), ("MAIM_div", presets.div2(share_network=True, prev_actions=True)),
+             ("IM_div", presets.div2(prev_length=2))]
+    for kind, cfg in cases:
+        amode = "near_eq" if kind.endswith("div") else "uniform"
+        demand, actions = random_case(kind, cfg, rng, mu=6, action_mode=amode)
+        want = run_oracle(kind, cfg, demand, actions)
+        # through the public env API, without info buffers (the specialised kernel serves the plain step)
+        c = copy_config(cfg)
+        c.update(num_envs=128, return_info=False)
+        env = ENV_CLASSES[kind](c)
+        d = np.broadcast_to(np.asarray(demand)[None], (128,) + np.asarray(demand).shape)
+        o = env.reset(customer_demand=d)
+        multi = kind.startswith("MAIM")
+        for t in range(env.num_periods):
+            a = torch.as_tensor(np.broadcast_to(actions[t][None], (128, env.num_nodes)).copy(), device="cuda:0")
+            o, r, done, _ = env.step(a)
+            assert env._lib.imx_kernel_variant(env._handle) == 2, env._lib.imx_jit_log()
+            got_o = (torch.stack([o[n] for n in env.agent_names], dim=1) if multi else o).cpu().numpy()
+            got_r = (torch.stack([r[n] for n in env.agent_names], dim=1) if multi else r[:, None]).cpu().numpy()
+            for n in (0, 63, 64, 127):
+                np.testing.assert_array_equal(got_o[n], want["obs"][t + 1], err_msg=f"{kind} obs t={t}")
+                np.testing.assert_array_equal(got_r[n, :got_r.shape[1]], want["reward"][t, :got_r.shape[1]], err_msg=f"{kind} reward t={t}")
+        st = env.state_dict()
+        np.testing.assert_array_equal(st["inv"][5].cpu().numpy(), want["inv"][-1])
+        np.testing.assert_array_equal(st["backlog"][77].cpu().numpy(), want["backlog"][-1])
