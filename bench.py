@@ -32,7 +32,11 @@ import numpy as np  # noqa: E402
 
 T_PERIODS = 30
 M_STAGES = 4
+KERNEL_VARIANTS = {0: "imx::step_kernel (ahead-of-time, direct global accesses)",
+                   1: "imx::step_kernel_tma (ahead-of-time, TMA-staged tiles)",
+                   2: "imx::step_kernel_tma<4,3,1,1,false> (NVRTC-specialised, TMA-staged tiles)"}
 ENVS_PER_GPU = 65536
+NCU_TRAFFIC_BYTES_65536 = 8402944        # dram__bytes_read.sum + dram__bytes_write.sum, one launch, see profiles/
 WORKLOAD = ("MAIM_env 4-stage serial, MA_6 obs mode (td=T,pd=T,pa=F,P=1, shared reward), step() on "
             "65536 envs per GPU, 30-period episodes, replayed Poisson(5) demand, uniform(-1,1) actions pre-staged")
 
@@ -64,7 +68,7 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(episodes_per_worker=120, pool=None):
+def cpu_baseline(episodes_per_worker=1000, pool=None):
     """agent-steps/s of the oracle port with one process per host core (bounded sample)."""
     import multiprocessing as mp
     cores = host_cores()
@@ -320,7 +324,9 @@ def run_ours(args):
     dt = timed_replays(g_steps, reps, torch) / (reps * T)
     achieved = B * N / dt / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "imx::step_kernel<4,4,1,1,false>", "us_per_launch": dt * 1e6,
+                "traffic": NCU_TRAFFIC_BYTES_65536 if N == ENVS_PER_GPU else None,
+                "traffic_source": "profiles/r1_ncu_step_kernel_tma_specialised.txt (ncu --set full: dram__bytes_read+write per launch; "
+                                  "the 31 MB working set of one launch is L2-resident, hence traffic << algorithmic bytes)", "kernel": KERNEL_VARIANTS[env._lib.imx_kernel_variant(env._handle)], "us_per_launch": dt * 1e6,
                 "algorithmic_bytes_per_env_step": B, "envs_per_launch": N, "peak_source": peak_src,
                 "note": "per-launch time = steps-only graph of 30 dependent launches / 30 (includes inter-kernel gaps)"}
 
@@ -348,7 +354,7 @@ def run_ours(args):
                        "timing": "CUDA events around K CUDA-graph replays (reset + 30 step launches) + per-episode return statistics"
                                  + (" + 1 NCCL all-reduce" if world > 1 else "") + ", max over ranks"},
             "roofline": roofline, "roofline_large_n": roof_large, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches_per_episode * args.steps + args.steps),
+            "gpu_launches": int((launches_per_episode + 2) * args.steps),
             "clocks": clocks,
             "episode_stats": {"n": float(stats_buf[-1][0].item()), "mean_return": float((stats_buf[-1][1] / stats_buf[-1][0]).item())},
         }

@@ -78,6 +78,7 @@ struct imx_env {
     uint8_t* d_mask_T = nullptr;
     double* d_cdf = nullptr;
     int cdf_len = 0;
+    double* d_stats_partial = nullptr;   // [2 + 2m][STATS_BLOCKS] scratch of imx_return_stats
     double* d_tab = nullptr;             // [m][4][TL] rescale tables
     int TL = 0;
     // host-call staging (allocated on first use)
@@ -529,6 +530,7 @@ extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
             IMX_CREATE_CUDA(cudaMemcpy(e->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
         }
     }
+    IMX_CREATE_CUDA(cudaMalloc(&e->d_stats_partial, (size_t)(2 + 2 * IMX_MAX_NODES) * STATS_BLOCKS * sizeof(double)));
     // reset state with an all-zero demand trace (the reference constructors end with self.reset())
     IMX_CREATE_CUDA(cudaMemset(e->d_demand_T, 0, dem_bytes));
     IMX_CREATE_CUDA(cudaMemset(e->d_state, 0, total ? total : 256));
@@ -554,7 +556,7 @@ extern "C" int imx_destroy(imx_env* e) {
     cudaSetDevice(e->cfg.device);
     if (e->hstream) { cudaStreamSynchronize(e->hstream); cudaStreamDestroy(e->hstream); }
     cudaFree(e->d_nodes); cudaFree(e->d_children); cudaFree(e->d_state); cudaFree(e->d_err);
-    cudaFree(e->d_demand_T); cudaFree(e->d_mask_T); cudaFree(e->d_cdf); cudaFree(e->d_tab);
+    cudaFree(e->d_demand_T); cudaFree(e->d_mask_T); cudaFree(e->d_cdf); cudaFree(e->d_tab); cudaFree(e->d_stats_partial);
     cudaFree(e->d_act_h); cudaFree(e->d_obs_h); cudaFree(e->d_rew_h); cudaFree(e->d_dem_h); cudaFree(e->d_mask_h);
     delete e;
     return 0;
@@ -758,8 +760,12 @@ extern "C" int imx_rollout_basestock(imx_env* e, const double* z_dev, int z_stri
 extern "C" int imx_return_stats(imx_env* e, const double* return_dev, double* stats_dev, void* stream) {
     if (!e || !return_dev || !stats_dev) return fail(-1, "null argument");
     IMX_CUDA(cudaSetDevice(e->cfg.device));
-    return_stats_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(return_dev, stats_dev, e->N, e->multi ? e->m : 1, e->multi ? 1 : 0);
-    IMX_CHECK_LAUNCH("return_stats_kernel");
+    const int cols = e->multi ? e->m : 1;
+    const int nstat = e->multi ? 2 + 2 * cols : 2;
+    return_stats_partial_kernel<<<dim3(STATS_BLOCKS, nstat), STATS_THREADS, 0, (cudaStream_t)stream>>>(return_dev, e->d_stats_partial, e->N, cols);
+    IMX_CHECK_LAUNCH("return_stats_partial_kernel");
+    return_stats_final_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(e->d_stats_partial, stats_dev, e->N, nstat);
+    IMX_CHECK_LAUNCH("return_stats_final_kernel");
     return 0;
 }
 

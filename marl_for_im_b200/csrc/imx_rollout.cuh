@@ -192,34 +192,51 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
 }
 
 // Episode statistics [n, Σ total, Σ total², then per agent (Σ, Σ²)] in a fixed, deterministic
-// order: one block, each thread strides over envs, then a shared-memory tree.  The per-env total
-// of a MAIM kind is the sum over agents in agent order.
-__global__ void __launch_bounds__(1024) return_stats_kernel(const double* __restrict__ ret, double* __restrict__ stats,
-                                                            int64_t N, int cols, int multi) {
-    __shared__ double red[1024];
-    const int nstat = multi ? 2 + 2 * cols : 2;
-    for (int q = 0; q < nstat; ++q) {
-        double acc = 0.0;
-        for (int64_t n = threadIdx.x; n < N; n += blockDim.x) {
-            double v;
-            if (q < 2) {
-                v = 0.0;
-                for (int c = 0; c < cols; ++c) v += ret[n * cols + c];
-            } else {
-                v = ret[n * cols + (q - 2) / 2];
-            }
-            acc += (q & 1) ? v * v : v;
-        }
-        red[threadIdx.x] = acc;
-        __syncthreads();
-        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-            if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) stats[1 + q] = red[0];
+// order (the payload of the single cross-GPU all-reduce).  Two stages: STATS_BLOCKS x nstat blocks
+// each reduce one statistic over a fixed slice of the envs (strided threads + shared-memory tree),
+// then one block per statistic adds the STATS_BLOCKS partials in index order.  The grid is a
+// constant, so the result depends only on N, never on the device.  The per-env total of a MAIM kind
+// is the sum over agents in agent order.
+constexpr int STATS_BLOCKS = 128;
+constexpr int STATS_THREADS = 256;
+
+__device__ __forceinline__ double stats_value(const double* __restrict__ ret, int64_t n, int cols, int q) {
+    double v;
+    if (q < 2) {
+        v = 0.0;
+        for (int c = 0; c < cols; ++c) v += ret[n * cols + c];
+    } else {
+        v = ret[n * cols + (q - 2) / 2];
+    }
+    return (q & 1) ? v * v : v;
+}
+
+__global__ void __launch_bounds__(STATS_THREADS) return_stats_partial_kernel(const double* __restrict__ ret, double* __restrict__ partial,
+                                                                             int64_t N, int cols) {
+    __shared__ double red[STATS_THREADS];
+    const int q = blockIdx.y;
+    const int64_t per_block = (N + STATS_BLOCKS - 1) / STATS_BLOCKS;
+    const int64_t lo = (int64_t)blockIdx.x * per_block;
+    const int64_t hi = lo + per_block < N ? lo + per_block : N;
+    double acc = 0.0;
+    for (int64_t n = lo + threadIdx.x; n < hi; n += STATS_THREADS) acc += stats_value(ret, n, cols, q);
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = STATS_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) stats[0] = (double)N;
+    if (threadIdx.x == 0) partial[q * STATS_BLOCKS + blockIdx.x] = red[0];
+}
+
+__global__ void return_stats_final_kernel(const double* __restrict__ partial, double* __restrict__ stats, int64_t N, int nstat) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) stats[0] = (double)N;
+    if (q < nstat) {
+        double acc = 0.0;
+        for (int b = 0; b < STATS_BLOCKS; ++b) acc += partial[q * STATS_BLOCKS + b];
+        stats[1 + q] = acc;
+    }
 }
 
 }  // namespace imx
