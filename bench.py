@@ -89,6 +89,26 @@ def cpu_baseline(episodes_per_worker=1000, pool=None):
                       f"MA_6 workload through oracle/im_oracle.py (one env per process, like the reference); {wall:.2f} s wall"}
 
 
+def cpu_baseline_c():
+    """The plain-C restatement (oracle/imx_oracle.c) with all OpenMP threads on the full 65536-env
+    episode: the strongest CPU implementation of the same path we can offer, for context."""
+    from marl_for_im_b200 import presets
+    from oracle import c_oracle
+    N, T, m = ENVS_PER_GPU, T_PERIODS, M_STAGES
+    demand = np.random.default_rng(420).poisson(5, size=(N, T)).astype(np.int32)
+    actions = np.random.default_rng(0).uniform(-1, 1, size=(T, N, m))
+    co = c_oracle.COracle("MAIM", presets.serial4())
+    co.run(demand[:1024], actions[:, :1024])               # warm-up
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        co.run(demand, actions)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": N * T * m / best, "unit": "agent-steps/s", "cores": c_oracle.max_threads(), "kind": "port (plain C, OpenMP)",
+            "sample": f"full config-2 episode batch ({N} envs x {T} periods), best of 3, {best * 1e3:.1f} ms"}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU design (per-env Python/numpy objects), restated by the
     oracle port because the reference tree cannot travel to the GPU box; all host cores."""
@@ -225,9 +245,13 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    cpu = None
+    cpu = cpu_c = None
     if world == 1 and not args.skip_cpu:
         cpu = cpu_baseline()                       # before CUDA is initialised (fork-safe)
+        try:
+            cpu_c = cpu_baseline_c()
+        except Exception as exc:
+            cpu_c = {"error": str(exc)[:200]}
 
     import torch
     import torch.distributed as dist
@@ -353,7 +377,7 @@ def run_ours(args):
                               f"({(T * N * m * (2 + O) * 8) / 1e6:.0f} MB > 126 MB L2); the {env.state_words * 4 * N / 1e6:.1f} MB state stays cached by design"),
                        "timing": "CUDA events around K CUDA-graph replays (reset + 30 step launches) + per-episode return statistics"
                                  + (" + 1 NCCL all-reduce" if world > 1 else "") + ", max over ranks"},
-            "roofline": roofline, "roofline_large_n": roof_large, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "roofline_large_n": roof_large, "cpu_baseline": cpu, "cpu_baseline_c": cpu_c, "e2e": e2e,
             "gpu_launches": int((launches_per_episode + 2) * args.steps),
             "clocks": clocks,
             "episode_stats": {"n": float(stats_buf[-1][0].item()), "mean_return": float((stats_buf[-1][1] / stats_buf[-1][0]).item())},

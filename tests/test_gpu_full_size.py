@@ -1,0 +1,93 @@
+"""Full BASELINE sizes on the GPU against the plain-C oracle (every env, every period's reward,
+final observation and final integer state, bit for bit) plus size-independent invariants."""
+import numpy as np
+import pytest
+import torch
+
+from marl_for_im_b200 import presets
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_gpu(cls, cfg, demand, actions):
+    N, T = demand.shape[0], actions.shape[0]
+    env = cls(dict(cfg, num_envs=N, reuse_buffers=False))
+    env.reset(customer_demand=demand)
+    a_dev = torch.as_tensor(actions, device="cuda:0")
+    rewards = []
+    for t in range(T):
+        o, r, done, _ = env.step(a_dev[t])
+        rewards.append(torch.stack([r[n] for n in env.agent_names], dim=1) if env.MULTI else r[:, None])
+    obs_last = torch.stack([o[n] for n in env.agent_names], dim=1) if env.MULTI else o
+    assert (done["__all__"] if env.MULTI else done)
+    st = {k: v.cpu().numpy() for k, v in env.state_dict().items()}
+    return obs_last.cpu().numpy(), torch.stack(rewards).cpu().numpy(), st, env
+
+
+def test_config2_maim4_65536_envs_bit_exact():
+    from marl_for_im_b200.envs import MultiAgentInvManagement
+    cfg = presets.serial4()
+    N, T, m = 65536, 30, 4
+    demand = np.random.default_rng(420).poisson(5, size=(N, T)).astype(np.int32)
+    actions = np.random.default_rng(0).uniform(-1, 1, size=(T, N, m))
+    obs, rew, st, env = _run_gpu(MultiAgentInvManagement, cfg, demand, actions)
+    assert env._lib.imx_kernel_variant(env._handle) == 2          # the runtime-specialised TMA kernel served it
+    want = c_oracle.COracle("MAIM", cfg).run(demand, actions)
+    np.testing.assert_array_equal(obs, want["obs_last"])
+    np.testing.assert_array_equal(rew, want["reward"])
+    for k in ("inv", "backlog", "order_u", "pipe"):
+        np.testing.assert_array_equal(st[k], want[k], err_msg=k)
+    np.testing.assert_array_equal(st["hist_d"], want["hist_d"].reshape(N, -1))
+    # invariants (independent of the oracle)
+    assert st["inv"].min() >= 0 and st["inv"].max() <= 30 and st["backlog"].min() >= 0 and st["backlog"].max() <= 30
+    assert np.abs(obs[:, :, :3]).max() <= 1.0
+
+
+def test_config4_div_262144_envs_bit_exact():
+    from marl_for_im_b200.envs import MultiAgentInvManagementDiv
+    N, T = 262144, 30
+    for name, R, m in (("div1", 2, 4), ("div2", 3, 6)):
+        cfg = presets.PRESETS[name]()
+        rng = np.random.default_rng(420)
+        demand = rng.poisson(5, size=(N, R, T)).astype(np.int32)
+        actions = np.clip(rng.normal(-0.6, 0.5, size=(T, N, m)), -1, 1)       # near-equilibrium: every split branch
+        obs, rew, st, env = _run_gpu(MultiAgentInvManagementDiv, cfg, demand, actions)
+        assert int(env.error_flags.abs().sum()) == 0
+        want = c_oracle.COracle("MAIM_div", cfg).run(demand, actions)
+        assert want["bad"] == 0
+        np.testing.assert_array_equal(obs, want["obs_last"])
+        np.testing.assert_array_equal(rew, want["reward"])
+        for k in ("inv", "backlog", "order_u", "pipe", "backlog_to"):
+            np.testing.assert_array_equal(st[k], want[k], err_msg=f"{name} {k}")
+
+
+def test_config3_rollout_8stage_131072_envs_bit_exact():
+    """One GPU's share of BASELINE config 3 (1 Mi envs over 8 GPUs): fused 30-period base-stock rollout."""
+    from marl_for_im_b200.envs import MultiAgentInvManagement
+    cfg = presets.serial8(time_dependency=False, prev_demand=False, prev_actions=False, standardise_actions=False)
+    N, T, m = 131072, 30, 8
+    demand = np.random.default_rng(420).poisson(5, size=(N, T)).astype(np.int32)
+    z = np.random.default_rng(7).integers(5, 41, size=(N, m)).astype(np.float64)
+    env = MultiAgentInvManagement(dict(cfg, num_envs=N))
+    out = env.rollout_basestock(z, customer_demand=demand, write_state=True)
+    want = c_oracle.COracle("MAIM", cfg).rollout(z, demand)
+    np.testing.assert_array_equal(out["returns"].cpu().numpy(), want["returns"])
+    st = {k: v.cpu().numpy() for k, v in env.state_dict().items()}
+    for k in ("inv", "backlog", "order_u", "pipe"):
+        np.testing.assert_array_equal(st[k], want[k], err_msg=k)
+    # all-stages z = 25 (inv_management.py:217) as a shared policy vector
+    out2 = env.rollout_basestock(np.full(m, 25.0), customer_demand=demand)
+    want2 = c_oracle.COracle("MAIM", cfg).rollout(np.full(m, 25.0), demand)
+    np.testing.assert_array_equal(out2["returns"].cpu().numpy(), want2["returns"])
+    # Philox path: returns are a deterministic function of (seed, global env, episode) — shard invariant
+    half = N // 2
+    e_lo = MultiAgentInvManagement(dict(cfg, num_envs=half, env_offset=0, seed=9))
+    e_hi = MultiAgentInvManagement(dict(cfg, num_envs=half, env_offset=half, seed=9))
+    e_all = MultiAgentInvManagement(dict(cfg, num_envs=N, seed=9))
+    for e in (e_lo, e_hi, e_all):
+        e._episode = 41
+    r_all = e_all.rollout_basestock(np.full(m, 25.0))["returns"]
+    r_lo = e_lo.rollout_basestock(np.full(m, 25.0))["returns"]
+    r_hi = e_hi.rollout_basestock(np.full(m, 25.0))["returns"]
+    assert torch.equal(r_all[:half], r_lo) and torch.equal(r_all[half:], r_hi)
