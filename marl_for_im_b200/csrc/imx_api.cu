@@ -77,6 +77,7 @@ struct imx_env {
     int32_t* d_demand_T = nullptr;
     uint8_t* d_mask_T = nullptr;
     double* d_cdf = nullptr;
+    uint16_t* d_guide = nullptr;         // cutpoint table of the Poisson inversion
     int cdf_len = 0;
     double* d_stats_partial = nullptr;   // [2 + 2m][STATS_BLOCKS] scratch of imx_return_stats
     double* d_tab = nullptr;             // [m][4][TL] rescale tables
@@ -522,6 +523,14 @@ extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
         e->cdf_len = (int)cdf.size();
         IMX_CREATE_CUDA(cudaMalloc(&e->d_cdf, cdf.size() * sizeof(double)));
         IMX_CREATE_CUDA(cudaMemcpy(e->d_cdf, cdf.data(), cdf.size() * sizeof(double), cudaMemcpyHostToDevice));
+        uint16_t guide[256];
+        int k = 0;
+        for (int g = 0; g < 256; ++g) {                       // smallest k with cdf[k] > g/256
+            while (!(cdf[k] > (double)g / 256.0)) ++k;
+            guide[g] = (uint16_t)k;
+        }
+        IMX_CREATE_CUDA(cudaMalloc(&e->d_guide, sizeof(guide)));
+        IMX_CREATE_CUDA(cudaMemcpy(e->d_guide, guide, sizeof(guide), cudaMemcpyHostToDevice));
     }
     {
         std::vector<double> tab = build_tables(e, &e->TL);
@@ -556,7 +565,7 @@ extern "C" int imx_destroy(imx_env* e) {
     cudaSetDevice(e->cfg.device);
     if (e->hstream) { cudaStreamSynchronize(e->hstream); cudaStreamDestroy(e->hstream); }
     cudaFree(e->d_nodes); cudaFree(e->d_children); cudaFree(e->d_state); cudaFree(e->d_err);
-    cudaFree(e->d_demand_T); cudaFree(e->d_mask_T); cudaFree(e->d_cdf); cudaFree(e->d_tab); cudaFree(e->d_stats_partial);
+    cudaFree(e->d_demand_T); cudaFree(e->d_mask_T); cudaFree(e->d_cdf); cudaFree(e->d_guide); cudaFree(e->d_tab); cudaFree(e->d_stats_partial);
     cudaFree(e->d_act_h); cudaFree(e->d_obs_h); cudaFree(e->d_rew_h); cudaFree(e->d_dem_h); cudaFree(e->d_mask_h);
     delete e;
     return 0;
@@ -606,7 +615,7 @@ extern "C" int imx_set_period(imx_env* e, int t) {
 static DemandGen make_gen(const imx_env* e, uint64_t episode) {
     DemandGen g;
     g.dist = e->cfg.demand_dist; g.low = e->cfg.uniform_low; g.high = e->cfg.uniform_high;
-    g.cdf_len = e->cdf_len; g.cdf = e->d_cdf; g.seed = e->cfg.seed; g.episode = episode; g.env_offset = e->cfg.env_offset;
+    g.cdf_len = e->cdf_len; g.cdf = e->d_cdf; g.guide = e->d_guide; g.seed = e->cfg.seed; g.episode = episode; g.env_offset = e->cfg.env_offset;
     return g;
 }
 
@@ -736,6 +745,11 @@ extern "C" int imx_rollout_basestock(imx_env* e, const double* z_dev, int z_stri
     Rg.ret = return_dev; Rg.step_reward = step_reward_dev; Rg.dfo = dfo_dev; Rg.write_state = write_state;
     Rg.gen = make_gen(e, episode);
     const int epw = 32 / e->m_pad;
+    // Philox demand is drawn cooperatively by the tile's lanes into shared memory when the episode fits
+    const size_t draw_bytes = (size_t)(ROLLOUT_THREADS / 32) * epw * e->R * ((e->T + 1) & ~1) * sizeof(int32_t);
+    const bool coop = (!demand_dev && draw_bytes <= 40 * 1024);
+    Rg.coop_demand = coop ? 1 : 0;
+    const size_t roll_smem = coop ? draw_bytes : 0;
     const int64_t warp_tiles = (e->N + epw - 1) / epw;
     const int64_t blocks_needed = (warp_tiles + (ROLLOUT_THREADS / 32) - 1) / (ROLLOUT_THREADS / 32);
     const unsigned grid = (unsigned)(blocks_needed < e->rollout_grid_cap ? blocks_needed : e->rollout_grid_cap);
@@ -744,12 +758,12 @@ extern "C" int imx_rollout_basestock(imx_env* e, const double* z_dev, int z_stri
         void* params[] = {(void*)&A, (void*)&Rg};
         int occ_blocks = e->rollout_grid_cap;
         const unsigned g2 = (unsigned)(blocks_needed < (int64_t)occ_blocks * 4 ? blocks_needed : (int64_t)occ_blocks * 4);
-        const CUresult cr = imxjit::g_api.LaunchKernel(e->jit->rollout, g2, 1, 1, ROLLOUT_THREADS, 1, 1, 0, (CUstream)s, params, nullptr);
+        const CUresult cr = imxjit::g_api.LaunchKernel(e->jit->rollout, g2, 1, 1, ROLLOUT_THREADS, 1, 1, (unsigned)roll_smem, (CUstream)s, params, nullptr);
         if (cr != CUDA_SUCCESS) return fail(-3, "launch of the specialised rollout kernel failed (CUresult %d)", (int)cr);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e->last_variant = 2;
     } else {
-        e->rollout_fn<<<grid, ROLLOUT_THREADS, 0, s>>>(A, Rg);
+        e->rollout_fn<<<grid, ROLLOUT_THREADS, roll_smem, s>>>(A, Rg);
         IMX_CHECK_LAUNCH("rollout_kernel");
         e->last_variant = 0;
     }

@@ -10,6 +10,7 @@ typedef signed char int8_t;
 typedef unsigned char uint8_t;
 typedef int int32_t;
 typedef unsigned int uint32_t;
+typedef unsigned short uint16_t;
 typedef long long int64_t;
 typedef unsigned long long uint64_t;
 typedef unsigned long uintptr_t;
@@ -226,27 +227,37 @@ struct DemandGen {
     int32_t dist;                 // imx_demand_dist
     int32_t low, high;            // uniform integers in [low, high)
     int32_t cdf_len;              // Poisson: entries in cdf[]
-    const double* __restrict__ cdf;   // Poisson CDF table, cdf[k] = P(X <= k); inversion: smallest k with u < cdf[k]
+    const double* __restrict__ cdf;       // Poisson CDF table, cdf[k] = P(X <= k); inversion: smallest k with u < cdf[k]
+    const uint16_t* __restrict__ guide;   // cutpoint table: guide[g] = smallest k with cdf[k] > g / 256
     uint64_t seed;
     uint64_t episode;
     int64_t env_offset;
 };
 
-__device__ __forceinline__ int draw_demand(const DemandGen& g, int64_t n_local, int r, int t) {
-    const Philox4 v = philox_draw(g.seed, (uint64_t)(g.env_offset + n_local), PHILOX_TAG_DEMAND, (uint32_t)r,
-                                  (uint32_t)t, g.episode);
-    const double u = u53(v.x, v.y);
+// One uniform -> one demand.  Poisson by CDF inversion started from the cutpoint table (the scan
+// from guide[floor(256 u)] reaches the same k as a search from 0, usually in 0-1 steps).
+__device__ __forceinline__ int demand_from_uniform(const DemandGen& g, double u) {
     if (g.dist == IMX_DIST_UNIFORM) {
-        int k = g.low + (int)(u * (double)(g.high - g.low));
+        const int k = g.low + (int)(u * (double)(g.high - g.low));
         return k < g.high ? k : g.high - 1;
     }
-    // Poisson by CDF inversion: binary search for the first entry above u
-    int lo = 0, hi = g.cdf_len - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (u < __ldg(g.cdf + mid)) hi = mid; else lo = mid + 1;
-    }
-    return lo;
+    int k = (int)__ldg(g.guide + (int)(u * 256.0));
+    while (u >= __ldg(g.cdf + k)) ++k;          // the last table entry is a sentinel > 1
+    return k;
+}
+
+// One Philox call serves TWO consecutive periods of one (env, retailer) row: the counter carries
+// t >> 1, words (x, y) make the uniform of the even period and (z, w) of the odd one.
+__device__ __forceinline__ void draw_demand_pair(const DemandGen& g, int64_t n_local, int r, int t_even, int& d0, int& d1) {
+    const Philox4 v = philox_draw(g.seed, (uint64_t)(g.env_offset + n_local), PHILOX_TAG_DEMAND, (uint32_t)r,
+                                  (uint32_t)(t_even >> 1), g.episode);
+    d0 = demand_from_uniform(g, u53(v.x, v.y));
+    d1 = demand_from_uniform(g, u53(v.z, v.w));
+}
+__device__ __forceinline__ int draw_demand(const DemandGen& g, int64_t n_local, int r, int t) {
+    int d0, d1;
+    draw_demand_pair(g, n_local, r, t & ~1, d0, d1);
+    return (t & 1) ? d1 : d0;
 }
 
 __device__ __forceinline__ bool draw_delay(uint64_t seed, int64_t env_global, int i, int t, uint64_t episode, double thr) {

@@ -47,7 +47,12 @@ __global__ void __launch_bounds__(256) demand_generate_kernel(int32_t* __restric
     if (idx >= N * R) return;
     const int r = (int)(idx / N);
     const int64_t n = idx % N;
-    for (int t = 0; t < T; ++t) out[((int64_t)t * R + r) * N + n] = draw_demand(g, n, r, t);
+    for (int t = 0; t < T; t += 2) {
+        int d0, d1;
+        draw_demand_pair(g, n, r, t, d0, d1);
+        out[((int64_t)t * R + r) * N + n] = d0;
+        if (t + 1 < T) out[((int64_t)(t + 1) * R + r) * N + n] = d1;
+    }
 }
 
 // noisy-delay mask [N][T][m] -> [T][N][m]

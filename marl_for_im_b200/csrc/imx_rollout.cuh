@@ -17,6 +17,8 @@ struct RolloutArgs {
     int32_t z_stride;                      // 0 or m
     int32_t write_state;
     const int32_t* __restrict__ demand;    // replayed [N][R][T] or nullptr → Philox
+    int32_t coop_demand;                   // Philox draws are produced cooperatively by the tile's lanes into shared memory
+    int32_t pad_r;
     const double* __restrict__ pmf;        // [N][T] or nullptr
     double* __restrict__ ret;              // [N] (IM kinds) / [N][m] (MAIM kinds)
     double* __restrict__ step_reward;      // [T][N] / [T][N][m] or nullptr
@@ -28,12 +30,15 @@ template <int M_PAD, int DMAX, int MAXC, bool DIV>
 __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_constant__ StepArgs A,
                                                                   const __grid_constant__ RolloutArgs Rg) {
     constexpr int EPW = 32 / M_PAD;
+    extern __shared__ int32_t s_draws[];            // [warps][EPW][R][T_even] when Rg.coop_demand
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int i = lane % M_PAD;
     const int sub = lane / M_PAD;
     const int m = KF(m), T = KF(T);
     const bool stage_ok = i < m;
+    const int T_even = (T + 1) & ~1;
+    int32_t* my_draws = s_draws + ((size_t)(warp * EPW + sub) * KF(R)) * T_even;   // this env's [R][T_even] block
 
     const NodeParams np = load_node(A.nodes + (stage_ok ? i : 0));
     int child_lane[MAXC];
@@ -65,6 +70,21 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
         for (int k = 0; k < MAXC; ++k) bt[k] = 0;
         const double z = ok ? Rg.z[Rg.z_stride ? cell : (int64_t)i] : 0.0;
         const int32_t* dem_row = (ok && Rg.demand && np.retailer_idx >= 0) ? Rg.demand + (n * KF(R) + np.retailer_idx) * T : nullptr;
+        if (Rg.coop_demand) {
+            // every lane of the tile draws a share of the episode's (retailer, period-pair) demands
+            __syncwarp();                           // previous env's reads are done
+            if (n < A.N) {
+                const int pairs = KF(R) * (T_even >> 1);
+                for (int q = i; q < pairs; q += M_PAD) {
+                    const int r = q / (T_even >> 1), t2 = (q % (T_even >> 1)) * 2;
+                    int d0, d1;
+                    draw_demand_pair(Rg.gen, n, r, t2, d0, d1);
+                    my_draws[r * T_even + t2] = d0;
+                    my_draws[r * T_even + t2 + 1] = d1;
+                }
+            }
+            __syncwarp();
+        }
         double ret = 0.0;                 // "dfo_reward = 0; dfo_reward += r" (inv_management.py:223-231)
         double acc8[8];                   // np.sum(prob * rewards) accumulators (numpy pairwise order)
         double dfo_sum = 0.0;
@@ -79,7 +99,8 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
             const int order = ok ? decode_order(act, om_d, KF(std_actions) != 0, KF(multi) != 0, A.a, A.bma, A.inv_bma, KBMA_POW2) : 0;
 
             int cust = 0;
-            if (ok && np.retailer_idx >= 0) cust = dem_row ? dem_row[t] : draw_demand(Rg.gen, n, np.retailer_idx, t);
+            if (ok && np.retailer_idx >= 0)
+                cust = dem_row ? dem_row[t] : (Rg.coop_demand ? my_draws[np.retailer_idx * T_even + t] : draw_demand(Rg.gen, n, np.retailer_idx, t));
 
             int demand;
             int od[MAXC];

@@ -79,55 +79,61 @@ __device__ __forceinline__ double tile_seq_sum(double v, int m) {
 }
 
 // One period of the divergent split for a node with > 1 child — MAIM_div_env.py:483-579 /
-// IM_div_env.py:403-502, pass for pass (whole round-robin passes: the shipped amount may go
-// negative inside a pass, the ledger may go negative; both are the reference's behaviour).
+// IM_div_env.py:403-502.  The reference hands out goods one unit per child per round-robin pass
+// (whole passes: the shipped amount may go negative inside a pass, the ledger may go negative; both
+// are reproduced).  Passes are applied in BATCHES: between two events (a child's counter reaching
+// zero, the goods or the outstanding total running out) every pass does the same thing, so the
+// number of passes up to the next event is computed in closed form and applied at once — at most
+// nchild + 1 batches instead of up to demand_max passes, with identical results.  The watchdog
+// counters count passes, exactly like the reference's while_counter.
 // Returns the watchdog code (0 ok; 1..4 = the reference's "Infinite Loop k").
+__device__ __forceinline__ int ceil_div_pos(int a, int b) { return (a + b - 1) / b; }
+
+// while sum(cnt_k) > 0 and amt > 0: for k: if cnt_k > 0: st_k++, cnt_k--, amt--       (LOOP1 / LOOP2)
+template <int MAXC>
+__device__ __forceinline__ int drain_round_robin(int nchild, int (&cnt)[MAXC], int (&st)[MAXC], int& amt, int limit) {
+    int passes = 0;
+    while (true) {
+        int sum = 0, active = 0, lo = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            if (k < nchild) {
+                sum += cnt[k];
+                if (cnt[k] > 0) { active += 1; lo = min(lo, cnt[k]); }
+            }
+        }
+        if (!(sum > 0 && amt > 0)) break;
+        // sum > 0 implies active >= 1; identical passes until a counter empties, the goods run out or the total does
+        const int p = min(lo, min(ceil_div_pos(amt, active), ceil_div_pos(sum, active)));
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            if (k < nchild && cnt[k] > 0) { st[k] += p; cnt[k] -= p; }
+        }
+        amt -= p * active;
+        passes += p;
+        if (passes > limit) return 1;
+    }
+    return 0;
+}
+
 template <int MAXC>
 __device__ __forceinline__ int split_ship(int nchild, int ship, int demand, int backlog, int demand_max, int mult1,
                                           int mult, const int (&od)[MAXC], int (&bt)[MAXC], int (&st)[MAXC]) {
     int amt = ship;
-    int code = 0;
 #pragma unroll
     for (int k = 0; k < MAXC; ++k) st[k] = 0;
 
-    auto loop1 = [&](int limit, int which) {
-        int cnt = 0;
-        while (true) {
-            int sum = 0;
-#pragma unroll
-            for (int k = 0; k < MAXC; ++k) sum += (k < nchild) ? bt[k] : 0;
-            if (!(sum > 0 && amt > 0)) break;
-#pragma unroll
-            for (int k = 0; k < MAXC; ++k) {
-                if (k < nchild && bt[k] > 0) { st[k] += 1; bt[k] -= 1; amt -= 1; }
-            }
-            if (++cnt > limit) { code = which; break; }
-        }
-    };
-
     if (ship >= demand) {
         if (backlog > 0) {
-            loop1(demand_max * mult1, 1);
-            if (code == 0 && amt > 0 && demand > 0) {
+            if (drain_round_robin<MAXC>(nchild, bt, st, amt, demand_max * mult1)) return 1;
+            if (amt > 0 && demand > 0) {
                 int out[MAXC];
 #pragma unroll
                 for (int k = 0; k < MAXC; ++k) out[k] = (k < nchild) ? od[k] : 0;
-                int cnt = 0;
-                while (true) {
-                    int sum = 0;
+                if (drain_round_robin<MAXC>(nchild, out, st, amt, demand_max * mult)) return 2;
 #pragma unroll
-                    for (int k = 0; k < MAXC; ++k) sum += out[k];
-                    if (!(amt > 0 && sum > 0)) break;
-#pragma unroll
-                    for (int k = 0; k < MAXC; ++k) {
-                        if (out[k] > 0) { st[k] += 1; out[k] -= 1; amt -= 1; }
-                    }
-                    if (++cnt > demand_max * mult) { code = 2; break; }
-                }
-                if (code == 0) {
-#pragma unroll
-                    for (int k = 0; k < MAXC; ++k) bt[k] += out[k];
-                }
+                for (int k = 0; k < MAXC; ++k)
+                    if (k < nchild) bt[k] += out[k];
             }
         } else {
 #pragma unroll
@@ -135,25 +141,33 @@ __device__ __forceinline__ int split_ship(int nchild, int ship, int demand, int 
         }
     } else {
         if (backlog > 0) {
-            loop1(demand_max * mult, 3);
+            if (drain_round_robin<MAXC>(nchild, bt, st, amt, demand_max * mult)) return 3;
         } else {
-            int cnt = 0;
+            // while amt > 0: for k: if st_k < od_k + bt_k: st_k++, amt--                          (LOOP4)
+            int passes = 0;
             while (amt > 0) {
+                int active = 0, lo = 0x7fffffff;
 #pragma unroll
                 for (int k = 0; k < MAXC; ++k) {
-                    if (k < nchild && st[k] < od[k] + bt[k]) { st[k] += 1; amt -= 1; }
+                    if (k < nchild && st[k] < od[k] + bt[k]) { active += 1; lo = min(lo, od[k] + bt[k] - st[k]); }
                 }
-                if (++cnt > demand_max * mult) { code = 4; break; }
+                if (active == 0) return 4;                  // nobody can take a unit: the reference spins into its watchdog
+                const int p = min(lo, ceil_div_pos(amt, active));
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) {
+                    if (k < nchild && st[k] < od[k] + bt[k]) st[k] += p;
+                }
+                amt -= p * active;
+                passes += p;
+                if (passes > demand_max * mult) return 4;
             }
         }
-        if (code == 0) {
 #pragma unroll
-            for (int k = 0; k < MAXC; ++k) {
-                if (k < nchild) bt[k] += od[k] - st[k];
-            }
+        for (int k = 0; k < MAXC; ++k) {
+            if (k < nchild) bt[k] += od[k] - st[k];
         }
     }
-    return code;
+    return 0;
 }
 
 // Writes one agent's observation vector (O doubles) — the field order and per-field maxima of

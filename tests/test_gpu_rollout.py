@@ -120,7 +120,7 @@ def test_batched_basestock_policy_tensor_path():
 def philox_numpy(seed, env, tag, idx, t, episode):
     """numpy restatement of philox_draw (imx_device.cuh) for bit-exact stream checks."""
     M = 0xFFFFFFFF
-    c = [env & M, (env >> 32) & M, ((tag << 28) | ((idx & 0xFFF) << 16) | (t & 0xFFFF)) & M, episode & M]
+    c = [env & M, (env >> 32) & M, ((tag << 28) | ((idx & 0xFFF) << 16) | ((t >> 1) & 0xFFFF)) & M, episode & M]
     k0, k1 = seed & M, ((seed >> 32) ^ (episode >> 32)) & M
     for _ in range(10):
         p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
@@ -143,9 +143,10 @@ def test_philox_demand_stream_exact_and_shard_invariant():
     cdf = np.array(buf[:])
     ep = env._episode
     for n in (0, 1, 17, 1023):
-        for t in (0, 5, 29):
+        for t in (0, 5, 28, 29):
             w = philox_numpy(1234, n, 0, 0, t, ep)
-            u = float((((w[0] >> 5) << 26) | (w[1] >> 6))) / 9007199254740992.0
+            hi, lo = (w[2], w[3]) if (t & 1) else (w[0], w[1])           # one Philox call serves periods 2k (x, y) and 2k+1 (z, w)
+            u = float((((hi >> 5) << 26) | (lo >> 6))) / 9007199254740992.0
             assert d[t, 0, n] == int(np.searchsorted(cdf, u, side="right"))
     # sharding: envs [512, 1024) created as their own handle with env_offset draw the same trace
     e2 = MultiAgentInvManagement(dict(cfg, num_envs=512, env_offset=512, seed=1234))
