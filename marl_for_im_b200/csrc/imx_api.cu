@@ -96,6 +96,7 @@ struct imx_env {
     tma_fn_t tma_fn = nullptr;
     TileLayout tile = {};
     int step_path = 0;                   // 0 auto, 1 direct only, 2 TMA wherever legal (IMX_STEP_PATH)
+    int use_pdl = 1;                     // chain step launches with programmatic dependent launch (IMX_PDL=0 disables)
     int jit_policy = 0;                  // 0 auto (large batches), 1 always, -1 never (IMX_JIT)
     int jit_state = 0;                   // 0 not tried, 1 specialised kernels loaded, -1 unavailable
     const imxjit::Kernels* jit = nullptr;
@@ -238,6 +239,8 @@ static int select_kernels(imx_env* e) {
     {
         const char* pth = getenv("IMX_STEP_PATH");
         e->step_path = (pth && !strcmp(pth, "direct")) ? 1 : (pth && !strcmp(pth, "tma")) ? 2 : 0;
+        const char* pd = getenv("IMX_PDL");
+        e->use_pdl = (pd && !strcmp(pd, "0")) ? 0 : 1;
         const char* jp = getenv("IMX_JIT");
         e->jit_policy = (jp && !strcmp(jp, "1")) ? 1 : (jp && !strcmp(jp, "0")) ? -1 : 0;
     }
@@ -688,8 +691,18 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
             ensure_jit(e);
             if (e->jit_state == 1) {
                 void* params[] = {(void*)&A, (void*)&e->tile};
-                const CUresult cr = imxjit::g_api.LaunchKernel(e->jit->step, (unsigned)(n_tma / e->tile.E), 1, 1, STEP_THREADS, 1, 1,
-                                                               (unsigned)e->tile.total, (CUstream)s, params, nullptr);
+                CUlaunchConfig lc;
+                memset(&lc, 0, sizeof(lc));
+                lc.gridDimX = (unsigned)(n_tma / e->tile.E); lc.gridDimY = 1; lc.gridDimZ = 1;
+                lc.blockDimX = STEP_THREADS; lc.blockDimY = 1; lc.blockDimZ = 1;
+                lc.sharedMemBytes = (unsigned)e->tile.total;
+                lc.hStream = (CUstream)s;
+                CUlaunchAttribute at[1];
+                at[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+                at[0].value.programmaticStreamSerializationAllowed = 1;
+                lc.attrs = at;
+                lc.numAttrs = e->use_pdl ? 1 : 0;
+                const CUresult cr = imxjit::g_api.LaunchKernelEx(&lc, e->jit->step, params, nullptr);
                 if (cr != CUDA_SUCCESS) return fail(-3, "launch of the specialised step kernel failed (CUresult %d)", (int)cr);
                 g_launches.fetch_add(1, std::memory_order_relaxed);
                 launched = true;
@@ -697,7 +710,18 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
             }
         }
         if (!launched) {
-            e->tma_fn<<<(unsigned)(n_tma / e->tile.E), STEP_THREADS, e->tile.total, s>>>(A, e->tile);
+            cudaLaunchConfig_t lc;
+            memset(&lc, 0, sizeof(lc));
+            lc.gridDim = dim3((unsigned)(n_tma / e->tile.E));
+            lc.blockDim = dim3(STEP_THREADS);
+            lc.dynamicSmemBytes = (size_t)e->tile.total;
+            lc.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            lc.attrs = at;
+            lc.numAttrs = e->use_pdl ? 1 : 0;
+            IMX_CUDA(cudaLaunchKernelEx(&lc, e->tma_fn, A, e->tile));
             IMX_CHECK_LAUNCH("step_kernel_tma");
             e->last_variant = 1;
         }

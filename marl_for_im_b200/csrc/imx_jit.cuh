@@ -37,6 +37,7 @@ struct Api {
     CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**);
     CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction);
+    CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**);
 };
 
 struct Kernels {
@@ -71,7 +72,8 @@ static bool load_api() {
               sym(a.h_nvrtc, "nvrtcAddNameExpression", a.AddNameExpression) && sym(a.h_nvrtc, "nvrtcGetLoweredName", a.GetLoweredName) &&
               sym(a.h_nvrtc, "nvrtcDestroyProgram", a.DestroyProgram) && sym(a.h_cuda, "cuModuleLoadData", a.ModuleLoadData) &&
               sym(a.h_cuda, "cuModuleGetFunction", a.ModuleGetFunction) && sym(a.h_cuda, "cuFuncSetAttribute", a.FuncSetAttribute) &&
-              sym(a.h_cuda, "cuLaunchKernel", a.LaunchKernel) && sym(a.h_cuda, "cuFuncGetAttribute", a.FuncGetAttribute);
+              sym(a.h_cuda, "cuLaunchKernel", a.LaunchKernel) && sym(a.h_cuda, "cuFuncGetAttribute", a.FuncGetAttribute) &&
+              sym(a.h_cuda, "cuLaunchKernelEx", a.LaunchKernelEx);
     if (!ok) g_last_log = "a required NVRTC / driver symbol is missing";
     g_api.ok = ok;
     return ok;

@@ -58,6 +58,13 @@ __device__ __forceinline__ void bulk_store_only(void* gdst, const void* ssrc, ui
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 
+// Programmatic dependent launch (sm_90+): back-to-back step() launches are chained with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next grid may start its prologue
+// (barrier init, per-lane constants) while this one drains; it blocks in pdl_wait() until the
+// previous grid has completed and its writes are visible, before touching any state.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV>
 __global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_constant__ StepArgs A,
                                                                 const __grid_constant__ TileLayout TLY) {
@@ -90,9 +97,11 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_con
     const uint32_t b_pipe = (uint32_t)E * KF(L) * 4u, b_hist = b_cell4 * (uint32_t)KF(P);
     const uint32_t b_bt = (uint32_t)E * KF(NB) * 4u, b_dem = (uint32_t)E * 4u;
 
+    pdl_launch_dependents();
     if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (tid == 0) {
+        pdl_wait();                                  // state written by the previous step must be complete and visible
         uint32_t bytes = b_cell8 + 3u * b_cell4 + b_pipe + (uint32_t)KF(R) * b_dem;
         if (KF(need_hd)) bytes += b_hist;
         if (KF(need_ho)) bytes += b_hist;
@@ -124,6 +133,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_con
     const int delay_m1 = np.delay - 1;
     const double om_d = (double)np.order_max;
     const double* __restrict__ tabrow = KHAS(tab) ? A.tab + (size_t)(ok ? i : 0) * 4 * KF(TL) : nullptr;
+    pdl_wait();
     bool delayed = false;
     if (KF(noisy) && ok) delayed = A.mask_T[((int64_t)A.t * A.N + n0 + e_loc) * m + i] != 0;
 
