@@ -14,6 +14,7 @@
 #include "imx_step_tma.cuh"
 #include "imx_rollout.cuh"
 #include "imx_jit.cuh"
+#include "imx_cc.cuh"
 
 using namespace imx;
 
@@ -897,4 +898,28 @@ extern "C" int imx_jit_compile_check(const imx_config* cfg, char* log, int cap) 
     if (log && cap > 0) { strncpy(log, lg.c_str(), (size_t)cap - 1); log[cap - 1] = 0; }
     if (n == 0) return fail(-7, "runtime specialisation did not compile: %s", lg.substr(0, 300).c_str());
     return (int)n;
+}
+
+// --------------------------------------------------------------------------------------
+// centralised-critic observation (models/CC_Model.py:165-214)
+// --------------------------------------------------------------------------------------
+extern "C" int imx_cc_obs_len(const imx_env* e) { return e ? (e->m - 1) * (1 + e->O) + e->O : fail(-1, "null env"); }
+
+extern "C" int imx_cc_observe(imx_env* e, const double* obs_dev, const double* actions_dev, double clip_lo, double clip_hi,
+                              void* out_dev, int out_is_f32, void* stream) {
+    if (!e || !obs_dev || !out_dev) return fail(-1, "null argument");
+    if (!e->multi) return fail(-1, "the centralised-critic observation is defined for the multi-agent kinds");
+    IMX_CUDA(cudaSetDevice(e->cfg.device));
+    const int W = (e->m - 1) * (1 + e->O) + e->O;
+    const int64_t total = e->N * e->m * W;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
+    const int64_t want = (total + 255) / 256;
+    const unsigned grid = (unsigned)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+    if (out_is_f32)
+        cc_observer_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(obs_dev, actions_dev, (float*)out_dev, e->N, e->m, e->O, clip_lo, clip_hi);
+    else
+        cc_observer_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(obs_dev, actions_dev, (double*)out_dev, e->N, e->m, e->O, clip_lo, clip_hi);
+    IMX_CHECK_LAUNCH("cc_observer_kernel");
+    return 0;
 }

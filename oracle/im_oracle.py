@@ -537,3 +537,23 @@ def dfo_value(env: OracleEnv, z: Sequence[float], customer_demand, pmf) -> float
     rewards = base_stock_rollout(env, z, customer_demand)
     prod = np.asarray(pmf, dtype=np.float64) * np.asarray(rewards, dtype=np.float64)
     return -1 / env.T * np.sum(prod)
+
+
+# --------------------------------------------------------------------------------------
+# centralised-critic observer — models/CC_Model.py:196-214 (+ FillInActions :165-193)
+# --------------------------------------------------------------------------------------
+def central_critic_flat(agent_obs: np.ndarray, actions=None, clip=(-1.0, 1.0)) -> np.ndarray:
+    """agent_obs [m, O] → [m, (m-1) + (m-1)*O + O]: per agent the dict {own_obs, opponent_obs,
+    opponent_action} of central_critic_observer flattened in sorted key order (opponent_action,
+    opponent_obs, own_obs).  Opponents in agent order skipping the agent itself; opponent actions are
+    the same step's actions clipped to [a, b] (CC_inv_management.py:523) or zeros (CC_Model.py:207)."""
+    m, O = agent_obs.shape
+    out = np.zeros((m, (m - 1) * (1 + O) + O))
+    for i in range(m):
+        others = [j for j in range(m) if j != i]
+        for slot, j in enumerate(others):
+            if actions is not None:
+                out[i, slot] = min(max(float(actions[j]), clip[0]), clip[1])
+            out[i, (m - 1) + slot * O:(m - 1) + (slot + 1) * O] = agent_obs[j]
+        out[i, (m - 1) * (1 + O):] = agent_obs[i]
+    return out

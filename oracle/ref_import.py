@@ -88,3 +88,41 @@ def load_reference():
     )
     _cache["ns"] = ns
     return ns
+
+
+def load_reference_cc_observer():
+    """central_critic_observer from models/CC_Model.py, imported unmodified.  The module pulls in a
+    dozen RLlib names at import time; they are stubbed (the observer itself is pure numpy)."""
+    if "cc" in _cache:
+        return _cache["cc"]
+    _install_stubs()
+    import torch
+
+    def mod(name, **attrs):
+        m = sys.modules.get(name) or types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    sys.modules["gym.spaces"].Box = _Box
+    mod("ray.rllib.agents.callbacks", DefaultCallbacks=type("DefaultCallbacks", (), {}))
+    mod("ray.rllib.models", ModelCatalog=type("ModelCatalog", (), {}))
+    mod("ray.rllib.policy")
+    mod("ray.rllib.policy.sample_batch", SampleBatch=type("SampleBatch", (), {"CUR_OBS": "obs", "ACTIONS": "actions"}))
+    mod("ray.rllib.models.torch")
+    mod("ray.rllib.models.torch.torch_modelv2", TorchModelV2=type("TorchModelV2", (), {}))
+    mod("ray.rllib.utils")
+    mod("ray.rllib.utils.framework", try_import_torch=lambda: (torch, torch.nn))
+    mod("ray.rllib.models.torch.fcnet", FullyConnectedNetwork=type("FullyConnectedNetwork", (), {}))
+    mod("ray.rllib.models.torch.recurrent_net", RecurrentNetwork=type("RecurrentNetwork", (), {}))
+    mod("ray.rllib.utils.annotations", override=lambda cls: (lambda f: f))
+    mod("ray.rllib.models.modelv2", ModelV2=type("ModelV2", (), {}))
+    mod("ray.rllib.models.preprocessors", get_preprocessor=lambda *a, **k: None)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from models.CC_Model import central_critic_observer
+    _cache["cc"] = central_critic_observer
+    return central_critic_observer

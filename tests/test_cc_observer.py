@@ -1,0 +1,59 @@
+"""Centralised-critic observer: oracle restatement pinned to the reference function (CPU), and the
+CUDA kernel against the oracle (GPU)."""
+import numpy as np
+import pytest
+
+from harness import reference_available
+from oracle import im_oracle
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not present")
+def test_oracle_cc_matches_reference_function():
+    from oracle.ref_import import load_reference_cc_observer
+    ref = load_reference_cc_observer()
+    rng = np.random.default_rng(0)
+    for m, O in ((2, 8), (4, 7), (8, 8), (3, 5)):
+        agent_obs = {f"stage_{i}": rng.uniform(-1, 1, O) for i in range(m)}
+        want = ref(agent_obs)
+        got = im_oracle.central_critic_flat(np.stack([agent_obs[f"stage_{i}"] for i in range(m)]))
+        for i in range(m):
+            w = want[f"stage_{i}"]
+            flat = np.concatenate([w["opponent_action"], w["opponent_obs"], w["own_obs"]])     # sorted-key flattening
+            np.testing.assert_array_equal(got[i], flat)
+
+
+@pytest.mark.gpu
+def test_cuda_cc_observer_matches_oracle():
+    import torch
+    from marl_for_im_b200 import presets
+    from marl_for_im_b200.cc import cc_observe, central_critic_observer
+    from marl_for_im_b200.envs import MultiAgentInvManagement
+    rng = np.random.default_rng(1)
+    for cfg in (presets.serial2(), presets.serial4(), presets.serial8(prev_actions=True)):
+        N = 777
+        env = MultiAgentInvManagement(dict(cfg, num_envs=N))
+        m, O = env.num_nodes, env.obs_len
+        demand = rng.poisson(5, size=(N, 30)).astype(np.int32)
+        obs = env.reset(customer_demand=demand)
+        act = torch.as_tensor(rng.uniform(-1.3, 1.3, size=(N, m)), device="cuda:0")
+        obs, _, _, _ = env.step(act)
+        full = torch.stack([obs[n] for n in env.agent_names], dim=1)
+        got0 = cc_observe(env, obs).cpu().numpy()
+        got1 = cc_observe(env, full, actions=act).cpu().numpy()
+        got32 = cc_observe(env, full, actions=act, dtype=torch.float32).cpu().numpy()
+        full_h, act_h = full.cpu().numpy(), act.cpu().numpy()
+        for n in (0, 1, 400, N - 1):
+            np.testing.assert_array_equal(got0[n], im_oracle.central_critic_flat(full_h[n]))
+            np.testing.assert_array_equal(got1[n], im_oracle.central_critic_flat(full_h[n], act_h[n]))
+            np.testing.assert_array_equal(got32[n], im_oracle.central_critic_flat(full_h[n], act_h[n]).astype(np.float32))
+        d = central_critic_observer(obs, env=env)
+        assert set(d["stage_0"]) == {"own_obs", "opponent_obs", "opponent_action"}
+        assert d["stage_1"]["own_obs"].shape == (N, O) and d["stage_1"]["opponent_obs"].shape == (N, (m - 1) * O)
+        assert torch.equal(d["stage_1"]["own_obs"], obs["stage_1"])
+    # drop-in (N = 1, numpy dicts) — the reference's call pattern
+    env = MultiAgentInvManagement(presets.serial2())
+    o = env.reset(customer_demand=np.full(30, 5))
+    d = central_critic_observer(o, env=env)
+    np.testing.assert_array_equal(d["stage_0"]["own_obs"], o["stage_0"])
+    np.testing.assert_array_equal(d["stage_0"]["opponent_obs"], o["stage_1"])
+    np.testing.assert_array_equal(d["stage_0"]["opponent_action"], np.zeros(1))
