@@ -21,6 +21,13 @@
 
 namespace imx {
 
+// Threads per CTA of the TMA kernel = M_PAD * (envs per tile).  256 for the ahead-of-time build (an
+// upper bound: the host may launch fewer); the runtime-specialised build pins the value it launches with.
+#ifndef IMX_TMA_THREADS
+#define IMX_TMA_THREADS 256
+#endif
+constexpr int TMA_THREADS = IMX_TMA_THREADS;
+
 // Byte offsets of the tile regions inside dynamic shared memory (all multiples of 128).
 struct TileLayout {
     int32_t E;                 // envs per tile
@@ -66,7 +73,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV>
-__global__ void __launch_bounds__(STEP_THREADS) step_kernel_tma(const __grid_constant__ StepArgs A,
+__global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_constant__ StepArgs A,
                                                                 const __grid_constant__ TileLayout TLY) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;

@@ -160,3 +160,43 @@ def test_runtime_specialised_kernels_match(monkeypatch):
         st = env.state_dict()
         np.testing.assert_array_equal(st["inv"][5].cpu().numpy(), want["inv"][-1])
         np.testing.assert_array_equal(st["backlog"][77].cpu().numpy(), want["backlog"][-1])
+
+
+def test_host_buffer_path_matches_device_path(monkeypatch):
+    """imx_reset_host / imx_step_host on pinned buffers (zero-copy: the kernel addresses host memory),
+    on pinned buffers with staged copies, and on pageable numpy memory — same bytes as the device path."""
+    import ctypes as C
+    from marl_for_im_b200 import _lib
+    from marl_for_im_b200.envs import MultiAgentInvManagement
+    cfg = presets.serial4()
+    N, T, m = 4096 + 64, 30, 4
+    rng = np.random.default_rng(6)
+    demand = rng.poisson(5, size=(N, 1, T)).astype(np.int32)
+    actions = rng.uniform(-1, 1, size=(T, N, m))
+    ref_env = MultiAgentInvManagement(dict(cfg, num_envs=N))
+    ref_env.reset(customer_demand=demand)
+    want_obs, want_rew = [], []
+    a_dev = torch.as_tensor(actions, device="cuda:0")
+    for t in range(T):
+        o, r, _, _ = ref_env.step(a_dev[t])
+        want_obs.append(torch.stack([o[n] for n in ref_env.agent_names], dim=1).cpu().numpy())
+        want_rew.append(torch.stack([r[n] for n in ref_env.agent_names], dim=1).cpu().numpy())
+    for mode in ("zero_copy", "staged_pinned", "pageable"):
+        monkeypatch.setenv("IMX_HOST_ZERO_COPY", "0" if mode == "staged_pinned" else "1")
+        env = MultiAgentInvManagement(dict(cfg, num_envs=N))
+        O = env.obs_len
+        if mode == "pageable":
+            dem_h, act_h = demand.copy(), actions.copy()
+            obs_h, rew_h = np.empty((N, m, O)), np.empty((N, m))
+            ptr = lambda a: C.c_void_p(a.ctypes.data)          # noqa: E731
+            view = lambda a: a                                 # noqa: E731
+        else:
+            dem_h, act_h = torch.as_tensor(demand).pin_memory(), torch.as_tensor(actions).pin_memory()
+            obs_h, rew_h = torch.empty((N, m, O), dtype=torch.float64).pin_memory(), torch.empty((N, m), dtype=torch.float64).pin_memory()
+            ptr = lambda a: C.c_void_p(a.data_ptr())           # noqa: E731
+            view = lambda a: a.numpy()                         # noqa: E731
+        _lib.check(env._lib.imx_reset_host(env._handle, ptr(dem_h), None, 0, 3, ptr(obs_h)))
+        for t in range(T):
+            _lib.check(env._lib.imx_step_host(env._handle, ptr(act_h[t]), ptr(obs_h), ptr(rew_h)))
+            np.testing.assert_array_equal(view(obs_h), want_obs[t], err_msg=f"{mode} obs t={t}")
+            np.testing.assert_array_equal(view(rew_h), want_rew[t], err_msg=f"{mode} reward t={t}")
