@@ -299,42 +299,44 @@ def run_ours(args):
         ep.steps(stream, T)
 
     g_steps = capture(steps_only, torch)
-    stats_buf, works = [], []
-
-    def drain():
-        for w in works:
-            w.wait()
-        works.clear()
+    # Episode statistics [n, sum, sum of squares, per-agent ...] accumulate on the device; like the reference's
+    # evaluation loops (np.mean / np.std over all test episodes, MA_inv_management.py:591-595) they are
+    # reduced ONCE per evaluation batch = the K timed episodes: a single NCCL all-reduce of 3 + 2m doubles.
+    stats_acc = torch.zeros(3 + 2 * m, dtype=torch.float64, device=dev)
 
     def bench_step():
         g_episode.replay()
         ret = rew.sum(dim=0)                                 # per-env, per-agent episode return
-        st = env.return_stats(ret)
-        if world > 1:                                        # the single NCCL all-reduce of episode statistics:
-            works.append(dist.all_reduce(st, async_op=True))  # runs on NCCL's stream, overlapping the next episode
-        stats_buf.append(st)
+        stats_acc.add_(env.return_stats(ret))
+
+    def reduce_batch():
+        if world > 1:
+            dist.all_reduce(stats_acc)                       # the single collective of the data path
+        return stats_acc
 
     for _ in range(max(args.warmup, 3)):
         bench_step()
-    drain()
-    stats_buf.clear()
+    reduce_batch()                                           # also initialises the NCCL communicator outside the timed region
+    stats_acc.zero_()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                                      # before the barrier: spawning nvidia-smi must not skew the ranks
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         bench_step()
-    drain()                                                  # every all-reduce completes inside the timed region
+    final_stats = reduce_batch()                             # inside the timed region
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     elapsed = e0.elapsed_time(e1) * 1e-3
+    if os.environ.get("IMX_BENCH_DEBUG"):
+        print(f"[rank {rank}] elapsed {elapsed * 1e3:.3f} ms for {args.steps} steps", file=sys.stderr, flush=True)
     # keep the GPU busy a little longer so that the 100 ms clock sampler sees the kernel under load
     t_end = time.perf_counter() + 0.6
     while rank == 0 and time.perf_counter() < t_end:
@@ -383,11 +385,11 @@ def run_ours(args):
                        "l2": (f"inputs larger than L2: each step streams {T} distinct action/obs/reward buffers "
                               f"({(T * N * m * (2 + O) * 8) / 1e6:.0f} MB > 126 MB L2); the {env.state_words * 4 * N / 1e6:.1f} MB state stays cached by design"),
                        "timing": "CUDA events around K CUDA-graph replays (reset + 30 step launches) + per-episode return statistics"
-                                 + (" + 1 NCCL all-reduce" if world > 1 else "") + ", max over ranks"},
+                                 + (" + 1 NCCL all-reduce of the batch statistics" if world > 1 else "") + ", max over ranks"},
             "roofline": roofline, "roofline_large_n": roof_large, "cpu_baseline": cpu, "cpu_baseline_c": cpu_c, "e2e": e2e,
             "gpu_launches": int((launches_per_episode + 2) * args.steps),
             "clocks": clocks,
-            "episode_stats": {"n": float(stats_buf[-1][0].item()), "mean_return": float((stats_buf[-1][1] / stats_buf[-1][0]).item())},
+            "episode_stats": {"n": float(final_stats[0].item()), "mean_return": float((final_stats[1] / final_stats[0]).item())},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
