@@ -255,6 +255,7 @@ def run_ours(args):
 
     import torch
     import torch.distributed as dist
+    from marl_for_im_b200 import _lib as _lib_mod
     from marl_for_im_b200 import presets
     from marl_for_im_b200.envs import MultiAgentInvManagement
 
@@ -282,16 +283,21 @@ def run_ours(args):
     obs0 = torch.empty((N, m, O), dtype=torch.float64, device=dev)
     ep = RawEpisode(env, demand, actions, obs, [rew[t] for t in range(T)], obs0)
 
-    launches0 = env.launch_count()
-    ep.reset(torch.cuda.current_stream().cuda_stream)
-    ep.steps(torch.cuda.current_stream().cuda_stream, T)
-    torch.cuda.synchronize()
-    launches_per_episode = env.launch_count() - launches0
+    # Episode statistics [n, sum, sum of squares, per-agent ...] accumulate on the device; like the reference's
+    # evaluation loops (np.mean / np.std over all test episodes, MA_inv_management.py:591-595) they are
+    # reduced ONCE per evaluation batch = the K timed episodes: a single NCCL all-reduce of 3 + 2m doubles.
+    stats_acc = torch.zeros(3 + 2 * m, dtype=torch.float64, device=dev)
 
     def episode(stream):
         ep.reset(stream)
         ep.steps(stream, T)
+        _lib_mod.check(env._lib.imx_episode_stats(env._handle, C.c_void_p(rew.data_ptr()), T, None, C.c_void_p(stats_acc.data_ptr()),
+                                                  1, C.c_void_p(stream)))
 
+    launches0 = env.launch_count()
+    episode(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    launches_per_episode = env.launch_count() - launches0
     g_episode = capture(episode, torch)
 
     def steps_only(stream):
@@ -299,15 +305,8 @@ def run_ours(args):
         ep.steps(stream, T)
 
     g_steps = capture(steps_only, torch)
-    # Episode statistics [n, sum, sum of squares, per-agent ...] accumulate on the device; like the reference's
-    # evaluation loops (np.mean / np.std over all test episodes, MA_inv_management.py:591-595) they are
-    # reduced ONCE per evaluation batch = the K timed episodes: a single NCCL all-reduce of 3 + 2m doubles.
-    stats_acc = torch.zeros(3 + 2 * m, dtype=torch.float64, device=dev)
-
     def bench_step():
-        g_episode.replay()
-        ret = rew.sum(dim=0)                                 # per-env, per-agent episode return
-        stats_acc.add_(env.return_stats(ret))
+        g_episode.replay()                                   # reset + 30 step launches + episode statistics, one graph
 
     def reduce_batch():
         if world > 1:
@@ -387,7 +386,7 @@ def run_ours(args):
                        "timing": "CUDA events around K CUDA-graph replays (reset + 30 step launches) + per-episode return statistics"
                                  + (" + 1 NCCL all-reduce of the batch statistics" if world > 1 else "") + ", max over ranks"},
             "roofline": roofline, "roofline_large_n": roof_large, "cpu_baseline": cpu, "cpu_baseline_c": cpu_c, "e2e": e2e,
-            "gpu_launches": int((launches_per_episode + 2) * args.steps),
+            "gpu_launches": int(launches_per_episode * args.steps),
             "clocks": clocks,
             "episode_stats": {"n": float(final_stats[0].item()), "mean_return": float((final_stats[1] / final_stats[0]).item())},
         }

@@ -177,6 +177,14 @@ int imx_rollout_basestock(imx_env* env, const double* z_dev, int z_stride, const
  * per-env total return, then per agent {sum, sum of squares} (MAIM kinds).  Deterministic order. */
 int imx_return_stats(imx_env* env, const double* return_dev, double* stats_dev /* [3 + 2m] */, void* stream);
 
+/* Statistics of one episode from its per-period rewards (the evaluation loops' "reward += r" then
+ * np.mean / np.std over episodes): return[n][agent] = sum over periods in period order, then the
+ * reduction of imx_return_stats.  step_reward_dev [periods][N][m] (MAIM kinds) / [periods][N];
+ * return_dev [N][m] / [N] optional; accumulate != 0 adds into stats_dev (an evaluation batch builds
+ * up on the device, reduced across GPUs once).  Three launches, no host work: graph-capturable. */
+int imx_episode_stats(imx_env* env, const double* step_reward_dev, int periods, double* return_dev, double* stats_dev,
+                      int accumulate, void* stream);
+
 /* central_critic_observer + FillInActions  —  models/CC_Model.py:165-214 (and the hand-built CC
  * observation of CC_inv_management.py:516-528): for every agent the flat vector
  * [opponent_action (m-1) | opponent_obs (m-1)*O | own_obs O], W = imx_cc_obs_len() values.

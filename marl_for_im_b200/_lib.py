@@ -64,6 +64,7 @@ SYMBOLS = {
     "imx_reset_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint64, _P]),
     "imx_step_host": (C.c_int, [_P, _P, _P, _P]),
     "imx_poisson_cdf": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
+    "imx_episode_stats": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
     "imx_cc_obs_len": (C.c_int, [_P]),
     "imx_cc_observe": (C.c_int, [_P, _P, _P, C.c_double, C.c_double, _P, C.c_int, _P]),
     "imx_kernel_variant": (C.c_int, [_P]),

@@ -81,6 +81,7 @@ struct imx_env {
     uint16_t* d_guide = nullptr;         // cutpoint table of the Poisson inversion
     int cdf_len = 0;
     double* d_stats_partial = nullptr;   // [2 + 2m][STATS_BLOCKS] scratch of imx_return_stats
+    double* d_returns = nullptr;         // [N][cols] scratch of imx_episode_stats
     double* d_tab = nullptr;             // [m][4][TL] rescale tables
     int TL = 0;
     // host-call staging (allocated on first use)
@@ -557,6 +558,7 @@ extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
         }
     }
     IMX_CREATE_CUDA(cudaMalloc(&e->d_stats_partial, (size_t)(2 + 2 * IMX_MAX_NODES) * STATS_BLOCKS * sizeof(double)));
+    IMX_CREATE_CUDA(cudaMalloc(&e->d_returns, (size_t)N * m * sizeof(double)));
     // reset state with an all-zero demand trace (the reference constructors end with self.reset())
     IMX_CREATE_CUDA(cudaMemset(e->d_demand_T, 0, dem_bytes));
     IMX_CREATE_CUDA(cudaMemset(e->d_state, 0, total ? total : 256));
@@ -582,7 +584,7 @@ extern "C" int imx_destroy(imx_env* e) {
     cudaSetDevice(e->cfg.device);
     if (e->hstream) { cudaStreamSynchronize(e->hstream); cudaStreamDestroy(e->hstream); }
     cudaFree(e->d_nodes); cudaFree(e->d_children); cudaFree(e->d_state); cudaFree(e->d_err);
-    cudaFree(e->d_demand_T); cudaFree(e->d_mask_T); cudaFree(e->d_cdf); cudaFree(e->d_guide); cudaFree(e->d_tab); cudaFree(e->d_stats_partial);
+    cudaFree(e->d_demand_T); cudaFree(e->d_mask_T); cudaFree(e->d_cdf); cudaFree(e->d_guide); cudaFree(e->d_tab); cudaFree(e->d_stats_partial); cudaFree(e->d_returns);
     cudaFree(e->d_act_h); cudaFree(e->d_obs_h); cudaFree(e->d_rew_h); cudaFree(e->d_dem_h); cudaFree(e->d_mask_h);
     delete e;
     return 0;
@@ -816,7 +818,26 @@ extern "C" int imx_return_stats(imx_env* e, const double* return_dev, double* st
     const int nstat = e->multi ? 2 + 2 * cols : 2;
     return_stats_partial_kernel<<<dim3(STATS_BLOCKS, nstat), STATS_THREADS, 0, (cudaStream_t)stream>>>(return_dev, e->d_stats_partial, e->N, cols);
     IMX_CHECK_LAUNCH("return_stats_partial_kernel");
-    return_stats_final_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(e->d_stats_partial, stats_dev, e->N, nstat);
+    return_stats_final_kernel<<<nstat, 32, 0, (cudaStream_t)stream>>>(e->d_stats_partial, stats_dev, e->N, nstat, 0);
+    IMX_CHECK_LAUNCH("return_stats_final_kernel");
+    return 0;
+}
+
+extern "C" int imx_episode_stats(imx_env* e, const double* step_reward_dev, int periods, double* return_dev, double* stats_dev,
+                                 int accumulate, void* stream) {
+    if (!e || !step_reward_dev || !stats_dev) return fail(-1, "null argument");
+    if (periods < 1) return fail(-1, "periods must be >= 1");
+    IMX_CUDA(cudaSetDevice(e->cfg.device));
+    const int cols = e->multi ? e->m : 1;
+    const int nstat = e->multi ? 2 + 2 * cols : 2;
+    const int64_t cells = e->N * cols;
+    double* ret = return_dev ? return_dev : e->d_returns;
+    cudaStream_t s = (cudaStream_t)stream;
+    episode_return_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(step_reward_dev, ret, cells, periods);
+    IMX_CHECK_LAUNCH("episode_return_kernel");
+    return_stats_partial_kernel<<<dim3(STATS_BLOCKS, nstat), STATS_THREADS, 0, s>>>(ret, e->d_stats_partial, e->N, cols);
+    IMX_CHECK_LAUNCH("return_stats_partial_kernel");
+    return_stats_final_kernel<<<nstat, 32, 0, s>>>(e->d_stats_partial, stats_dev, e->N, nstat, accumulate);
     IMX_CHECK_LAUNCH("return_stats_final_kernel");
     return 0;
 }

@@ -250,14 +250,32 @@ __global__ void __launch_bounds__(STATS_THREADS) return_stats_partial_kernel(con
     if (threadIdx.x == 0) partial[q * STATS_BLOCKS + blockIdx.x] = red[0];
 }
 
-__global__ void return_stats_final_kernel(const double* __restrict__ partial, double* __restrict__ stats, int64_t N, int nstat) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q == 0) stats[0] = (double)N;
-    if (q < nstat) {
-        double acc = 0.0;
-        for (int b = 0; b < STATS_BLOCKS; ++b) acc += partial[q * STATS_BLOCKS + b];
-        stats[1 + q] = acc;
+// One warp per statistic: fixed-shape tree over the STATS_BLOCKS partials (deterministic).
+// accumulate != 0: stats += result (statistics of an evaluation batch build up on the device).
+__global__ void __launch_bounds__(32) return_stats_final_kernel(const double* __restrict__ partial, double* __restrict__ stats, int64_t N,
+                                                                int nstat, int accumulate) {
+    const int q = blockIdx.x;
+    const int lane = threadIdx.x;
+    double acc = 0.0;
+    for (int b = lane; b < STATS_BLOCKS; b += 32) acc += partial[q * STATS_BLOCKS + b];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+        stats[1 + q] = accumulate ? stats[1 + q] + acc : acc;
+        if (q == 0) stats[0] = accumulate ? stats[0] + (double)N : (double)N;
     }
+}
+
+// Episode return per (env, agent) = sum over periods of the step rewards, added in period order like
+// the host loops of the reference ("reward += r", inv_management.py:223-231).  One thread per cell;
+// each period is one coalesced row of step_reward [T][cells].
+__global__ void __launch_bounds__(256) episode_return_kernel(const double* __restrict__ step_reward, double* __restrict__ ret, int64_t cells,
+                                                             int T) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    double acc = 0.0;
+    for (int t = 0; t < T; ++t) acc += step_reward[(int64_t)t * cells + c];
+    ret[c] = acc;
 }
 
 }  // namespace imx

@@ -523,6 +523,17 @@ class _ImxEnvBase:
         _lib.check(self._lib.imx_return_stats(self._handle, C.c_void_p(returns.data_ptr()), C.c_void_p(out.data_ptr()), self._stream()))
         return out
 
+    def episode_stats(self, step_rewards, stats=None, accumulate=False):
+        """step_rewards [T, N, m] (MAIM kinds) or [T, N] float64 on the device → statistics vector (see
+        return_stats); ``accumulate=True`` adds into ``stats`` (evaluation batches, one all-reduce at the end)."""
+        m = self.num_nodes
+        if stats is None:
+            stats = torch.zeros(3 + (2 * m if self.MULTI else 0), dtype=torch.float64, device=self.device)
+        sr = step_rewards.contiguous()
+        _lib.check(self._lib.imx_episode_stats(self._handle, C.c_void_p(sr.data_ptr()), int(sr.shape[0]), None,
+                                               C.c_void_p(stats.data_ptr()), int(bool(accumulate)), self._stream()))
+        return stats
+
     # ------------------------------------------------------------------ spaces
     def _obs_shape_declared(self):
         """Per-agent observation length the reference declares (MAIM_env.py:83-153)."""

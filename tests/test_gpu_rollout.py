@@ -180,3 +180,25 @@ def test_return_stats():
     for i in range(4):
         np.testing.assert_allclose(st[3 + 2 * i], ret[:, i].sum().item(), rtol=1e-12)
         np.testing.assert_allclose(st[4 + 2 * i], (ret[:, i] ** 2).sum().item(), rtol=1e-12)
+
+
+def test_episode_stats_accumulates_like_the_eval_loops():
+    from marl_for_im_b200.envs import InvManagement, MultiAgentInvManagement
+    N, T = 3001, 30
+    env = MultiAgentInvManagement(dict(presets.serial4(), num_envs=N))
+    sr = torch.randn((T, N, 4), dtype=torch.float64, device="cuda:0")
+    st = env.episode_stats(sr)
+    ret = torch.zeros((N, 4), dtype=torch.float64, device="cuda:0")
+    for t in range(T):
+        ret += sr[t]                                         # "reward += r" in period order
+    want = env.return_stats(ret)
+    assert torch.equal(st, want)
+    st2 = env.episode_stats(sr * 2, stats=st.clone(), accumulate=True)
+    np.testing.assert_allclose(st2.cpu().numpy()[0], 2 * N)
+    np.testing.assert_allclose(st2.cpu().numpy()[1], 3 * want.cpu().numpy()[1], rtol=1e-12)
+    np.testing.assert_allclose(st2.cpu().numpy()[2], 5 * want.cpu().numpy()[2], rtol=1e-12)
+    env1 = InvManagement(dict(presets.serial4_dfo(), num_envs=N))
+    sr1 = torch.randn((T, N), dtype=torch.float64, device="cuda:0")
+    st1 = env1.episode_stats(sr1).cpu().numpy()
+    tot = sr1.sum(dim=0)
+    np.testing.assert_allclose(st1, [N, tot.sum().item(), (tot * tot).sum().item()], rtol=1e-12)
