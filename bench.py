@@ -36,7 +36,8 @@ KERNEL_VARIANTS = {0: "imx::step_kernel (ahead-of-time, direct global accesses)"
                    1: "imx::step_kernel_tma (ahead-of-time, TMA-staged tiles)",
                    2: "imx::step_kernel_tma<4,3,1,1,false> (NVRTC-specialised, TMA-staged tiles)"}
 ENVS_PER_GPU = 65536
-NCU_TRAFFIC_BYTES_65536 = 8402944        # dram__bytes_read.sum + dram__bytes_write.sum, one launch, see profiles/
+NCU_TRAFFIC_BYTES_65536 = 8402432        # dram__bytes_read.sum + dram__bytes_write.sum, one launch (cold L2), profiles/r1_ncu_step_kernel_tma_specialised_pdl_final.txt
+NCU_TRAFFIC_BYTES_4MI = 537099264 + 1402789000   # same counters at 4 Mi envs, profiles/r1_ncu_step_kernel_tma_specialised_4Mi_envs.txt
 WORKLOAD = ("MAIM_env 4-stage serial, MA_6 obs mode (td=T,pd=T,pa=F,P=1, shared reward), step() on "
             "65536 envs per GPU, 30-period episodes, replayed Poisson(5) demand, uniform(-1,1) actions pre-staged")
 
@@ -357,7 +358,7 @@ def run_ours(args):
     achieved = B * N / dt / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_TRAFFIC_BYTES_65536 if N == ENVS_PER_GPU else None,
-                "traffic_source": "profiles/r1_ncu_step_kernel_tma_specialised.txt (ncu --set full: dram__bytes_read+write per launch; "
+                "traffic_source": "profiles/r1_ncu_step_kernel_tma_specialised_pdl_final.txt (ncu --set full: dram__bytes_read+write per launch; "
                                   "the 31 MB working set of one launch is L2-resident, hence traffic << algorithmic bytes)", "kernel": KERNEL_VARIANTS[env._lib.imx_kernel_variant(env._handle)], "us_per_launch": dt * 1e6,
                 "algorithmic_bytes_per_env_step": B, "envs_per_launch": N, "peak_source": peak_src,
                 "note": "per-launch time = steps-only graph of 30 dependent launches / 30 (includes inter-kernel gaps)"}
@@ -425,7 +426,9 @@ def large_n_roofline(torch, dev, peak, N=4 * 1024 * 1024, periods=8):
     del env
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "envs_per_launch": N, "us_per_launch": dt * 1e6, "working_set_mb": B * N / 1e6,
-            "agent_steps_per_sec": N * m / dt}
+            "agent_steps_per_sec": N * m / dt, "algorithmic_bytes_per_launch": B * N,
+            "traffic": NCU_TRAFFIC_BYTES_4MI if N == 4 * 1024 * 1024 else None,
+            "traffic_source": "profiles/r1_ncu_step_kernel_tma_specialised_4Mi_envs.txt (dram read 537 MB + write 1403 MB per launch = 0.97 x algorithmic)"}
 
 
 def e2e_measure(env, demand_h, actions_h, torch, dev, world, episodes):
@@ -473,8 +476,13 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-large", action="store_true")
+    ap.add_argument("--large-only", action="store_true", help="only the 4 Mi-env roofline point (used for the ncu capture)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.large_only:
+        import torch
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        print(json.dumps(large_n_roofline(torch, torch.device("cuda:0"), peak)), flush=True)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_ours(args)
