@@ -202,3 +202,23 @@ def test_episode_stats_accumulates_like_the_eval_loops():
     st1 = env1.episode_stats(sr1).cpu().numpy()
     tot = sr1.sum(dim=0)
     np.testing.assert_allclose(st1, [N, tot.sum().item(), (tot * tot).sum().item()], rtol=1e-12)
+
+
+def test_dfo_func_batch_matches_single_env_objective():
+    from scipy.stats import poisson
+    from marl_for_im_b200.base_restock_policy import dfo_func_batch, population_search_inventory_policy
+    from marl_for_im_b200.envs import InvManagement
+    cfg = presets.serial4_dfo()
+    rng = np.random.default_rng(21)
+    K, D = 7, 9
+    policies = rng.integers(10, 40, size=(K, 4)).astype(float) + rng.choice([0.0, 0.25], size=(K, 4))
+    demands = rng.poisson(5, size=(D, 30))
+    env = InvManagement(dict(cfg, num_envs=K * D))
+    got = dfo_func_batch(policies, env, demands).cpu().numpy()
+    orc = im_oracle.OracleEnv("IM", cfg)
+    for k in range(K):
+        for d in range(D):
+            assert got[k, d] == im_oracle.dfo_value(orc, policies[k], demands[d], poisson.pmf(demands[d], mu=5))
+    pol, score = population_search_inventory_policy(InvManagement, cfg, demands, np.ones(4) * 25, sweeps=2, radius=3)
+    base = dfo_func_batch(np.ones((1, 4)) * 25, InvManagement(dict(cfg, num_envs=D)), demands).mean().item()
+    assert pol.shape == (4,) and score <= base + 1e-12
