@@ -112,7 +112,8 @@ enum imx_field {
     IMX_F_BACKLOG_TO = 7, /* [N][NB] signed per-child backlog ledger of the split nodes, NB = sum of their child counts */
     IMX_F_ERROR = 8,      /* [N] watchdog code of the divergent split (0 = ok, 1..4 = "Infinite Loop k") */
     IMX_F_DEMAND = 9,     /* [T][R][N] the episode's demand trace as the kernels read it (transposed) */
-    IMX_F_COUNT = 10
+    IMX_F_DELAY_MASK = 10, /* [T][N][m] uint8: this episode's noisy-delay outcomes (replayed or drawn from Philox) */
+    IMX_F_COUNT = 11
 };
 
 #ifndef __CUDACC_RTC__   /* the device-side (NVRTC) build only needs the types above */

@@ -11,7 +11,7 @@ import os
 MAX_NODES, MAX_CHILDREN, MAX_DELAY, MAX_HIST = 32, 8, 8, 8
 KIND = {"IM": 0, "MAIM": 1, "IM_div": 2, "MAIM_div": 3}
 DIST = {"replay": 0, "custom": 0, "poisson": 1, "uniform": 2}
-F_INV, F_BACKLOG, F_ORDER_U, F_PIPE, F_HIST_D, F_HIST_O, F_CARRY, F_BACKLOG_TO, F_ERROR, F_DEMAND = range(10)
+F_INV, F_BACKLOG, F_ORDER_U, F_PIPE, F_HIST_D, F_HIST_O, F_CARRY, F_BACKLOG_TO, F_ERROR, F_DEMAND, F_DELAY_MASK = range(11)
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libimx_b200.so")
 

@@ -515,7 +515,7 @@ extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
     const int64_t cnt[IMX_F_COUNT] = {
         N * m, N * m, N * m, N * e->L,
         e->need_hd ? N * m * e->P : 0, e->need_ho ? N * m * e->P : 0,
-        e->has_carry ? N * m : 0, N * e->NB, 0, 0};
+        e->has_carry ? N * m : 0, N * e->NB, 0, 0, 0};
     size_t off[IMX_F_COUNT] = {};
     size_t total = 0;
     for (int f = 0; f <= IMX_F_BACKLOG_TO; ++f) {
@@ -535,7 +535,12 @@ extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
     IMX_CREATE_CUDA(cudaMalloc(&e->d_demand_T, dem_bytes));
     e->field_ptr[IMX_F_DEMAND] = e->d_demand_T;
     e->field_cnt[IMX_F_DEMAND] = (int64_t)e->T * e->R * N;
-    if (e->has_carry) IMX_CREATE_CUDA(cudaMalloc(&e->d_mask_T, (size_t)e->T * N * m));
+    if (e->has_carry) {
+        IMX_CREATE_CUDA(cudaMalloc(&e->d_mask_T, (size_t)e->T * N * m));
+        IMX_CREATE_CUDA(cudaMemset(e->d_mask_T, 0, (size_t)e->T * N * m));
+        e->field_ptr[IMX_F_DELAY_MASK] = e->d_mask_T;
+        e->field_cnt[IMX_F_DELAY_MASK] = (int64_t)e->T * N * m;
+    }
     if (cfg->demand_dist == IMX_DIST_POISSON) {
         std::vector<double> cdf = poisson_cdf(cfg->mu);
         e->cdf_len = (int)cdf.size();

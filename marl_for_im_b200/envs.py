@@ -380,6 +380,14 @@ class _ImxEnvBase:
         self.state = self._shape_obs(obs_buf)
         return self.state
 
+    def delay_mask_device(self):
+        """[T, N, m] uint8 view of this episode's noisy-delay outcomes (None without noisy delays)."""
+        ptr, cnt = C.c_void_p(), C.c_int64()
+        _lib.check(self._lib.imx_state_field(self._handle, _lib.F_DELAY_MASK, C.byref(ptr), C.byref(cnt)))
+        if cnt.value == 0:
+            return None
+        return torch.as_tensor(_DevView(ptr.value, (self.num_periods, self.num_envs, self.num_nodes), "|u1"), device=self.device)
+
     def customer_demand_device(self):
         """[T, R, N] int32 view of the episode's demand trace as the kernels read it."""
         return self._state_view(_lib.F_DEMAND)

@@ -59,7 +59,7 @@ _cache = {}
 
 def load_reference():
     """Returns a namespace with the four reference env classes and the base-stock helpers."""
-    if _cache:
+    if "ns" in _cache:
         return _cache["ns"]
     if not reference_available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")

@@ -126,3 +126,46 @@ def test_watchdog_sets_error_flag():
     env.step(act)
     flags = env.error_flags.cpu().numpy()
     assert flags[3] == 4 and flags[[0, 1, 2, 4, 5, 6, 7]].sum() == 0
+
+
+HOSTSTREAM_DIR = __import__("os").path.join(__import__("harness").GOLDEN_DIR, "hoststream")
+
+
+@pytest.mark.parametrize("name", sorted(f[:-4] for f in __import__("os").listdir(HOSTSTREAM_DIR) if f.endswith(".npz")))
+def test_dropin_consumes_the_host_random_stream_like_the_reference(name):
+    """Episodes driven only by the constructor seed: the demand draw inside reset(), the noisy-demand
+    mutations and the per-period noisy-delay uniforms must come off numpy's global stream in the
+    reference's order (fixtures: tests/golden/make_golden_hoststream.py)."""
+    import json
+    z = np.load(__import__("os").path.join(HOSTSTREAM_DIR, name + ".npz"), allow_pickle=False)
+    raw = json.loads(str(z["config"]))
+    cfg = {}
+    for k, v in raw.items():
+        if isinstance(v, dict) and "__nd__" in v:
+            cfg[k] = np.array(v["__nd__"], dtype=v["dtype"])
+        elif isinstance(v, dict) and "__dict__" in v:
+            cfg[k] = {int(a): list(b) for a, b in v["__dict__"].items()}
+        elif isinstance(v, list):
+            cfg[k] = tuple(v)
+        else:
+            cfg[k] = v
+    kind = str(z["kind"])
+    multi = kind.startswith("MAIM")
+    thr = float(z["noisy_delay_threshold"])
+    env = ENV_CLASSES[kind](cfg)
+    m, T = env.num_nodes, env.num_periods
+    names = agent_names(kind, m)
+    for e in range(z["demands"].shape[0]):
+        obs = env.reset(noisy_delay=True, noisy_delay_threshold=thr) if thr >= 0 else env.reset()
+        np.testing.assert_array_equal(np.asarray(env.customer_demand), z["demands"][e], err_msg=f"{name} demand draw, episode {e}")
+        got = np.stack([obs[n] for n in names]) if multi else obs
+        np.testing.assert_array_equal(got, z["obs"][e, 0])
+        for t in range(T):
+            act = {names[i]: np.array([z["actions"][e, t, i]]) for i in range(m)} if multi else z["actions"][e, t]
+            obs, rew, done, info = env.step(act)
+            got = np.stack([obs[n] for n in names]) if multi else obs
+            np.testing.assert_array_equal(got, z["obs"][e, t + 1], err_msg=f"{name} obs episode {e} t={t}")
+            if multi:
+                np.testing.assert_array_equal([rew[n] for n in names], z["reward"][e, t])
+            else:
+                assert rew == z["reward"][e, t, 0]

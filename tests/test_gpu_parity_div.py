@@ -92,3 +92,31 @@ def test_cuda_div_batch_distinct_envs():
         want = run_oracle("MAIM_div", cfg, demand[n], actions[:, n])
         np.testing.assert_array_equal(want["obs"][1:], obs[:, n])
         np.testing.assert_array_equal(want["reward"], rew[:, n])
+
+
+def test_device_generated_noisy_delay_mask():
+    """Batched envs draw the noisy-delay outcomes from Philox on the device: the drawn mask is exposed,
+    its rate matches the threshold, and the dynamics under it match the oracle replaying that mask."""
+    import torch
+    from marl_for_im_b200.envs import MultiAgentInvManagement, MultiAgentInvManagementDiv
+    for cls, kind, cfg in ((MultiAgentInvManagement, "MAIM", presets.serial4()), (MultiAgentInvManagementDiv, "MAIM_div", presets.div2())):
+        N, T = 4096, 30
+        m = cfg.get("num_nodes", cfg.get("num_stages"))
+        rng = np.random.default_rng(44)
+        R = 3 if kind == "MAIM_div" else 1
+        demand = rng.poisson(5, size=(N, R, T)).astype(np.int32)
+        actions = np.clip(rng.normal(-0.5, 0.5, size=(T, N, m)), -1, 1)
+        env = cls(dict(cfg, num_envs=N, seed=5))
+        env.reset(customer_demand=demand if R > 1 else demand[:, 0], noisy_delay=True, noisy_delay_threshold=0.3)
+        mask = env.delay_mask_device().cpu().numpy()                       # [T, N, m]
+        assert abs(mask.mean() - 0.3) < 0.01
+        a_dev = torch.as_tensor(actions, device="cuda:0")
+        for t in range(T):
+            o, r, _, _ = env.step(a_dev[t])
+        obs = torch.stack([o[n] for n in env.agent_names], dim=1).cpu().numpy()
+        for n in (0, 77, 4095):
+            want = run_oracle(kind, cfg, demand[n] if R > 1 else demand[n, 0], actions[:, n], mask[:, n].astype(bool))
+            np.testing.assert_array_equal(obs[n], want["obs"][-1])
+        # a different threshold re-creates the generator state (handle rebuilt) and changes the rate
+        env.reset(customer_demand=demand if R > 1 else demand[:, 0], noisy_delay=True, noisy_delay_threshold=0.6)
+        assert abs(env.delay_mask_device().float().mean().item() - 0.6) < 0.01
