@@ -96,7 +96,8 @@ struct imx_env {
     // kernels
     step_fn_t step_fn = nullptr;
     tma_fn_t tma_fn = nullptr;
-    TileLayout tile = {};
+    TileLayout tile = {};                // ahead-of-time kernels: tile width = m rounded up to a power of two
+    TileLayout tile_jit = {};            // runtime-specialised kernels: tile width = m (dense lane packing)
     int step_path = 0;                   // 0 auto, 1 direct only, 2 TMA wherever legal (IMX_STEP_PATH)
     int host_zero_copy = 1;              // imx_step_host addresses pinned host buffers directly (IMX_HOST_ZERO_COPY=0: staged copies)
     int tma_threads = 256;               // CTA size of the TMA kernel (IMX_TMA_THREADS: 64, 128 or 256)
@@ -144,10 +145,9 @@ static int m_pad_of(const imx_env* e) {
 }
 
 // shared-memory tile layout of the TMA kernel (regions 128-byte aligned); pure host arithmetic
-static void compute_tile(imx_env* e) {
-    TileLayout& L = e->tile;
+static void compute_tile(const imx_env* e, TileLayout& L, int tile_width) {
     const int m = e->m;
-    const int E = e->tma_threads / m_pad_of(e);
+    const int E = (e->tma_threads / 32) * (32 / tile_width);
     int off = 0;
     auto take = [&](int bytes) { const int o = off; off += (bytes + 127) & ~127; return o; };
     L.E = E;
@@ -184,19 +184,19 @@ static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, s
     const double fr = std::frexp(c.b - c.a, &ex);
     add("bma_pow2", (fr == 0.5 && ex > -1000 && ex < 1000) ? 1 : 0);
     add("m_pow2", ((e->m & (e->m - 1)) == 0) ? 1 : 0);
-    const TileLayout& L = e->tile;
+    const TileLayout& L = e->tile_jit;
     auto addt = [&](const char* k, long long v) { defs.push_back(std::string("IMX_KT_") + k + "=" + std::to_string(v)); };
     addt("E", L.E); addt("off_act", L.off_act); addt("off_inv", L.off_inv); addt("off_bl", L.off_bl); addt("off_ou", L.off_ou);
     addt("off_pipe", L.off_pipe); addt("off_hd", L.off_hd); addt("off_ho", L.off_ho); addt("off_carry", L.off_carry);
     addt("off_bt", L.off_bt); addt("off_dem", L.off_dem); addt("off_obs", L.off_obs); addt("off_rew", L.off_rew); addt("total", L.total);
     defs.push_back("IMX_TMA_THREADS=" + std::to_string(e->tma_threads));
-    const int mp = m_pad_of(e);
+    const int mp = m_pad_of(e);                            // step kernel: power-of-two tile width (see select_kernels)
     const int pmax = (e->need_hd || e->need_ho) ? e->P : 1;
     const int maxc = e->maxc > 1 ? e->maxc : 1;
     const std::string dv = e->div ? "true" : "false";
     step_name = "imx::step_kernel_tma<" + std::to_string(mp) + ", " + std::to_string(e->D) + ", " + std::to_string(pmax) + ", " +
                 std::to_string(e->div ? maxc : 1) + ", " + dv + ">";
-    rollout_name = "imx::rollout_kernel<" + std::to_string(mp) + ", " + std::to_string(e->D) + ", " + std::to_string(e->div ? maxc : 1) +
+    rollout_name = "imx::rollout_kernel<" + std::to_string(e->m) + ", " + std::to_string(e->D) + ", " + std::to_string(e->div ? maxc : 1) +
                    ", " + dv + ">";
 }
 
@@ -209,7 +209,8 @@ static void ensure_jit(imx_env* e) {
     std::vector<std::string> defs;
     std::string sn, rn;
     jit_spec(e, e->TL, defs, sn, rn);
-    e->jit = imxjit::get(defs, sn, rn, e->tile.total);
+    if (e->tile_jit.total > 200 * 1024) return;
+    e->jit = imxjit::get(defs, sn, rn, e->tile_jit.total);
     if (e->jit) e->jit_state = 1;
 }
 
@@ -244,7 +245,11 @@ static int select_kernels(imx_env* e) {
         const int v = tt ? atoi(tt) : dflt;
         e->tma_threads = (v == 64 || v == 128 || v == 256) && v >= 2 * m_pad_of(e) ? v : 256;
     }
-    compute_tile(e);
+    compute_tile(e, e->tile, m_pad_of(e));
+    // the specialised STEP kernel keeps the power-of-two tile: a dense m-wide tile makes the per-field byte
+    // ranges (e.g. 40 envs x 6 nodes x 4 B = 960 B) straddle 128-byte lines, measured slower at 262144 envs;
+    // the issue-bound ROLLOUT kernel is specialised with tile width = m (dense lane packing, +21% on div2)
+    compute_tile(e, e->tile_jit, m_pad_of(e));
     if (e->tile.total <= 200 * 1024)
         IMX_CUDA(cudaFuncSetAttribute((const void*)e->tma_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->tile.total));
     else
@@ -699,43 +704,46 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
     }
     // fast path: whole tiles of E envs through the TMA-staged kernel; the tail (and configurations the
     // bulk copies cannot address: unaligned caller buffers, N not a multiple of 4) through the direct kernel
-    int64_t n_tma = 0;
     const auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    if (e->tma_fn && e->step_path != 1 && (e->N % 4) == 0 && aligned16(actions_dev) && aligned16(obs_dev) && aligned16(reward_dev)) {
-        n_tma = (e->N / e->tile.E) * e->tile.E;
-        if (e->step_path == 0 && n_tma < e->tile.E) n_tma = 0;
+    const bool tma_legal = e->tma_fn && e->step_path != 1 && (e->N % 4) == 0 && aligned16(actions_dev) && aligned16(obs_dev) &&
+                           aligned16(reward_dev);
+    bool use_jit = false;
+    if (tma_legal && obs_dev && !A.has_info && !A.noisy) {
+        ensure_jit(e);
+        use_jit = (e->jit_state == 1);
+    }
+    const TileLayout& TL_use = use_jit ? e->tile_jit : e->tile;
+    const int epw_direct = 32 / e->m_pad;
+    int64_t n_tma = 0;
+    if (tma_legal) {
+        n_tma = (e->N / TL_use.E) * TL_use.E;
+        while (n_tma > 0 && (n_tma % epw_direct) != 0) n_tma -= TL_use.E;      // the tail kernel starts on a warp-tile boundary
     }
     e->last_variant = 0;
     if (n_tma > 0) {
-        bool launched = false;
-        if (obs_dev && !A.has_info && !A.noisy) {
-            ensure_jit(e);
-            if (e->jit_state == 1) {
-                void* params[] = {(void*)&A, (void*)&e->tile};
-                CUlaunchConfig lc;
-                memset(&lc, 0, sizeof(lc));
-                lc.gridDimX = (unsigned)(n_tma / e->tile.E); lc.gridDimY = 1; lc.gridDimZ = 1;
-                lc.blockDimX = (unsigned)e->tma_threads; lc.blockDimY = 1; lc.blockDimZ = 1;
-                lc.sharedMemBytes = (unsigned)e->tile.total;
-                lc.hStream = (CUstream)s;
-                CUlaunchAttribute at[1];
-                at[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
-                at[0].value.programmaticStreamSerializationAllowed = 1;
-                lc.attrs = at;
-                lc.numAttrs = e->use_pdl ? 1 : 0;
-                const CUresult cr = imxjit::g_api.LaunchKernelEx(&lc, e->jit->step, params, nullptr);
-                if (cr != CUDA_SUCCESS) return fail(-3, "launch of the specialised step kernel failed (CUresult %d)", (int)cr);
-                g_launches.fetch_add(1, std::memory_order_relaxed);
-                launched = true;
-                e->last_variant = 2;
-            }
-        }
-        if (!launched) {
+        if (use_jit) {
+            void* params[] = {(void*)&A, (void*)&e->tile_jit};
+            CUlaunchConfig lc;
+            memset(&lc, 0, sizeof(lc));
+            lc.gridDimX = (unsigned)(n_tma / TL_use.E); lc.gridDimY = 1; lc.gridDimZ = 1;
+            lc.blockDimX = (unsigned)e->tma_threads; lc.blockDimY = 1; lc.blockDimZ = 1;
+            lc.sharedMemBytes = (unsigned)TL_use.total;
+            lc.hStream = (CUstream)s;
+            CUlaunchAttribute at[1];
+            at[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+            at[0].value.programmaticStreamSerializationAllowed = 1;
+            lc.attrs = at;
+            lc.numAttrs = e->use_pdl ? 1 : 0;
+            const CUresult cr = imxjit::g_api.LaunchKernelEx(&lc, e->jit->step, params, nullptr);
+            if (cr != CUDA_SUCCESS) return fail(-3, "launch of the specialised step kernel failed (CUresult %d)", (int)cr);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            e->last_variant = 2;
+        } else {
             cudaLaunchConfig_t lc;
             memset(&lc, 0, sizeof(lc));
-            lc.gridDim = dim3((unsigned)(n_tma / e->tile.E));
+            lc.gridDim = dim3((unsigned)(n_tma / TL_use.E));
             lc.blockDim = dim3((unsigned)e->tma_threads);
-            lc.dynamicSmemBytes = (size_t)e->tile.total;
+            lc.dynamicSmemBytes = (size_t)TL_use.total;
             lc.stream = s;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -801,9 +809,15 @@ extern "C" int imx_rollout_basestock(imx_env* e, const double* z_dev, int z_stri
     ensure_jit(e);
     if (e->jit_state == 1) {
         void* params[] = {(void*)&A, (void*)&Rg};
-        int occ_blocks = e->rollout_grid_cap;
-        const unsigned g2 = (unsigned)(blocks_needed < (int64_t)occ_blocks * 4 ? blocks_needed : (int64_t)occ_blocks * 4);
-        const CUresult cr = imxjit::g_api.LaunchKernel(e->jit->rollout, g2, 1, 1, ROLLOUT_THREADS, 1, 1, (unsigned)roll_smem, (CUstream)s, params, nullptr);
+        const int epw_j = 32 / e->m;                         // dense packing in the specialised build
+        const int64_t wt_j = (e->N + epw_j - 1) / epw_j;
+        const int64_t need_j = (wt_j + (ROLLOUT_THREADS / 32) - 1) / (ROLLOUT_THREADS / 32);
+        const int64_t cap_j = (int64_t)e->rollout_grid_cap * 4;
+        const unsigned g2 = (unsigned)(need_j < cap_j ? need_j : cap_j);
+        const size_t draw_j = (size_t)(ROLLOUT_THREADS / 32) * epw_j * e->R * ((e->T + 1) & ~1) * sizeof(int32_t);
+        if (coop && draw_j > 40 * 1024) Rg.coop_demand = 0;
+        const size_t roll_smem_j = Rg.coop_demand ? draw_j : 0;
+        const CUresult cr = imxjit::g_api.LaunchKernel(e->jit->rollout, g2, 1, 1, ROLLOUT_THREADS, 1, 1, (unsigned)roll_smem_j, (CUstream)s, params, nullptr);
         if (cr != CUDA_SUCCESS) return fail(-3, "launch of the specialised rollout kernel failed (CUresult %d)", (int)cr);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e->last_variant = 2;
@@ -943,7 +957,8 @@ extern "C" int imx_jit_compile_check(const imx_config* cfg, char* log, int cap) 
     tmp.cfg = *cfg;
     const int rc = derive(&tmp);
     if (rc) return rc;
-    compute_tile(&tmp);
+    compute_tile(&tmp, tmp.tile, m_pad_of(&tmp));
+    compute_tile(&tmp, tmp.tile_jit, m_pad_of(&tmp));
     int TL = 0;
     build_tables(&tmp, &TL);
     std::vector<std::string> defs;

@@ -35,8 +35,9 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
     const int warp = threadIdx.x >> 5;
     const int i = lane % M_PAD;
     const int sub = lane / M_PAD;
+    const int tbase = lane - i;
     const int m = KF(m), T = KF(T);
-    const bool stage_ok = i < m;
+    const bool stage_ok = i < m && sub < EPW;         // M_PAD is the tile width (exactly m in the specialised build)
     const int T_even = (T + 1) & ~1;
     int32_t* my_draws = s_draws + ((size_t)(warp * EPW + sub) * KF(R)) * T_even;   // this env's [R][T_even] block
 
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
         if (Rg.coop_demand) {
             // every lane of the tile draws a share of the episode's (retailer, period-pair) demands
             __syncwarp();                           // previous env's reads are done
-            if (n < A.N) {
+            if (n < A.N && sub < EPW) {
                 const int pairs = KF(R) * (T_even >> 1);
                 for (int q = i; q < pairs; q += M_PAD) {
                     const int r = q / (T_even >> 1), t2 = (q % (T_even >> 1)) * 2;
@@ -110,14 +111,14 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
                 for (int k = 0; k < MAXC; ++k) {
                     od[k] = 0;
                     if (k < KF(maxc)) {
-                        const int v = __shfl_sync(0xffffffffu, order, child_lane[k] < 0 ? 0 : child_lane[k], M_PAD);
+                        const int v = __shfl_sync(0xffffffffu, order, tbase + (child_lane[k] < 0 ? 0 : child_lane[k]));
                         od[k] = child_lane[k] < 0 ? 0 : v;
                         s += od[k];
                     }
                 }
                 demand = (np.retailer_idx >= 0) ? min(cust, np.inv_max) : s;
             } else {
-                const int down = __shfl_up_sync(0xffffffffu, order, 1, M_PAD);
+                const int down = __shfl_up_sync(0xffffffffu, order, 1);
                 demand = (i == 0) ? min(cust, np.inv_max) : down;
             }
 
@@ -137,12 +138,12 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
 #pragma unroll
                 for (int k = 0; k < MAXC; ++k) {
                     if (k < KF(maxc)) {
-                        const int v = __shfl_sync(0xffffffffu, st[k], np.parent < 0 ? 0 : np.parent, M_PAD);
+                        const int v = __shfl_sync(0xffffffffu, st[k], tbase + (np.parent < 0 ? 0 : np.parent));
                         if (np.parent >= 0 && np.child_slot == k) incoming = v;
                     }
                 }
             } else {
-                const int up = __shfl_down_sync(0xffffffffu, ship, 1, M_PAD);
+                const int up = __shfl_down_sync(0xffffffffu, ship, 1);
                 incoming = is_last ? order : up;
             }
 
@@ -159,8 +160,8 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
 
             const double profit = ok ? profit_of(np.p, np.c, np.h, np.bc, np.target, ship, order, inv, backlog) : 0.0;
             double r;
-            if (KF(multi)) r = KF(independent) ? profit : div_by_m(tile_seq_sum<M_PAD>(profit, m), m, A.inv_m, KM_POW2);
-            else r = tile_np_sum<M_PAD>(profit, m);
+            if (KF(multi)) r = KF(independent) ? profit : div_by_m(tile_seq_sum<M_PAD>(profit, m, tbase), m, A.inv_m, KM_POW2);
+            else r = tile_np_sum<M_PAD>(profit, m, tbase);
             ret = __dadd_rn(ret, r);
             if (ok && Rg.step_reward) {
                 if (KF(multi)) Rg.step_reward[(int64_t)t * A.N * m + cell] = r;

@@ -23,12 +23,12 @@ constexpr int STEP_THREADS = 256;
 // np.sum order for the IM kinds' scalar reward (numpy pairwise_sum: sequential below 8 elements,
 // eight running accumulators from 8 to 128) — IM_env.py:372, IM_div_env.py:561.
 template <int M_PAD>
-__device__ __forceinline__ double tile_np_sum(double v, int m) {
+__device__ __forceinline__ double tile_np_sum(double v, int m, int tb) {
     if constexpr (M_PAD < 8) {
         double s = 0.0;
 #pragma unroll
         for (int j = 0; j < M_PAD; ++j) {
-            const double x = __shfl_sync(0xffffffffu, v, j, M_PAD);
+            const double x = __shfl_sync(0xffffffffu, v, tb + (j));
             if (j < m) s = __dadd_rn(s, x);
         }
         return s;
@@ -37,20 +37,20 @@ __device__ __forceinline__ double tile_np_sum(double v, int m) {
             double s = 0.0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const double x = __shfl_sync(0xffffffffu, v, j, M_PAD);
+                const double x = __shfl_sync(0xffffffffu, v, tb + (j));
                 if (j < m) s = __dadd_rn(s, x);
             }
             return s;
         }
         double r[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = __shfl_sync(0xffffffffu, v, j, M_PAD);
+        for (int j = 0; j < 8; ++j) r[j] = __shfl_sync(0xffffffffu, v, tb + (j));
         const int full = m - (m % 8);
 #pragma unroll
         for (int base = 8; base < M_PAD; base += 8) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const double x = __shfl_sync(0xffffffffu, v, base + j, M_PAD);
+                const double x = __shfl_sync(0xffffffffu, v, tb + (base + j));
                 if (base + j < full) r[j] = __dadd_rn(r[j], x);
             }
         }
@@ -58,7 +58,7 @@ __device__ __forceinline__ double tile_np_sum(double v, int m) {
                              __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
 #pragma unroll
         for (int j = 8; j < M_PAD; ++j) {
-            const double x = __shfl_sync(0xffffffffu, v, j, M_PAD);
+            const double x = __shfl_sync(0xffffffffu, v, tb + (j));
             if (j >= full && j < m) s = __dadd_rn(s, x);
         }
         return s;
@@ -68,11 +68,11 @@ __device__ __forceinline__ double tile_np_sum(double v, int m) {
 // MAIM shared reward: reward_sum starts at integer 0 and adds the profits in stage order
 // (MAIM_env.py:418-426), then / num_stages (:434).
 template <int M_PAD>
-__device__ __forceinline__ double tile_seq_sum(double v, int m) {
+__device__ __forceinline__ double tile_seq_sum(double v, int m, int tb) {
     double s = 0.0;
 #pragma unroll
     for (int j = 0; j < M_PAD; ++j) {
-        const double x = __shfl_sync(0xffffffffu, v, j, M_PAD);
+        const double x = __shfl_sync(0xffffffffu, v, tb + (j));
         if (j < m) s = __dadd_rn(s, x);
     }
     return s;
@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
     const int warp = threadIdx.x >> 5;
     const int i = lane % M_PAD;                     // stage / node owned by this lane
     const int sub = lane / M_PAD;                   // env slot inside the warp
+    const int tbase = lane - i;                     // first lane of this env's tile
     const bool stage_ok = i < KF(m);
     const int m = KF(m), O = KF(O);
 
@@ -331,14 +332,14 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
             for (int k = 0; k < MAXC; ++k) {
                 od[k] = 0;
                 if (k < KF(maxc)) {
-                    const int v = __shfl_sync(0xffffffffu, order, child_lane[k] < 0 ? 0 : child_lane[k], M_PAD);
+                    const int v = __shfl_sync(0xffffffffu, order, tbase + (child_lane[k] < 0 ? 0 : child_lane[k]));
                     od[k] = child_lane[k] < 0 ? 0 : v;
                     s += od[k];
                 }
             }
             demand = (np.retailer_idx >= 0) ? min(cust, np.inv_max) : s;
         } else {
-            const int down = __shfl_up_sync(0xffffffffu, order, 1, M_PAD);
+            const int down = __shfl_up_sync(0xffffffffu, order, 1);      // lane i-1 of the same tile (unused for i == 0)
             demand = (i == 0) ? min(cust, np.inv_max) : down;
         }
 
@@ -365,12 +366,12 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
 #pragma unroll
             for (int k = 0; k < MAXC; ++k) {
                 if (k < KF(maxc)) {
-                    const int v = __shfl_sync(0xffffffffu, st[k], np.parent < 0 ? 0 : np.parent, M_PAD);
+                    const int v = __shfl_sync(0xffffffffu, st[k], tbase + (np.parent < 0 ? 0 : np.parent));
                     if (np.parent >= 0 && np.child_slot == k) incoming = v;
                 }
             }
         } else {
-            const int up = __shfl_down_sync(0xffffffffu, ship, 1, M_PAD);
+            const int up = __shfl_down_sync(0xffffffffu, ship, 1);        // lane i+1 of the same tile (unused for the last stage)
             incoming = is_last ? order : up;
         }
 
@@ -395,9 +396,9 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
         double reward_out;
         if (KF(multi)) {
             if (KF(independent)) reward_out = profit;
-            else reward_out = div_by_m(tile_seq_sum<M_PAD>(profit, m), m, A.inv_m, KM_POW2);
+            else reward_out = div_by_m(tile_seq_sum<M_PAD>(profit, m, tbase), m, A.inv_m, KM_POW2);
         } else {
-            reward_out = tile_np_sum<M_PAD>(profit, m);
+            reward_out = tile_np_sum<M_PAD>(profit, m, tbase);
         }
 
         // ---- stores -----------------------------------------------------------------------

@@ -80,10 +80,15 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    // M_PAD is the tile width: a power of two >= m in the ahead-of-time build, exactly m in the
+    // runtime-specialised build (dense packing: 32 / m envs per warp, e.g. 5 instead of 4 for m = 6)
+    constexpr int EPW = 32 / M_PAD;
     const int i = lane % M_PAD;                      // stage / node of this lane
-    const int e_loc = tid / M_PAD;                   // env inside the tile
+    const int sub = lane / M_PAD;                    // env slot inside the warp
+    const int tbase = lane - i;                      // first lane of this env's tile
+    const int e_loc = (tid >> 5) * EPW + sub;        // env inside the CTA tile
     const int m = KF(m), O = KF(O), E = KT(E);
-    const bool ok = i < m;                            // full tiles only: every env slot is live
+    const bool ok = i < m && sub < EPW;               // full tiles only: every env slot is live
     const int cell = e_loc * m + i;                  // index inside a [E][m] tile
     const int64_t n0 = (int64_t)blockIdx.x * E;      // first env of the tile
 
@@ -196,14 +201,14 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
         for (int k = 0; k < MAXC; ++k) {
             od[k] = 0;
             if (k < KF(maxc)) {
-                const int v = __shfl_sync(0xffffffffu, order, child_lane[k] < 0 ? 0 : child_lane[k], M_PAD);
+                const int v = __shfl_sync(0xffffffffu, order, tbase + (child_lane[k] < 0 ? 0 : child_lane[k]));
                 od[k] = child_lane[k] < 0 ? 0 : v;
                 s += od[k];
             }
         }
         demand = (np.retailer_idx >= 0) ? min(cust, np.inv_max) : s;
     } else {
-        const int down = __shfl_up_sync(0xffffffffu, order, 1, M_PAD);
+        const int down = __shfl_up_sync(0xffffffffu, order, 1);
         demand = (i == 0) ? min(cust, np.inv_max) : down;
     }
     int acq = carry;
@@ -226,12 +231,12 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
             if (k < KF(maxc)) {
-                const int v = __shfl_sync(0xffffffffu, st[k], np.parent < 0 ? 0 : np.parent, M_PAD);
+                const int v = __shfl_sync(0xffffffffu, st[k], tbase + (np.parent < 0 ? 0 : np.parent));
                 if (np.parent >= 0 && np.child_slot == k) incoming = v;
             }
         }
     } else {
-        const int up = __shfl_down_sync(0xffffffffu, ship, 1, M_PAD);
+        const int up = __shfl_down_sync(0xffffffffu, ship, 1);
         incoming = is_last ? order : up;
     }
     int backlog_new = backlog + demand - ship;
@@ -252,9 +257,9 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
     double reward_out;
     if (KF(multi)) {
         if (KF(independent)) reward_out = profit;
-        else reward_out = div_by_m(tile_seq_sum<M_PAD>(profit, m), m, A.inv_m, KM_POW2);
+        else reward_out = div_by_m(tile_seq_sum<M_PAD>(profit, m, tbase), m, A.inv_m, KM_POW2);
     } else {
-        reward_out = tile_np_sum<M_PAD>(profit, m);
+        reward_out = tile_np_sum<M_PAD>(profit, m, tbase);
     }
 
     // ---- write the tile back (in place) ----------------------------------------------------------
