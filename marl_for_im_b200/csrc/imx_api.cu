@@ -100,6 +100,7 @@ struct imx_env {
     TileLayout tile_jit = {};            // runtime-specialised kernels: tile width = m (dense lane packing)
     int step_path = 0;                   // 0 auto, 1 direct only, 2 TMA wherever legal (IMX_STEP_PATH)
     int host_zero_copy = 1;              // imx_step_host addresses pinned host buffers directly (IMX_HOST_ZERO_COPY=0: staged copies)
+    int step_dense = 0;                  // experimental: m-wide tiles in the specialised step kernel (IMX_STEP_DENSE=1)
     int tma_threads = 256;               // CTA size of the TMA kernel (IMX_TMA_THREADS: 64, 128 or 256)
     int use_pdl = 1;                     // chain step launches with programmatic dependent launch (IMX_PDL=0 disables)
     int jit_policy = 0;                  // 0 auto (large batches), 1 always, -1 never (IMX_JIT)
@@ -190,7 +191,7 @@ static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, s
     addt("off_pipe", L.off_pipe); addt("off_hd", L.off_hd); addt("off_ho", L.off_ho); addt("off_carry", L.off_carry);
     addt("off_bt", L.off_bt); addt("off_dem", L.off_dem); addt("off_obs", L.off_obs); addt("off_rew", L.off_rew); addt("total", L.total);
     defs.push_back("IMX_TMA_THREADS=" + std::to_string(e->tma_threads));
-    const int mp = m_pad_of(e);                            // step kernel: power-of-two tile width (see select_kernels)
+    const int mp = e->step_dense ? e->m : m_pad_of(e);     // step kernel: power-of-two tile width (see select_kernels)
     const int pmax = (e->need_hd || e->need_ho) ? e->P : 1;
     const int maxc = e->maxc > 1 ? e->maxc : 1;
     const std::string dv = e->div ? "true" : "false";
@@ -239,17 +240,20 @@ static int select_kernels(imx_env* e) {
     e->step_grid_cap = dev_sms * occ;
     {
         const char* tt = getenv("IMX_TMA_THREADS");
-        // smaller CTAs de-synchronise the load / compute / store phases of a single-wave launch (measured:
-        // 6.09 vs 6.36 us at 65536 envs); large batches prefer the 256-thread tile
-        const int dflt = (e->N * m_pad_of(e) <= (int64_t)148 * 2048 * 2) ? 128 : 256;
+        // 128-thread CTAs de-synchronise the load / compute / store phases of neighbouring tiles and measured
+        // faster on every shipped config (profiles/r1_other_configs_1gpu.jsonl) except the 4-wide chain at
+        // multi-million-env batches, where the 256-thread tile is 2.5% ahead; 512-thread CTAs lose 25%
+        const int dflt = (m_pad_of(e) <= 4 && e->N >= ((int64_t)1 << 20)) ? 256 : 128;
         const int v = tt ? atoi(tt) : dflt;
-        e->tma_threads = (v == 64 || v == 128 || v == 256) && v >= 2 * m_pad_of(e) ? v : 256;
+        e->tma_threads = (v == 64 || v == 128 || v == 256 || v == 512) && v >= 2 * m_pad_of(e) ? v : 256;
+        const char* dn = getenv("IMX_STEP_DENSE");
+        e->step_dense = (dn && !strcmp(dn, "1")) ? 1 : 0;
     }
     compute_tile(e, e->tile, m_pad_of(e));
     // the specialised STEP kernel keeps the power-of-two tile: a dense m-wide tile makes the per-field byte
     // ranges (e.g. 40 envs x 6 nodes x 4 B = 960 B) straddle 128-byte lines, measured slower at 262144 envs;
     // the issue-bound ROLLOUT kernel is specialised with tile width = m (dense lane packing, +21% on div2)
-    compute_tile(e, e->tile_jit, m_pad_of(e));
+    compute_tile(e, e->tile_jit, e->step_dense ? e->m : m_pad_of(e));
     if (e->tile.total <= 200 * 1024)
         IMX_CUDA(cudaFuncSetAttribute((const void*)e->tma_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->tile.total));
     else

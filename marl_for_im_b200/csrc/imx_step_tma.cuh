@@ -21,10 +21,10 @@
 
 namespace imx {
 
-// Threads per CTA of the TMA kernel = M_PAD * (envs per tile).  256 for the ahead-of-time build (an
-// upper bound: the host may launch fewer); the runtime-specialised build pins the value it launches with.
+// Threads per CTA of the TMA kernel = M_PAD * (envs per tile).  512 for the ahead-of-time build (an
+// upper bound: the host launches 128 or 256); the runtime-specialised build pins the value it launches with.
 #ifndef IMX_TMA_THREADS
-#define IMX_TMA_THREADS 256
+#define IMX_TMA_THREADS 512
 #endif
 constexpr int TMA_THREADS = IMX_TMA_THREADS;
 
