@@ -53,7 +53,7 @@ extern "C" int64_t imx_launch_count(void) { return g_launches.load(); }
 // --------------------------------------------------------------------------------------
 typedef void (*step_fn_t)(const StepArgs);
 typedef void (*tma_fn_t)(const StepArgs, const TileLayout);
-typedef void (*reset_fn_t)(const StepArgs, int);
+typedef void (*reset_fn_t)(const StepArgs, const ResetArgs, int);
 typedef void (*rollout_fn_t)(const StepArgs, const RolloutArgs);
 
 struct imx_env {
@@ -376,6 +376,8 @@ static int derive(imx_env* e) {
     return 0;
 }
 
+static void launch_reset_kernel(imx_env* e, double* obs_dev, cudaStream_t s);
+
 static void fill_args(const imx_env* e, StepArgs& A) {
     const imx_config& c = e->cfg;
     memset(&A, 0, sizeof(A));
@@ -575,14 +577,8 @@ extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
     IMX_CREATE_CUDA(cudaMalloc(&e->d_returns, (size_t)N * m * sizeof(double)));
     // reset state with an all-zero demand trace (the reference constructors end with self.reset())
     IMX_CREATE_CUDA(cudaMemset(e->d_demand_T, 0, dem_bytes));
-    IMX_CREATE_CUDA(cudaMemset(e->d_state, 0, total ? total : 256));
-    IMX_CREATE_CUDA(cudaMemset(e->d_err, 0, (size_t)N * sizeof(int32_t)));
     {
-        StepArgs A;
-        fill_args(e, A);
-        A.obs = nullptr;
-        const int64_t cells = N * m;
-        e->reset_fn<<<(unsigned)((cells + 255) / 256), 256>>>(A, e->div ? 1 : 0);
+        launch_reset_kernel(e, nullptr, nullptr);
         cudaError_t le = cudaGetLastError();
         if (le != cudaSuccess) { fail(-3, "reset launch failed: %s", cudaGetErrorString(le)); imx_destroy(e); return -3; }
         g_launches.fetch_add(1);
@@ -645,6 +641,25 @@ extern "C" int imx_set_period(imx_env* e, int t) {
 // --------------------------------------------------------------------------------------
 // reset / step
 // --------------------------------------------------------------------------------------
+// launches the reset fill kernel (state zero + inv init + optional t = 0 observation)
+static void launch_reset_kernel(imx_env* e, double* obs_dev, cudaStream_t s) {
+    StepArgs A;
+    fill_args(e, A);
+    A.obs = obs_dev;
+    ResetArgs Z;
+    Z.zero_base = e->d_state;
+    Z.zero_words = (int64_t)(e->state_bytes / sizeof(int32_t));
+    Z.err = e->d_err;
+    const int64_t work = (obs_dev ? e->N * e->m * e->O : 0) > Z.zero_words / 4 ? e->N * e->m * e->O : Z.zero_words / 4;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
+    int64_t blocks = (work + 255) / 256;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    if (blocks < 1) blocks = 1;
+    const size_t smem = (size_t)e->m * e->O * sizeof(double) + (size_t)e->m * sizeof(int32_t);
+    e->reset_fn<<<(unsigned)blocks, 256, smem, s>>>(A, Z, e->div ? 1 : 0);
+}
+
 static DemandGen make_gen(const imx_env* e, uint64_t episode) {
     DemandGen g;
     g.dist = e->cfg.demand_dist; g.low = e->cfg.uniform_low; g.high = e->cfg.uniform_high;
@@ -682,14 +697,9 @@ extern "C" int imx_reset(imx_env* e, const int32_t* demand_dev, const uint8_t* d
             IMX_CHECK_LAUNCH("mask_generate_kernel");
         }
     }
-    IMX_CUDA(cudaMemsetAsync(e->d_state, 0, e->state_bytes, s));
-    IMX_CUDA(cudaMemsetAsync(e->d_err, 0, (size_t)N * sizeof(int32_t), s));
     e->t = 0;
     e->episode = episode;
-    StepArgs A;
-    fill_args(e, A);
-    A.obs = obs_dev;
-    e->reset_fn<<<cb, 256, 0, s>>>(A, e->div ? 1 : 0);
+    launch_reset_kernel(e, obs_dev, s);
     IMX_CHECK_LAUNCH("reset_kernel");
     return 0;
 }

@@ -9,22 +9,59 @@
 
 namespace imx {
 
-// One thread per (env, stage) cell.  The zero part of the state is cleared by a memset before
-// this kernel; here inv = init_inv and the t = 0 observation (every history / pipeline slot 0).
+// reset(): inv = init_inv, every other state word 0, and the t = 0 observation.  The initial
+// observation is the same m x O block for every env (all history / pipeline slots are 0), so each
+// CTA builds that block once in shared memory and the grid then streams it out with coalesced
+// 8-byte stores; the zero part of the state is written by the same kernel (no memset nodes).
+struct ResetArgs {
+    int32_t* zero_base;        // the state block (all fields back to back) ...
+    int64_t zero_words;        // ... and its length in int32 words
+    int32_t* err;              // [N] watchdog flags, cleared
+};
+
 template <int DMAX, int PMAX>
-__global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ StepArgs A, int div) {
-    const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= A.N * KF(m)) return;
-    const int i = (int)(cell % KF(m));
-    const NodeParams np = load_node(A.nodes + i);
-    A.inv[cell] = np.init_inv;
-    if (KHAS(obs)) {
-        int pipe[DMAX], hd[PMAX], ho[PMAX];
+__global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ ResetArgs Z, int div) {
+    extern __shared__ double s_tmpl[];                  // [m][O] observation template, then int init_inv[m]
+    const int m = A.m, O = A.O;
+    int32_t* s_init = reinterpret_cast<int32_t*>(s_tmpl + m * O);
+    if ((int)threadIdx.x < m) {
+        const int i = threadIdx.x;
+        const NodeParams np = load_node(A.nodes + i);
+        s_init[i] = np.init_inv;
+        if (A.obs) {
+            int pipe[DMAX], hd[PMAX], ho[PMAX];
 #pragma unroll
-        for (int k = 0; k < DMAX; ++k) pipe[k] = 0;
+            for (int k = 0; k < DMAX; ++k) pipe[k] = 0;
 #pragma unroll
-        for (int j = 0; j < PMAX; ++j) { hd[j] = 0; ho[j] = 0; }
-        write_obs_row<DMAX, PMAX>(A.obs + cell * KF(O), A, np, i, KHAS(tab) ? A.tab + (size_t)i * 4 * KF(TL) : nullptr, np.init_inv, 0, 0, pipe, hd, ho, div != 0);
+            for (int j = 0; j < PMAX; ++j) { hd[j] = 0; ho[j] = 0; }
+            write_obs_row<DMAX, PMAX>(s_tmpl + i * O, A, np, i, A.tab ? A.tab + (size_t)i * 4 * A.TL : nullptr, np.init_inv, 0, 0, pipe, hd,
+                                      ho, div != 0);
+        }
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // zero the whole state block (16 bytes per store), then overwrite inv with init_inv
+    int4* z4 = reinterpret_cast<int4*>(Z.zero_base);
+    const int64_t n4 = Z.zero_words / 4;
+    for (int64_t k = gtid; k < n4; k += stride) z4[k] = make_int4(0, 0, 0, 0);
+    for (int64_t k = n4 * 4 + gtid; k < Z.zero_words; k += stride) Z.zero_base[k] = 0;
+    for (int64_t k = gtid; k < A.N; k += stride) Z.err[k] = 0;
+    if (A.obs) {
+        const int64_t total = A.N * m * O;
+        const int mo = m * O;
+        for (int64_t k = gtid; k < total; k += stride) A.obs[k] = s_tmpl[(int)(k % mo)];
+    }
+    // inv lives inside the zeroed block: a grid-wide ordering is needed between the zero fill and the
+    // init fill of the same words, so the init fill is done by the thread that zeroed the word:
+    // inv is the FIRST field of the block (offset 0), words [0, N*m)
+    const int64_t cells = A.N * m;
+    for (int64_t k = gtid; k < (cells + 3) / 4; k += stride) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t c = k * 4 + q;
+            if (c < cells) A.inv[c] = s_init[(int)(c % m)];
+        }
     }
 }
 
