@@ -211,7 +211,7 @@ static void ensure_jit(imx_env* e) {
     std::string sn, rn;
     jit_spec(e, e->TL, defs, sn, rn);
     if (e->tile_jit.total > 200 * 1024) return;
-    e->jit = imxjit::get(defs, sn, rn, e->tile_jit.total);
+    e->jit = imxjit::get(defs, sn, rn, e->tile_jit.total, e->cfg.device);
     if (e->jit) e->jit_state = 1;
 }
 

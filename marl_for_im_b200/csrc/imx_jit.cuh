@@ -101,10 +101,11 @@ static bool read_file(const std::string& path, std::string& out) {
 // Compiles (or fetches from the in-process cache) the kernels specialised by `defines`.
 // step_name / rollout_name are C++ name expressions of the template instantiations.
 static const Kernels* get(const std::vector<std::string>& defines, const std::string& step_name,
-                          const std::string& rollout_name, int step_smem_bytes) {
+                          const std::string& rollout_name, int step_smem_bytes, int device) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (!load_api()) return nullptr;
-    std::string key = step_name + "|" + rollout_name;
+    // a CUmodule belongs to the context it was loaded in: one cache entry per (device, specialisation)
+    std::string key = "dev" + std::to_string(device) + "|" + step_name + "|" + rollout_name;
     for (const auto& d : defines) key += "|" + d;
     auto it = g_cache.find(key);
     if (it != g_cache.end()) return it->second.mod ? &it->second : nullptr;
