@@ -23,7 +23,7 @@
  *
  * Data layout (row-major, env index slowest unless stated)
  *   actions  [N][m] float64      reward (MAIM kinds) [N][m] float64, (IM kinds) [N] float64
- *   obs      [N][m][O] float64   row i of env n = agent i's observation vector
+ *   obs      [N][m][O] float64   row i of env n = agent i's observation vector (float32 when cfg.obs_f32)
  *   demand   [N][R][T] int32     replayed customer demand, R = number of retailers (serial: 1)
  *   mask     [N][T][m] uint8     replayed noisy-delay Bernoulli outcomes (u <= threshold)
  *   state    int32 structure-of-arrays, see imx_state_field()
@@ -69,6 +69,8 @@ typedef struct imx_config {
     int32_t uniform_low;          /* IMX_DIST_UNIFORM: integers in [low, high)               */
     int32_t uniform_high;
     int32_t device;               /* CUDA device ordinal                                      */
+    int32_t obs_f32;              /* 1: observations are written as float32 (= the float32 cast of the reference's float64 value; RLlib casts anyway), obs buffers are [N][m][O] float */
+    int32_t reserved0;
     double a, b;                  /* rescale interval (IM_DIV: the host passes -1, 1)        */
     double mu;                    /* IMX_DIST_POISSON mean                                   */
     double noisy_delay_threshold; /* used when the mask is generated (Philox) instead of replayed */

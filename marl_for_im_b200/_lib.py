@@ -23,6 +23,7 @@ class ImxConfig(C.Structure):
         ("standardise_state", C.c_int32), ("standardise_actions", C.c_int32), ("independent", C.c_int32),
         ("share_network", C.c_int32), ("noisy_delay", C.c_int32), ("demand_dist", C.c_int32),
         ("uniform_low", C.c_int32), ("uniform_high", C.c_int32), ("device", C.c_int32),
+        ("obs_f32", C.c_int32), ("reserved0", C.c_int32),
         ("a", C.c_double), ("b", C.c_double), ("mu", C.c_double), ("noisy_delay_threshold", C.c_double),
         ("seed", C.c_uint64), ("num_envs", C.c_int64), ("env_offset", C.c_int64),
         ("inv_init", C.c_int32 * MAX_NODES), ("inv_max", C.c_int32 * MAX_NODES),

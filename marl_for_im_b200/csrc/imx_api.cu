@@ -162,7 +162,7 @@ static void compute_tile(const imx_env* e, TileLayout& L, int tile_width) {
     L.off_carry = take(e->has_carry ? E * m * 4 : 0);
     L.off_bt = take(E * e->NB * 4);
     L.off_dem = take(e->R * E * 4);
-    L.off_obs = take(E * m * e->O * 8);
+    L.off_obs = take(E * m * e->O * (e->cfg.obs_f32 ? 4 : 8));
     L.off_rew = take(E * m * 8);
     L.total = off;
 }
@@ -180,7 +180,7 @@ static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, s
     add("td", c.time_dependency != 0); add("pd", c.prev_demand != 0); add("pa", c.prev_actions != 0);
     add("write_hd", e->write_hd); add("noisy", 0); add("has_carry", e->has_carry); add("need_hd", e->need_hd);
     add("need_ho", e->need_ho); add("wd_mult1", e->multi ? 2 : 4); add("wd_mult", e->multi ? 1 : 2); add("TL", TL);
-    add("has_info", 0); add("has_obs", 1); add("has_tab", TL > 0);
+    add("has_info", 0); add("has_obs", 1); add("has_tab", TL > 0); add("obs_f32", c.obs_f32 != 0);
     int ex = 0;
     const double fr = std::frexp(c.b - c.a, &ex);
     add("bma_pow2", (fr == 0.5 && ex > -1000 && ex < 1000) ? 1 : 0);
@@ -230,8 +230,8 @@ static int select_kernels(imx_env* e) {
         else pick_kernels<32, false>(e);
     }
     const int epw = 32 / e->m_pad;
-    const int tile_doubles = (epw * m * e->O + 1) & ~1;
-    e->step_smem = (size_t)(STEP_THREADS / 32) * tile_doubles * sizeof(double);
+    const int tile_bytes = (epw * m * e->O * (e->cfg.obs_f32 ? 4 : 8) + 15) & ~15;
+    e->step_smem = (size_t)(STEP_THREADS / 32) * tile_bytes;
     IMX_CUDA(cudaFuncSetAttribute((const void*)e->step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem));
     int dev_sms = 0, occ = 0;
     IMX_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e->cfg.device));
@@ -396,6 +396,7 @@ static void fill_args(const imx_env* e, StepArgs& A) {
     A.noisy = e->noisy_now;
     A.has_carry = e->has_carry;
     A.need_hd = e->need_hd; A.need_ho = e->need_ho;
+    A.obs_f32 = c.obs_f32 != 0;
     // watchdog thresholds: MAIM_div 2*dm, dm, dm, dm (:504,526,560,574); IM_div 4*dm, 2*dm, 2*dm, 2*dm (:424,449,483,497)
     A.wd_mult1 = e->multi ? 2 : 4;
     A.wd_mult = e->multi ? 1 : 2;
@@ -656,7 +657,7 @@ static void launch_reset_kernel(imx_env* e, double* obs_dev, cudaStream_t s) {
     int64_t blocks = (work + 255) / 256;
     if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
     if (blocks < 1) blocks = 1;
-    const size_t smem = (size_t)e->m * e->O * sizeof(double) + (size_t)e->m * sizeof(int32_t);
+    const size_t smem = (size_t)e->m * e->O * sizeof(double) + (size_t)e->m * sizeof(int32_t);   // template sized for float64
     e->reset_fn<<<(unsigned)blocks, 256, smem, s>>>(A, Z, e->div ? 1 : 0);
 }
 
@@ -883,7 +884,7 @@ static int ensure_host_path(imx_env* e) {
     IMX_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
     const size_t cells = (size_t)e->N * e->m;
     IMX_CUDA(cudaMalloc(&e->d_act_h, cells * sizeof(double)));
-    IMX_CUDA(cudaMalloc(&e->d_obs_h, cells * e->O * sizeof(double)));
+    IMX_CUDA(cudaMalloc(&e->d_obs_h, cells * e->O * (e->cfg.obs_f32 ? 4 : 8)));
     IMX_CUDA(cudaMalloc(&e->d_rew_h, cells * sizeof(double)));
     IMX_CUDA(cudaMalloc(&e->d_dem_h, (size_t)e->N * e->R * e->T * sizeof(int32_t)));
     if (e->has_carry) IMX_CUDA(cudaMalloc(&e->d_mask_h, (size_t)e->N * e->T * e->m));
@@ -907,7 +908,7 @@ extern "C" int imx_reset_host(imx_env* e, const int32_t* demand_host, const uint
                    obs_host ? e->d_obs_h : nullptr, s);
     if (rc) return rc;
     if (obs_host)
-        IMX_CUDA(cudaMemcpyAsync(obs_host, e->d_obs_h, (size_t)e->N * e->m * e->O * sizeof(double), cudaMemcpyDeviceToHost, s));
+        IMX_CUDA(cudaMemcpyAsync(obs_host, e->d_obs_h, (size_t)e->N * e->m * e->O * (e->cfg.obs_f32 ? 4 : 8), cudaMemcpyDeviceToHost, s));
     IMX_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
@@ -943,7 +944,7 @@ extern "C" int imx_step_host(imx_env* e, const double* actions_host, double* obs
     IMX_CUDA(cudaMemcpyAsync(e->d_act_h, actions_host, cells * sizeof(double), cudaMemcpyHostToDevice, s));
     rc = launch_step(e, e->d_act_h, obs_host ? e->d_obs_h : nullptr, e->d_rew_h, nullptr, s);
     if (rc) return rc;
-    if (obs_host) IMX_CUDA(cudaMemcpyAsync(obs_host, e->d_obs_h, cells * e->O * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (obs_host) IMX_CUDA(cudaMemcpyAsync(obs_host, e->d_obs_h, cells * e->O * (e->cfg.obs_f32 ? 4 : 8), cudaMemcpyDeviceToHost, s));
     IMX_CUDA(cudaMemcpyAsync(reward_host, e->d_rew_h, (e->multi ? cells : (size_t)e->N) * sizeof(double), cudaMemcpyDeviceToHost, s));
     IMX_CUDA(cudaStreamSynchronize(s));
     return 0;
@@ -998,6 +999,7 @@ extern "C" int imx_cc_observe(imx_env* e, const double* obs_dev, const double* a
                               void* out_dev, int out_is_f32, void* stream) {
     if (!e || !obs_dev || !out_dev) return fail(-1, "null argument");
     if (!e->multi) return fail(-1, "the centralised-critic observation is defined for the multi-agent kinds");
+    if (e->cfg.obs_f32) return fail(-1, "imx_cc_observe reads float64 observations; create the env with obs_f32 = 0 and ask for float32 output instead");
     IMX_CUDA(cudaSetDevice(e->cfg.device));
     const int W = (e->m - 1) * (1 + e->O) + e->O;
     const int64_t total = e->N * e->m * W;

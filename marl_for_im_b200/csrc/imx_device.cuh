@@ -97,6 +97,7 @@ struct StepArgs {
     int32_t has_carry;         // carry field allocated
     int32_t need_hd, need_ho;  // history state present
     int32_t has_info;          // any imx_info_out pointer set
+    int32_t obs_f32;           // observations are written as float32 (the cast of the float64 value), else float64
     int32_t wd_mult1, wd_mult;   // watchdog multipliers: LOOP1(A) and the other three
     double a, b, bma;          // bma = b - a
     double inv_bma;            // 1/(b-a) when b-a is a power of two (the division is then an exact scaling), else 0
@@ -165,6 +166,13 @@ __device__ __forceinline__ double scaled(bool has_tab, const double* __restrict_
 __device__ __forceinline__ double div_by_m(double s, int m, double inv_m, bool m_pow2) {
     return m_pow2 ? __dmul_rn(s, inv_m) : __ddiv_rn(s, (double)m);
 }
+// One observation element.  `row` addresses the agent's vector in the output element type.
+#define OBS_PUT(row, k, v)                                                           \
+    do {                                                                             \
+        if (KF(obs_f32)) reinterpret_cast<float*>(row)[k] = (float)(v);              \
+        else reinterpret_cast<double*>(row)[k] = (v);                                \
+    } while (0)
+
 // profit = p*ship - c*order - h*|inv' - target| - bc*backlog'           MAIM_env.py:421-424
 __device__ __forceinline__ double profit_of(double p, double c, double h, double bc, double target,
                                             int ship, int order, int inv_new, int backlog_new) {

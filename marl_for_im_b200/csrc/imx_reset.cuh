@@ -21,8 +21,9 @@ struct ResetArgs {
 
 template <int DMAX, int PMAX>
 __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ ResetArgs Z, int div) {
-    extern __shared__ double s_tmpl[];                  // [m][O] observation template, then int init_inv[m]
+    extern __shared__ double s_tmpl[];                  // [m][O] observation template (8 bytes reserved per element), then int init_inv[m]
     const int m = A.m, O = A.O;
+    const int es = A.obs_f32 ? 4 : 8;
     int32_t* s_init = reinterpret_cast<int32_t*>(s_tmpl + m * O);
     if ((int)threadIdx.x < m) {
         const int i = threadIdx.x;
@@ -34,7 +35,7 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
             for (int k = 0; k < DMAX; ++k) pipe[k] = 0;
 #pragma unroll
             for (int j = 0; j < PMAX; ++j) { hd[j] = 0; ho[j] = 0; }
-            write_obs_row<DMAX, PMAX>(s_tmpl + i * O, A, np, i, A.tab ? A.tab + (size_t)i * 4 * A.TL : nullptr, np.init_inv, 0, 0, pipe, hd,
+            write_obs_row<DMAX, PMAX>(reinterpret_cast<unsigned char*>(s_tmpl) + (size_t)i * O * es, A, np, i, A.tab ? A.tab + (size_t)i * 4 * A.TL : nullptr, np.init_inv, 0, 0, pipe, hd,
                                       ho, div != 0);
         }
     }
@@ -50,7 +51,13 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
     if (A.obs) {
         const int64_t total = A.N * m * O;
         const int mo = m * O;
-        for (int64_t k = gtid; k < total; k += stride) A.obs[k] = s_tmpl[(int)(k % mo)];
+        if (A.obs_f32) {
+            float* dst = reinterpret_cast<float*>(A.obs);
+            const float* src = reinterpret_cast<const float*>(s_tmpl);
+            for (int64_t k = gtid; k < total; k += stride) dst[k] = src[(int)(k % mo)];
+        } else {
+            for (int64_t k = gtid; k < total; k += stride) A.obs[k] = s_tmpl[(int)(k % mo)];
+        }
     }
     // inv lives inside the zeroed block: a grid-wide ordering is needed between the zero fill and the
     // init fill of the same words, so the init fill is done by the thread that zeroed the word:

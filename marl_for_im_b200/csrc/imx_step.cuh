@@ -173,7 +173,7 @@ __device__ __forceinline__ int split_ship(int nchild, int ship, int demand, int 
 // Writes one agent's observation vector (O doubles) — the field order and per-field maxima of
 // SURVEY.md table A.5.  `row` points into the warp's shared-memory staging tile.
 template <int DMAX, int PMAX>
-__device__ __forceinline__ void write_obs_row(double* row, const StepArgs& A, const NodeParams& np, int node_idx,
+__device__ __forceinline__ void write_obs_row(void* row, const StepArgs& A, const NodeParams& np, int node_idx,
                                               const double* __restrict__ tabrow, int inv, int backlog, int order_u,
                                               const int (&pipe)[DMAX], const int (&hd)[PMAX], const int (&ho)[PMAX], bool div) {
     const double a = A.a, bma = A.bma;
@@ -182,21 +182,21 @@ __device__ __forceinline__ void write_obs_row(double* row, const StepArgs& A, co
     const double dem_max = (double)np.demand_max;
     const double ou_max = KF(multi) ? order_max : inv_max;   // MAIM_env.py:300 vs IM_env.py:265
     if (KF(std_state)) {
-        row[0] = scaled(KHAS(tab), tabrow, TL, TAB_INV, inv, inv_max, a, bma);
-        row[1] = scaled(KHAS(tab), tabrow, TL, TAB_DEM, backlog, dem_max, a, bma);
-        row[2] = scaled(KHAS(tab), tabrow, TL, KF(multi) ? TAB_ORD : TAB_INV, order_u, ou_max, a, bma);
+        OBS_PUT(row, 0, scaled(KHAS(tab), tabrow, TL, TAB_INV, inv, inv_max, a, bma));
+        OBS_PUT(row, 1, scaled(KHAS(tab), tabrow, TL, TAB_DEM, backlog, dem_max, a, bma));
+        OBS_PUT(row, 2, scaled(KHAS(tab), tabrow, TL, KF(multi) ? TAB_ORD : TAB_INV, order_u, ou_max, a, bma));
     } else {
-        row[0] = (double)inv;
-        row[1] = (double)backlog;
-        row[2] = (double)order_u;
+        OBS_PUT(row, 0, (double)inv);
+        OBS_PUT(row, 1, (double)backlog);
+        OBS_PUT(row, 2, (double)order_u);
     }
     if (KF(multi) && !KF(std_state)) {
         // MAIM_env.py:319-324 (quirk 13): raw pipeline at [3:3+D] whatever the history offsets, rest stays 0
-        for (int k = 3; k < KF(O); ++k) row[k] = 0.0;
+        for (int k = 3; k < KF(O); ++k) OBS_PUT(row, k, 0.0);
         if (KF(td)) {
 #pragma unroll
             for (int k = 0; k < DMAX; ++k)
-                if (k < KF(D)) row[3 + k] = (double)pipe[k];
+                if (k < KF(D)) OBS_PUT(row, 3 + k, (double)pipe[k]);
         }
         return;
     }
@@ -204,13 +204,13 @@ __device__ __forceinline__ void write_obs_row(double* row, const StepArgs& A, co
     if (KF(pd)) {
 #pragma unroll
         for (int j = 0; j < PMAX; ++j)
-            if (j < KF(P)) row[k0 + j] = KF(write_hd) ? scaled(KHAS(tab), tabrow, TL, TAB_DEM, hd[j], dem_max, a, bma) : 0.0;   // quirk 2
+            if (j < KF(P)) OBS_PUT(row, k0 + j, KF(write_hd) ? scaled(KHAS(tab), tabrow, TL, TAB_DEM, hd[j], dem_max, a, bma) : 0.0);   // quirk 2
         k0 += KF(P);
     }
     if (KF(pa)) {
 #pragma unroll
         for (int j = 0; j < PMAX; ++j)
-            if (j < KF(P)) row[k0 + j] = scaled(KHAS(tab), tabrow, TL, TAB_ORD, ho[j], order_max, a, bma);
+            if (j < KF(P)) OBS_PUT(row, k0 + j, scaled(KHAS(tab), tabrow, TL, TAB_ORD, ho[j], order_max, a, bma));
         k0 += KF(P);
     }
     if (KF(td)) {
@@ -221,30 +221,31 @@ __device__ __forceinline__ void write_obs_row(double* row, const StepArgs& A, co
                 if (!KF(std_state)) v = (double)pipe[k];                                    // IM kinds, raw
                 else if (div && KF(multi)) v = scaled(KHAS(tab), tabrow, TL, TAB_PIPE2, min(pipe[k], 2 * np.inv_max), 2.0 * inv_max, a, bma);   // MAIM_div_env.py:408-411
                 else v = scaled(KHAS(tab), tabrow, TL, TAB_INV, pipe[k], inv_max, a, bma);
-                row[k0 + k] = v;
+                OBS_PUT(row, k0 + k, v);
             }
         }
         k0 += KF(D);
     }
-    if (KF(share_network)) row[k0] = rescale((double)node_idx, (double)KF(m), a, bma);       // MAIM_div_env.py:434-435
+    if (KF(share_network)) OBS_PUT(row, k0, rescale((double)node_idx, (double)KF(m), a, bma));       // MAIM_div_env.py:434-435
 }
 
-// Flushes a warp's staged observation tile (`doubles` contiguous float64 values) to global memory.
-__device__ __forceinline__ void flush_obs_tile(double* gdst, const double* stile, int doubles, int lane) {
-    const uint32_t bytes = (uint32_t)doubles * 8u;
+// Flushes a warp's staged observation tile (`bytes` contiguous bytes, a multiple of 4) to global memory.
+__device__ __forceinline__ void flush_obs_tile(void* gdst, const void* stile, uint32_t bytes, int lane) {
     const bool bulk_ok = ((bytes & 15u) == 0u) && ((reinterpret_cast<uintptr_t>(gdst) & 15u) == 0u);
     if (bulk_ok) fence_proxy_async_smem();      // every writer orders its stores before the async-proxy read
     __syncwarp();
     if (bulk_ok) {
         if (lane == 0) bulk_store_s2g(gdst, stile, bytes);
     } else {
-        for (int k = lane; k < doubles; k += 32) gdst[k] = stile[k];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(stile);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(gdst);
+        for (uint32_t k = lane; k < bytes / 4u; k += 32) dst[k] = src[k];
     }
 }
 
 template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV>
 __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constant__ StepArgs A) {
-    extern __shared__ __align__(16) double smem_obs[];
+    extern __shared__ __align__(16) unsigned char smem_obs[];
     constexpr int EPW = 32 / M_PAD;                 // envs per warp
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -266,8 +267,9 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
     const double om_d = (double)np.order_max;
     const double* __restrict__ tabrow = KHAS(tab) ? A.tab + (size_t)(stage_ok ? i : 0) * 4 * KF(TL) : nullptr;
 
-    const int tile_doubles = (EPW * m * O + 1) & ~1;             // keep every warp's tile 16-byte aligned
-    double* wtile = smem_obs + (size_t)warp * tile_doubles;
+    const int es = KF(obs_f32) ? 4 : 8;                          // observation element size
+    const int tile_bytes = (EPW * m * O * es + 15) & ~15;        // keep every warp's tile 16-byte aligned
+    unsigned char* wtile = smem_obs + (size_t)warp * tile_bytes;
     bool tile_in_flight = false;
 
     const int64_t warps_in_grid = (int64_t)gridDim.x * (STEP_THREADS / 32);
@@ -443,12 +445,12 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
                 if (A.info.order_dev) A.info.order_dev[cell] = order;
                 if (A.info.profit_dev) A.info.profit_dev[cell] = profit;
             }
-            if (KHAS(obs)) write_obs_row<DMAX, PMAX>(wtile + (size_t)(sub * m + i) * O, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
+            if (KHAS(obs)) write_obs_row<DMAX, PMAX>(wtile + (size_t)(sub * m + i) * O * es, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
         }
         if (KHAS(obs)) {
             const int64_t first = wt * EPW;
             const int envs_here = (int)min((int64_t)EPW, A.N - first);
-            flush_obs_tile(A.obs + first * m * O, wtile, envs_here * m * O, lane);
+            flush_obs_tile(reinterpret_cast<unsigned char*>(A.obs) + first * m * O * es, wtile, (uint32_t)(envs_here * m * O * es), lane);
             tile_in_flight = true;
         }
     }

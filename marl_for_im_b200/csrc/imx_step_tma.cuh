@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
     int32_t* s_carry = reinterpret_cast<int32_t*>(smem + KT(off_carry));
     int32_t* s_bt = reinterpret_cast<int32_t*>(smem + KT(off_bt));
     int32_t* s_dem = reinterpret_cast<int32_t*>(smem + KT(off_dem));
-    double* s_obs = reinterpret_cast<double*>(smem + KT(off_obs));
+    unsigned char* s_obs = smem + KT(off_obs);
+    const int es = KF(obs_f32) ? 4 : 8;              // observation element size
     double* s_rew = reinterpret_cast<double*>(smem + KT(off_rew));
 
     const uint32_t b_cell4 = (uint32_t)E * m * 4u, b_cell8 = (uint32_t)E * m * 8u;
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
         }
         if (KF(multi)) s_rew[cell] = reward_out;
         else if (i == 0) s_rew[e_loc] = reward_out;
-        if (KHAS(obs)) write_obs_row<DMAX, PMAX>(s_obs + (size_t)cell * O, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
+        if (KHAS(obs)) write_obs_row<DMAX, PMAX>(s_obs + (size_t)cell * O * es, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
         // optional diagnostics go straight to global memory (off the fast path)
         if (KF(has_info)) {
         const int64_t gcell = (n0 + e_loc) * m + i;
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
         if (KF(need_ho)) bulk_store_only(A.hist_o + n0 * m * KF(P), s_ho, b_hist);
         if (KF(has_carry)) bulk_store_only(A.carry + n0 * m, s_carry, b_cell4);
         if (DIV && KF(NB) > 0) bulk_store_only(A.bt + n0 * KF(NB), s_bt, b_bt);
-        if (KHAS(obs)) bulk_store_only(A.obs + n0 * m * O, s_obs, b_cell8 * (uint32_t)O);
+        if (KHAS(obs)) bulk_store_only(reinterpret_cast<unsigned char*>(A.obs) + n0 * m * O * es, s_obs, (uint32_t)E * m * O * es);
         bulk_store_only(A.reward + (KF(multi) ? n0 * m : n0), s_rew, KF(multi) ? b_cell8 : (uint32_t)E * 8u);
         bulk_commit();
         bulk_wait_read_all();            // shared memory must outlive the bulk engine's reads

@@ -114,6 +114,9 @@ class _ImxEnvBase:
         self.return_info = bool(take("return_info", not self.batched))
         self.reuse_buffers = bool(take("reuse_buffers", False))
         self.demand_mode = take("demand_mode", "philox" if self.batched else "host")
+        obs_dtype = take("obs_dtype", "float64")             # "float32": the cast RLlib applies anyway, half the bytes
+        self.obs_dtype = {"float64": torch.float64, "float32": torch.float32, torch.float64: torch.float64,
+                          torch.float32: torch.float32}[obs_dtype]
         self.mu = self.config.get("mu", 5)
         if self.demand_dist == "poisson":                    # callers pre-draw test sets with env.dist.rvs (inv_management.py:200)
             from scipy.stats import poisson
@@ -160,6 +163,7 @@ class _ImxEnvBase:
         lower_upper = self.config.get("lower_upper", (1, 5))
         c.uniform_low, c.uniform_high = int(lower_upper[0]), int(lower_upper[1])
         c.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        c.obs_f32 = int(self.obs_dtype == torch.float32)
         c.a, c.b = float(self.a), float(self.b)
         c.mu = float(self.config.get("mu", 5))
         c.noisy_delay_threshold = float(self.noisy_delay_threshold)
@@ -396,9 +400,9 @@ class _ImxEnvBase:
         N, m, O = self.num_envs, self.num_nodes, self.obs_len
         if self.reuse_buffers:
             if getattr(self, "_obs_buf", None) is None:
-                self._obs_buf = torch.empty((N, m, O), dtype=torch.float64, device=self.device)
+                self._obs_buf = torch.empty((N, m, O), dtype=self.obs_dtype, device=self.device)
             return self._obs_buf
-        return torch.empty((N, m, O), dtype=torch.float64, device=self.device)
+        return torch.empty((N, m, O), dtype=self.obs_dtype, device=self.device)
 
     def _new_reward(self):
         shape = (self.num_envs, self.num_nodes) if self.MULTI else (self.num_envs,)
