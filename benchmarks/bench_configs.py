@@ -115,6 +115,7 @@ def time_rollout(kind, cfg, N, reps, replay):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--only", default="", help="run only the cases whose name contains this text (ncu captures)")
     args = ap.parse_args()
     jobs = [
         ("config2 MAIM 4-stage step, 65536 envs", lambda: time_steps("MAIM", presets.serial4(), 65536, args.reps)),
@@ -134,6 +135,8 @@ def main():
         ("MAIM_div div2 fused rollout, 262144 envs, philox", lambda: time_rollout("MAIM_div", presets.div2(), 262144, args.reps, False)),
     ]
     for name, fn in jobs:
+        if args.only and args.only not in name:
+            continue
         try:
             res = fn()
         except Exception as exc:

@@ -74,6 +74,8 @@ typedef struct imx_config {
     double a, b;                  /* rescale interval (IM_DIV: the host passes -1, 1)        */
     double mu;                    /* IMX_DIST_POISSON mean                                   */
     double noisy_delay_threshold; /* used when the mask is generated (Philox) instead of replayed */
+    double noisy_demand_threshold; /* divergent kinds, generated demand only (MAIM_div_env.py:287-295): each period's draw is
+                                      doubled with this probability, then zeroed with this probability; 0 = off */
     uint64_t seed;                /* Philox key                                               */
     int64_t num_envs;             /* N: envs in this handle (this rank's shard)              */
     int64_t env_offset;           /* global index of local env 0 (Philox counter; makes results independent of sharding) */
@@ -187,6 +189,22 @@ int imx_return_stats(imx_env* env, const double* return_dev, double* stats_dev /
  * up on the device, reduced across GPUs once).  Three launches, no host work: graph-capturable. */
 int imx_episode_stats(imx_env* env, const double* step_reward_dev, int periods, double* return_dev, double* stats_dev,
                       int accumulate, void* stream);
+
+/* The evaluation loops' per-episode accumulators  —  MA_inv_management.py:538-587 (same loop:
+ * CC_inv_management.py:512-556, CC_inv_management_div.py:500-544, inv_management.py:573-606, and the LP replay
+ * loops, e.g. DSHLP_4.py:896-928).  Call once after every step() with that step's outputs:
+ *   acc_dev [N][4 + m] float64 rows {episode_reward, total_inventory, total_backlog, customer_backlog,
+ *           stage_profit[0..m-1]}: inventory/backlog are obs[.][0] / obs[.][1] mapped back with
+ *           rev_scale(., 0, inv_max[stage], a, b) when the env standardises its state, summed over stages in
+ *           stage order and then over periods, in float64, operation for operation like the host loop;
+ *   profit_dev [N][m] (imx_info_out.profit_dev of the same step) or NULL: stage_profit columns stay as they are;
+ *   reset != 0 starts a new episode (accumulators begin at zero).
+ * imx_eval_stats reduces the rows to {n, then per column (sum, sum of squares)} = 1 + 2(4 + m) doubles, the
+ * np.mean / np.std inputs of MA_inv_management.py:589-600; accumulate != 0 adds into stats_dev.  Deterministic. */
+int imx_eval_len(const imx_env* env);   /* 4 + m */
+int imx_eval_accumulate(imx_env* env, const void* obs_dev, const double* reward_dev, const double* profit_dev,
+                        double* acc_dev, int reset, void* stream);
+int imx_eval_stats(imx_env* env, const double* acc_dev, double* stats_dev, int accumulate, void* stream);
 
 /* central_critic_observer + FillInActions  —  models/CC_Model.py:165-214 (and the hand-built CC
  * observation of CC_inv_management.py:516-528): for every agent the flat vector

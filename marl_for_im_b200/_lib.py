@@ -24,7 +24,7 @@ class ImxConfig(C.Structure):
         ("share_network", C.c_int32), ("noisy_delay", C.c_int32), ("demand_dist", C.c_int32),
         ("uniform_low", C.c_int32), ("uniform_high", C.c_int32), ("device", C.c_int32),
         ("obs_f32", C.c_int32), ("reserved0", C.c_int32),
-        ("a", C.c_double), ("b", C.c_double), ("mu", C.c_double), ("noisy_delay_threshold", C.c_double),
+        ("a", C.c_double), ("b", C.c_double), ("mu", C.c_double), ("noisy_delay_threshold", C.c_double), ("noisy_demand_threshold", C.c_double),
         ("seed", C.c_uint64), ("num_envs", C.c_int64), ("env_offset", C.c_int64),
         ("inv_init", C.c_int32 * MAX_NODES), ("inv_max", C.c_int32 * MAX_NODES),
         ("order_max", C.c_int32 * MAX_NODES), ("delay", C.c_int32 * MAX_NODES),
@@ -66,6 +66,9 @@ SYMBOLS = {
     "imx_step_host": (C.c_int, [_P, _P, _P, _P]),
     "imx_poisson_cdf": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "imx_episode_stats": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
+    "imx_eval_len": (C.c_int, [_P]),
+    "imx_eval_accumulate": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
+    "imx_eval_stats": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "imx_cc_obs_len": (C.c_int, [_P]),
     "imx_cc_observe": (C.c_int, [_P, _P, _P, C.c_double, C.c_double, _P, C.c_int, _P]),
     "imx_kernel_variant": (C.c_int, [_P]),

@@ -15,6 +15,7 @@
 #include "imx_rollout.cuh"
 #include "imx_jit.cuh"
 #include "imx_cc.cuh"
+#include "imx_eval.cuh"
 
 using namespace imx;
 
@@ -80,7 +81,7 @@ struct imx_env {
     double* d_cdf = nullptr;
     uint16_t* d_guide = nullptr;         // cutpoint table of the Poisson inversion
     int cdf_len = 0;
-    double* d_stats_partial = nullptr;   // [2 + 2m][STATS_BLOCKS] scratch of imx_return_stats
+    double* d_stats_partial = nullptr;   // [max(2 + 2m, 2(4 + m))][STATS_BLOCKS] scratch of imx_return_stats / imx_eval_stats
     double* d_returns = nullptr;         // [N][cols] scratch of imx_episode_stats
     double* d_tab = nullptr;             // [m][4][TL] rescale tables
     int TL = 0;
@@ -574,7 +575,7 @@ extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
             IMX_CREATE_CUDA(cudaMemcpy(e->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
         }
     }
-    IMX_CREATE_CUDA(cudaMalloc(&e->d_stats_partial, (size_t)(2 + 2 * IMX_MAX_NODES) * STATS_BLOCKS * sizeof(double)));
+    IMX_CREATE_CUDA(cudaMalloc(&e->d_stats_partial, (size_t)(2 * EVAL_FIXED + 2 + 2 * IMX_MAX_NODES) * STATS_BLOCKS * sizeof(double)));
     IMX_CREATE_CUDA(cudaMalloc(&e->d_returns, (size_t)N * m * sizeof(double)));
     // reset state with an all-zero demand trace (the reference constructors end with self.reset())
     IMX_CREATE_CUDA(cudaMemset(e->d_demand_T, 0, dem_bytes));
@@ -665,6 +666,7 @@ static DemandGen make_gen(const imx_env* e, uint64_t episode) {
     DemandGen g;
     g.dist = e->cfg.demand_dist; g.low = e->cfg.uniform_low; g.high = e->cfg.uniform_high;
     g.cdf_len = e->cdf_len; g.cdf = e->d_cdf; g.guide = e->d_guide; g.seed = e->cfg.seed; g.episode = episode; g.env_offset = e->cfg.env_offset;
+    g.noise_thr = e->div ? e->cfg.noisy_demand_threshold : 0.0;
     return g;
 }
 
@@ -872,6 +874,38 @@ extern "C" int imx_episode_stats(imx_env* e, const double* step_reward_dev, int 
     return_stats_partial_kernel<<<dim3(STATS_BLOCKS, nstat), STATS_THREADS, 0, s>>>(ret, e->d_stats_partial, e->N, cols);
     IMX_CHECK_LAUNCH("return_stats_partial_kernel");
     return_stats_final_kernel<<<nstat, 32, 0, s>>>(e->d_stats_partial, stats_dev, e->N, nstat, accumulate);
+    IMX_CHECK_LAUNCH("return_stats_final_kernel");
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// evaluation-loop accumulators (MA_inv_management.py:538-600 and its siblings)
+// --------------------------------------------------------------------------------------
+extern "C" int imx_eval_len(const imx_env* e) { return e ? EVAL_FIXED + e->m : -1; }
+
+extern "C" int imx_eval_accumulate(imx_env* e, const void* obs_dev, const double* reward_dev, const double* profit_dev,
+                                   double* acc_dev, int reset, void* stream) {
+    if (!e || !obs_dev || !reward_dev || !acc_dev) return fail(-1, "null argument");
+    IMX_CUDA(cudaSetDevice(e->cfg.device));
+    EvalArgs E;
+    memset(&E, 0, sizeof(E));
+    E.obs = obs_dev; E.reward = reward_dev; E.profit = profit_dev; E.acc = acc_dev; E.nodes = e->d_nodes;
+    E.N = e->N; E.m = e->m; E.O = e->O; E.multi = e->multi ? 1 : 0; E.obs_f32 = e->cfg.obs_f32 ? 1 : 0;
+    E.rescaled = (e->cfg.kind == IMX_KIND_MAIM_DIV || e->cfg.standardise_state) ? 1 : 0;
+    E.reset = reset ? 1 : 0;
+    E.a = e->cfg.a; E.bma = e->cfg.b - e->cfg.a;
+    eval_accumulate_kernel<<<(unsigned)((e->N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(E);
+    IMX_CHECK_LAUNCH("eval_accumulate_kernel");
+    return 0;
+}
+
+extern "C" int imx_eval_stats(imx_env* e, const double* acc_dev, double* stats_dev, int accumulate, void* stream) {
+    if (!e || !acc_dev || !stats_dev) return fail(-1, "null argument");
+    IMX_CUDA(cudaSetDevice(e->cfg.device));
+    const int W = EVAL_FIXED + e->m;
+    column_stats_partial_kernel<<<dim3(STATS_BLOCKS, 2 * W), STATS_THREADS, 0, (cudaStream_t)stream>>>(acc_dev, e->d_stats_partial, e->N, W);
+    IMX_CHECK_LAUNCH("column_stats_partial_kernel");
+    return_stats_final_kernel<<<2 * W, 32, 0, (cudaStream_t)stream>>>(e->d_stats_partial, stats_dev, e->N, 2 * W, accumulate);
     IMX_CHECK_LAUNCH("return_stats_final_kernel");
     return 0;
 }

@@ -211,7 +211,7 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(Philox4 c, uint32_t k0
     return c;
 }
 
-enum : uint32_t { PHILOX_TAG_DEMAND = 0u, PHILOX_TAG_DELAY = 1u };
+enum : uint32_t { PHILOX_TAG_DEMAND = 0u, PHILOX_TAG_DELAY = 1u, PHILOX_TAG_DEMAND_NOISE = 2u };
 
 // counter = (env_lo, env_hi, tag<<28 | idx<<16 | t, episode_lo), key = (seed_lo, seed_hi ^ episode_hi)
 __host__ __device__ __forceinline__ Philox4 philox_draw(uint64_t seed, uint64_t env_global, uint32_t tag,
@@ -240,6 +240,7 @@ struct DemandGen {
     uint64_t seed;
     uint64_t episode;
     int64_t env_offset;
+    double noise_thr;             // noisy demand (MAIM_div_env.py:287-295): 0 = off
 };
 
 // One uniform -> one demand.  Poisson by CDF inversion started from the cutpoint table (the scan
@@ -254,6 +255,15 @@ __device__ __forceinline__ int demand_from_uniform(const DemandGen& g, double u)
     return k;
 }
 
+// Noisy demand, MAIM_div_env.py:287-295 / IM_div_env.py: two uniforms per (retailer, period); "double" is
+// applied before "zero", so a period that draws both ends at 0.  Own Philox tag, counter = the period.
+__device__ __forceinline__ int demand_noise(const DemandGen& g, int64_t n_local, int r, int t, int d) {
+    const Philox4 v = philox_draw(g.seed, (uint64_t)(g.env_offset + n_local), PHILOX_TAG_DEMAND_NOISE, (uint32_t)r, (uint32_t)t, g.episode);
+    if (u53(v.x, v.y) <= g.noise_thr) d = 2 * d;
+    if (u53(v.z, v.w) <= g.noise_thr) d = 0;
+    return d;
+}
+
 // One Philox call serves TWO consecutive periods of one (env, retailer) row: the counter carries
 // t >> 1, words (x, y) make the uniform of the even period and (z, w) of the odd one.
 __device__ __forceinline__ void draw_demand_pair(const DemandGen& g, int64_t n_local, int r, int t_even, int& d0, int& d1) {
@@ -261,6 +271,10 @@ __device__ __forceinline__ void draw_demand_pair(const DemandGen& g, int64_t n_l
                                   (uint32_t)(t_even >> 1), g.episode);
     d0 = demand_from_uniform(g, u53(v.x, v.y));
     d1 = demand_from_uniform(g, u53(v.z, v.w));
+    if (g.noise_thr > 0.0) {
+        d0 = demand_noise(g, n_local, r, t_even, d0);
+        d1 = demand_noise(g, n_local, r, t_even + 1, d1);
+    }
 }
 __device__ __forceinline__ int draw_demand(const DemandGen& g, int64_t n_local, int r, int t) {
     int d0, d1;

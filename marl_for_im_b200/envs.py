@@ -167,6 +167,7 @@ class _ImxEnvBase:
         c.a, c.b = float(self.a), float(self.b)
         c.mu = float(self.config.get("mu", 5))
         c.noisy_delay_threshold = float(self.noisy_delay_threshold)
+        c.noisy_demand_threshold = float(self.noisy_demand_threshold) if (self.DIV and self.noisy_demand) else 0.0
         c.seed = int(self.SEED) & 0xFFFFFFFFFFFFFFFF
         c.num_envs, c.env_offset = self.num_envs, self.env_offset
         inv_init = _int_vec(self.inv_init, m, "init_inv")
@@ -381,6 +382,7 @@ class _ImxEnvBase:
         self._keepalive = (demand_dev, mask_dev)
         if not self.batched:
             self._alloc_histories()
+        self.last_obs, self.last_reward = obs_buf, None       # packed [N, m, O] tensor behind the returned views
         self.state = self._shape_obs(obs_buf)
         return self.state
 
@@ -449,6 +451,7 @@ class _ImxEnvBase:
             self._record_history(t, info_bufs)
             if int(self.error_flags[0]) != 0:
                 raise Exception(f"Infinite Loop {int(self.error_flags[0])}")     # MAIM_div_env.py:503-505 etc.
+        self.last_obs, self.last_reward = obs_buf, rew_buf    # packed [N, m, O] / [N, m] tensors behind the returned views
         self.state = self._shape_obs(obs_buf)
         return self.state, self._shape_reward(rew_buf), self._shape_done(done_flag), self._shape_info(t, info_bufs)
 
@@ -545,6 +548,53 @@ class _ImxEnvBase:
         _lib.check(self._lib.imx_episode_stats(self._handle, C.c_void_p(sr.data_ptr()), int(sr.shape[0]), None,
                                                C.c_void_p(stats.data_ptr()), int(bool(accumulate)), self._stream()))
         return stats
+
+    # ------------------------------------------------------------------ evaluation-loop accumulators
+    EVAL_COLUMNS = ("episode_reward", "total_inventory", "total_backlog", "customer_backlog")
+
+    def eval_accumulate(self, acc, obs, reward, profit=None, reset=False):
+        """One step of the scripts' evaluation loop (MA_inv_management.py:568-581, inv_management.py:585-600,
+        DSHLP_4.py:908-913) for the whole batch, on the device: ``acc [N, 4 + m]`` float64 rows
+        ``{episode_reward, total_inventory, total_backlog, customer_backlog, stage_profit[m]}``.
+        ``obs`` / ``reward`` are what ``step()`` returned (dicts or the packed tensors), ``profit`` is
+        ``info[...]['profit']`` packed ``[N, m]`` or None.  ``acc=None`` allocates; ``reset=True`` starts an episode."""
+        N, m = self.num_envs, self.num_nodes
+        if acc is None:
+            acc = torch.zeros((N, 4 + m), dtype=torch.float64, device=self.device)
+            reset = True
+        pack = lambda d, shape: (torch.stack([d[a] for a in self._agent_names], dim=1) if isinstance(d, dict) else d).reshape(shape).contiguous()   # noqa: E731
+        o = pack(obs, (N, m, self.obs_len))
+        if o.dtype != self.obs_dtype:
+            raise TypeError(f"observations must be {self.obs_dtype} (the dtype this env writes)")
+        r = pack(reward, (N, m) if self.MULTI else (N,)).to(torch.float64)
+        pr = pack(profit, (N, m)).to(torch.float64) if profit is not None else None
+        _lib.check(self._lib.imx_eval_accumulate(self._handle, C.c_void_p(o.data_ptr()), C.c_void_p(r.data_ptr()),
+                                                 C.c_void_p(pr.data_ptr()) if pr is not None else None,
+                                                 C.c_void_p(acc.data_ptr()), int(bool(reset)), self._stream()))
+        self._keepalive_eval = (o, r, pr)
+        return acc
+
+    def eval_stats(self, acc, stats=None, accumulate=False):
+        """``{n, then (Σ, Σ²) per column of acc}`` float64 ``[1 + 2(4 + m)]`` on the device — the inputs of the
+        ``np.mean`` / ``np.std`` lines MA_inv_management.py:589-600; add across GPUs with one all-reduce."""
+        W = 4 + self.num_nodes
+        if stats is None:
+            stats = torch.zeros(1 + 2 * W, dtype=torch.float64, device=self.device)
+        _lib.check(self._lib.imx_eval_stats(self._handle, C.c_void_p(acc.data_ptr()), C.c_void_p(stats.data_ptr()),
+                                            int(bool(accumulate)), self._stream()))
+        return stats
+
+    @staticmethod
+    def eval_summary(stats, num_nodes):
+        """mean / population std (np.std, ddof = 0) per accumulator column from an ``eval_stats`` vector."""
+        st = np.asarray(stats.detach().cpu().numpy() if isinstance(stats, torch.Tensor) else stats, dtype=np.float64)
+        n = st[0]
+        names = list(_ImxEnvBase.EVAL_COLUMNS) + [f"stage_profit_{i}" for i in range(num_nodes)]
+        out = {}
+        for k, name in enumerate(names):
+            mean = st[1 + 2 * k] / n
+            out[name] = (mean, float(np.sqrt(max(st[2 + 2 * k] / n - mean * mean, 0.0))))
+        return out
 
     # ------------------------------------------------------------------ spaces
     def _obs_shape_declared(self):

@@ -557,3 +557,42 @@ def central_critic_flat(agent_obs: np.ndarray, actions=None, clip=(-1.0, 1.0)) -
             out[i, (m - 1) + slot * O:(m - 1) + (slot + 1) * O] = agent_obs[j]
         out[i, (m - 1) * (1 + O):] = agent_obs[i]
     return out
+
+
+def eval_loop_accumulators(env: OracleEnv, customer_demand, actions, rescaled: bool = True, delay_mask=None):
+    """The scripts' evaluation loop for one episode — MA_inv_management.py:538-587 (multi-agent kinds; same in
+    CC_inv_management.py:512-556 and CC_inv_management_div.py:500-544), inv_management.py:570-606 (single-agent
+    kinds) and, with ``rescaled=False``, the LP replay loops (DSHLP_4.py:896-928: ``sum(s[:, 0])`` on raw state).
+    Returns ``[episode_reward, total_inventory, total_backlog, customer_backlog, stage_profit[0..m-1]]``."""
+    m, T = env.m, env.T
+    env.reset(np.array(customer_demand), delay_mask)
+    a, b = float(env.a), float(env.b)
+    episode_reward = 0
+    total_inventory = 0
+    total_backlog = 0
+    customer_backlog = 0
+    stage_rewards = [0.0] * m
+    for t in range(T):
+        obs, reward, done, info = env.step(actions[t])
+        undo = (lambda x, i: rev_scale(float(x), float(env.inv_max[i]), a, b)) if rescaled else (lambda x, i: float(x))
+        if env.multi:                                   # MA_inv_management.py:568-581
+            total_step_inv = 0
+            total_step_bl = 0
+            for i in range(m):
+                episode_reward += reward[i]
+                stage_rewards[i] += info["profit"][i]
+                total_step_inv += undo(obs[i][0], i)
+                total_step_bl += undo(obs[i][1], i)
+            total_inventory += total_step_inv
+            total_backlog += total_step_bl
+            customer_backlog += undo(obs[0][1], 0)
+        else:                                           # inv_management.py:585-598
+            inv = [undo(obs[i][0], i) for i in range(m)]
+            bl = [undo(obs[i][1], i) for i in range(m)]
+            total_inventory += sum(inv)
+            total_backlog += sum(bl)
+            customer_backlog += bl[0]
+            for i in range(m):
+                stage_rewards[i] += info["profit"][i]
+            episode_reward += reward
+    return np.array([episode_reward, total_inventory, total_backlog, customer_backlog] + stage_rewards, dtype=np.float64)

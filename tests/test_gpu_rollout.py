@@ -222,3 +222,52 @@ def test_dfo_func_batch_matches_single_env_objective():
     pol, score = population_search_inventory_policy(InvManagement, cfg, demands, np.ones(4) * 25, sweeps=2, radius=3)
     base = dfo_func_batch(np.ones((1, 4)) * 25, InvManagement(dict(cfg, num_envs=D)), demands).mean().item()
     assert pol.shape == (4,) and score <= base + 1e-12
+
+
+def test_device_noisy_demand_generator():
+    """noisy_demand (MAIM_div_env.py:287-295) on the device: each generated demand is doubled with probability thr and
+    then zeroed with probability thr, from its own Philox tag; replayed traces are never touched; the fused rollout's
+    in-kernel generator draws the same trace."""
+    from marl_for_im_b200.envs import InvManagementDiv, MultiAgentInvManagementDiv
+    thr, N, seed = 0.2, 8192, 99
+    cfg = presets.div2()
+    clean = MultiAgentInvManagementDiv(dict(cfg, num_envs=N, seed=seed))
+    clean.reset()
+    d0 = clean.customer_demand_device().cpu().numpy()                     # [T, R, N]
+    noisy = MultiAgentInvManagementDiv(dict(cfg, num_envs=N, seed=seed, noisy_demand=True, noisy_demand_threshold=thr))
+    noisy.reset()
+    d1 = noisy.customer_demand_device().cpu().numpy()
+    ep = noisy._episode
+    assert ep == clean._episode
+    T, R, _ = d0.shape
+    u = lambda hi, lo: float((((hi >> 5) << 26) | (lo >> 6))) / 9007199254740992.0   # noqa: E731
+    for n in (0, 3, 1000, N - 1):
+        for r in range(R):
+            for t in range(T):
+                w = philox_numpy(seed, n, 2, r, 2 * t, ep)                # tag 2, counter = the period
+                want = int(d0[t, r, n])
+                if u(w[0], w[1]) <= thr:
+                    want *= 2
+                if u(w[2], w[3]) <= thr:
+                    want = 0
+                assert d1[t, r, n] == want
+    zero_rate = (d1 == 0).mean()
+    p0 = np.exp(-5.0)
+    assert abs(zero_rate - (thr + (1 - thr) * p0)) < 0.005
+    doubled = (d1 == 2 * d0) & (d0 > 0)
+    assert abs(doubled.mean() / (1 - p0) - thr * (1 - thr)) < 0.01
+    # replayed demand is left alone
+    trace = np.random.default_rng(1).poisson(5, size=(N, R, T)).astype(np.int32)
+    noisy.reset(customer_demand=trace)
+    np.testing.assert_array_equal(noisy.customer_demand_device().cpu().numpy(), trace.transpose(2, 1, 0))
+    # the fused rollout draws the same noisy trace in-kernel as reset() stored for the step path
+    icfg = presets.div2()
+    env = InvManagementDiv(dict(icfg, num_envs=N, seed=seed, noisy_demand=True, noisy_demand_threshold=thr))
+    env.reset()
+    stored = env.customer_demand_device().permute(2, 1, 0).contiguous()  # [N, R, T]
+    z = np.array([40., 35., 20., 18., 12., 15.])
+    ep = env._episode
+    a = env.rollout_basestock(z, customer_demand=stored)["returns"]
+    env._episode = ep - 1
+    b = env.rollout_basestock(z)["returns"]
+    assert torch.equal(a, b)
