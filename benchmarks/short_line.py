@@ -1,9 +1,11 @@
-"""Prints the headline numbers of one bench.py JSON line read from stdin (helper for sweeps)."""
+"""Prints the headline numbers of bench.py JSON lines read from the files given as arguments, or from stdin."""
 import json
 import os
 import sys
 
-for line in sys.stdin:
+import fileinput
+
+for line in fileinput.input():
     if not line.startswith("{"):
         continue
     d = json.loads(line)

@@ -70,7 +70,6 @@ struct imx_env {
     int64_t N;
     // device memory
     NodeParams* d_nodes = nullptr;
-    int8_t* d_children = nullptr;
     int32_t* d_state = nullptr;          // one block holding every state field
     size_t state_bytes = 0;
     void* field_ptr[IMX_F_COUNT] = {};
@@ -411,7 +410,6 @@ static void fill_args(const imx_env* e, StepArgs& A) {
     A.TL = e->TL;
     A.tab = e->d_tab;
     A.nodes = e->d_nodes;
-    A.children = e->d_children;
     A.inv = (int32_t*)e->field_ptr[IMX_F_INV];
     A.backlog = (int32_t*)e->field_ptr[IMX_F_BACKLOG];
     A.order_u = (int32_t*)e->field_ptr[IMX_F_ORDER_U];
@@ -501,9 +499,7 @@ extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
     const int64_t N = e->N;
     // node table
     NodeParams h_nodes[IMX_MAX_NODES];
-    int8_t h_children[IMX_MAX_NODES * IMX_MAX_CHILDREN];
     memset(h_nodes, 0, sizeof(h_nodes));
-    memset(h_children, -1, sizeof(h_children));
     int pipe_off = 0, bt_off = 0;
     for (int i = 0; i < m; ++i) {
         NodeParams& q = h_nodes[i];
@@ -516,13 +512,15 @@ extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
         if (e->div && cfg->num_children[i] > 1) { q.bt_off = bt_off; bt_off += cfg->num_children[i]; }
         q.retailer_idx = e->retailer_idx[i];
         q.p = e->sell[i]; q.c = e->buy[i]; q.h = cfg->stock_cost[i]; q.bc = cfg->backlog_cost[i]; q.target = cfg->inv_target[i];
+        q.child_lo = q.child_hi = 0xFFFFFFFFu;
         if (e->div)
-            for (int k = 0; k < cfg->num_children[i]; ++k) h_children[i * IMX_MAX_CHILDREN + k] = (int8_t)cfg->children[i][k];
+            for (int k = 0; k < cfg->num_children[i]; ++k) {
+                uint32_t& w = (k < 4) ? q.child_lo : q.child_hi;
+                w = (w & ~(0xFFu << ((k & 3) * 8))) | ((uint32_t)cfg->children[i][k] << ((k & 3) * 8));
+            }
     }
     IMX_CREATE_CUDA(cudaMalloc(&e->d_nodes, sizeof(h_nodes)));
     IMX_CREATE_CUDA(cudaMemcpy(e->d_nodes, h_nodes, sizeof(h_nodes), cudaMemcpyHostToDevice));
-    IMX_CREATE_CUDA(cudaMalloc(&e->d_children, sizeof(h_children)));
-    IMX_CREATE_CUDA(cudaMemcpy(e->d_children, h_children, sizeof(h_children), cudaMemcpyHostToDevice));
 
     // state block: fields back to back, each 256-byte aligned
     const int64_t cnt[IMX_F_COUNT] = {
@@ -595,7 +593,7 @@ extern "C" int imx_destroy(imx_env* e) {
     if (!e) return 0;
     cudaSetDevice(e->cfg.device);
     if (e->hstream) { cudaStreamSynchronize(e->hstream); cudaStreamDestroy(e->hstream); }
-    cudaFree(e->d_nodes); cudaFree(e->d_children); cudaFree(e->d_state); cudaFree(e->d_err);
+    cudaFree(e->d_nodes); cudaFree(e->d_state); cudaFree(e->d_err);
     cudaFree(e->d_demand_T); cudaFree(e->d_mask_T); cudaFree(e->d_cdf); cudaFree(e->d_guide); cudaFree(e->d_tab); cudaFree(e->d_stats_partial); cudaFree(e->d_returns);
     cudaFree(e->d_act_h); cudaFree(e->d_obs_h); cudaFree(e->d_rew_h); cudaFree(e->d_dem_h); cudaFree(e->d_mask_h);
     delete e;

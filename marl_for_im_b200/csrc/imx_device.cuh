@@ -61,7 +61,7 @@ struct __align__(16) NodeParams {
     double h;              // stock holding cost
     double bc;             // backlog cost
     double target;         // inventory target
-    double pad1;
+    uint32_t child_lo, child_hi;   // divergent: lanes of up to 8 children, one byte each (0xFF = none), child k in byte k
 };
 static_assert(sizeof(NodeParams) == 96, "NodeParams must stay 96 bytes");
 
@@ -75,8 +75,15 @@ __device__ __forceinline__ NodeParams load_node(const NodeParams* p) {
     n.nchild = q2.x; n.bt_off = q2.y; n.retailer_idx = q2.z; n.pad0 = 0;
     n.p = __hiloint2double(q3.y, q3.x); n.c = __hiloint2double(q3.w, q3.z);
     n.h = __hiloint2double(q4.y, q4.x); n.bc = __hiloint2double(q4.w, q4.z);
-    n.target = __hiloint2double(q5.y, q5.x); n.pad1 = 0.0;
+    n.target = __hiloint2double(q5.y, q5.x); n.child_lo = (uint32_t)q5.z; n.child_hi = (uint32_t)q5.w;
     return n;
+}
+
+// Lane (inside the env's tile) of child k of this node, -1 if it has fewer children.
+__device__ __forceinline__ int child_lane_of(const NodeParams& n, int k) {
+    const uint32_t w = (k < 4) ? n.child_lo : n.child_hi;
+    const int v = (int)((w >> ((k & 3) * 8)) & 0xFFu);
+    return (k < n.nchild) ? v : -1;
 }
 
 // Batch-uniform arguments (kernel parameter space → constant bank, broadcast reads).
@@ -107,7 +114,6 @@ struct StepArgs {
     int32_t pad_tl;
     const double* __restrict__ tab;         // [m][4][TL] exact rescale results, see build_tables() in imx_api.cu
     const NodeParams* __restrict__ nodes;   // [m]
-    const int8_t* __restrict__ children;    // [m][IMX_MAX_CHILDREN] lanes of the children (-1 = none)
     // state (SoA, int32)
     int32_t* __restrict__ inv;
     int32_t* __restrict__ backlog;

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
     if constexpr (DIV) {
 #pragma unroll
         for (int k = 0; k < MAXC; ++k)
-            child_lane[k] = (stage_ok && k < np.nchild) ? (int)A.children[i * IMX_MAX_CHILDREN + k] : -1;
+            child_lane[k] = stage_ok ? child_lane_of(np, k) : -1;
     }
     const bool is_last = (i == m - 1);
     const int delay_m1 = np.delay - 1;

@@ -87,7 +87,21 @@ __device__ __forceinline__ double tile_seq_sum(double v, int m, int tb) {
 // nchild + 1 batches instead of up to demand_max passes, with identical results.  The watchdog
 // counters count passes, exactly like the reference's while_counter.
 // Returns the watchdog code (0 ok; 1..4 = the reference's "Infinite Loop k").
-__device__ __forceinline__ int ceil_div_pos(int a, int b) { return (a + b - 1) / b; }
+// ceil(a / b) for a >= 0 and b = a count of children in [1, MAXC], without an integer division (20+ instructions each,
+// two per batch — a fifth of the divergent kernel's issue slots): b <= 2 is a shift; otherwise multiply-high with
+// ceil(2^32 / b), exact while (a + b - 1) * b < 2^32 (checked: larger amounts take the division).
+template <int MAXC>
+__device__ __forceinline__ int ceil_div_pos(int a, int b) {
+    const uint32_t x = (uint32_t)(a + b - 1);
+    if constexpr (MAXC <= 2) {
+        return (int)(b == 2 ? x >> 1 : x);
+    } else {
+        if (x >> 28) return (int)(x / (uint32_t)b);
+        const uint32_t magic = b == 2 ? 0x80000000u : b == 3 ? 0x55555556u : b == 4 ? 0x40000000u : b == 5 ? 0x33333334u
+                             : b == 6 ? 0x2AAAAAABu : b == 7 ? 0x24924925u : 0x20000000u;
+        return (int)(b == 1 ? x : __umulhi(x, magic));
+    }
+}
 
 // while sum(cnt_k) > 0 and amt > 0: for k: if cnt_k > 0: st_k++, cnt_k--, amt--       (LOOP1 / LOOP2)
 template <int MAXC>
@@ -104,7 +118,7 @@ __device__ __forceinline__ int drain_round_robin(int nchild, int (&cnt)[MAXC], i
         }
         if (!(sum > 0 && amt > 0)) break;
         // sum > 0 implies active >= 1; identical passes until a counter empties, the goods run out or the total does
-        const int p = min(lo, min(ceil_div_pos(amt, active), ceil_div_pos(sum, active)));
+        const int p = min(lo, min(ceil_div_pos<MAXC>(amt, active), ceil_div_pos<MAXC>(sum, active)));
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
             if (k < nchild && cnt[k] > 0) { st[k] += p; cnt[k] -= p; }
@@ -152,7 +166,7 @@ __device__ __forceinline__ int split_ship(int nchild, int ship, int demand, int 
                     if (k < nchild && st[k] < od[k] + bt[k]) { active += 1; lo = min(lo, od[k] + bt[k] - st[k]); }
                 }
                 if (active == 0) return 4;                  // nobody can take a unit: the reference spins into its watchdog
-                const int p = min(lo, ceil_div_pos(amt, active));
+                const int p = min(lo, ceil_div_pos<MAXC>(amt, active));
 #pragma unroll
                 for (int k = 0; k < MAXC; ++k) {
                     if (k < nchild && st[k] < od[k] + bt[k]) st[k] += p;
@@ -260,7 +274,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const __grid_constan
     if constexpr (DIV) {
 #pragma unroll
         for (int k = 0; k < MAXC; ++k)
-            child_lane[k] = (stage_ok && k < np.nchild) ? (int)A.children[i * IMX_MAX_CHILDREN + k] : -1;
+            child_lane[k] = stage_ok ? child_lane_of(np, k) : -1;
     }
     const bool is_last = (i == m - 1);
     const int delay_m1 = np.delay - 1;

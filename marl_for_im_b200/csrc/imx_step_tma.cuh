@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
     if constexpr (DIV) {
 #pragma unroll
         for (int k = 0; k < MAXC; ++k)
-            child_lane[k] = (ok && k < np.nchild) ? (int)A.children[i * IMX_MAX_CHILDREN + k] : -1;
+            child_lane[k] = ok ? child_lane_of(np, k) : -1;
     }
     const bool is_last = (i == m - 1);
     const int delay_m1 = np.delay - 1;
