@@ -165,6 +165,15 @@ int imx_reset(imx_env* env, const int32_t* demand_dev, const uint8_t* delay_mask
 int imx_step(imx_env* env, const double* actions_dev, double* obs_dev, double* reward_dev,
              const imx_info_out* info, void* stream);
 
+/* K consecutive step() calls on pre-computed actions  —  the replay loops that drive an env with a stored plan
+ * (the LP scripts: "lp_action = np.round(LP_actions[t, :], 0); s, r, done, info = LP_env.step(lp_action)",
+ * DSHLP_4.py:905-908; evaluation of open-loop action traces).  Same results as K imx_step calls, bit for bit.
+ * Where the whole batch goes through the TMA-staged kernel this is ONE launch: every tile's state stays in shared
+ * memory for the K periods, actions / demand are prefetched two periods ahead and observations / rewards stream out
+ * behind the compute, so state moves once per launch instead of once per period; otherwise K plain launches.
+ *   actions_dev [K][N][m], obs_dev [K][N][m][O] or NULL, reward_dev [K][N][m] (MAIM kinds) / [K][N]. */
+int imx_step_many(imx_env* env, const double* actions_dev, int K, void* obs_dev, double* reward_dev, void* stream);
+
 /* dfo_func's loop  —  base_restock_policy.py:24-45 with base_stock_policy :4-21 fused in: a whole
  * K = T period episode per env in ONE kernel, state on chip.
  *   z_dev          base-stock levels, [m] (z_stride = 0) or [N][m] (z_stride = m)

@@ -96,6 +96,7 @@ struct imx_env {
     // kernels
     step_fn_t step_fn = nullptr;
     tma_fn_t tma_fn = nullptr;
+    tma_fn_t tma_many_fn = nullptr;      // the same kernel instantiated with the multi-period loop (imx_step_many)
     TileLayout tile = {};                // ahead-of-time kernels: tile width = m rounded up to a power of two
     TileLayout tile_jit = {};            // runtime-specialised kernels: tile width = m (dense lane packing)
     int step_path = 0;                   // 0 auto, 1 direct only, 2 TMA wherever legal (IMX_STEP_PATH)
@@ -103,6 +104,7 @@ struct imx_env {
     int step_dense = 0;                  // experimental: m-wide tiles in the specialised step kernel (IMX_STEP_DENSE=1)
     int tma_threads = 256;               // CTA size of the TMA kernel (IMX_TMA_THREADS: 64, 128 or 256)
     int use_pdl = 1;                     // chain step launches with programmatic dependent launch (IMX_PDL=0 disables)
+    int fuse_periods = 1;                // imx_step_many advances all its periods in one launch (IMX_FUSE_PERIODS=0: K plain launches)
     int jit_policy = 0;                  // 0 auto (large batches), 1 always, -1 never (IMX_JIT)
     int jit_state = 0;                   // 0 not tried, 1 specialised kernels loaded, -1 unavailable
     const imxjit::Kernels* jit = nullptr;
@@ -122,16 +124,17 @@ static void pick_kernels(imx_env* e) {
     const bool small = (e->D <= 4 && e->P <= 1);
     if constexpr (DIV) {
         const bool few = e->maxc <= 2;
-        if (small && few) e->tma_fn = step_kernel_tma<M_PAD, 4, 1, 2, true>;
-        else if (small) e->tma_fn = step_kernel_tma<M_PAD, 4, 1, 8, true>;
-        else if (few) e->tma_fn = step_kernel_tma<M_PAD, 8, 8, 2, true>;
-        else e->tma_fn = step_kernel_tma<M_PAD, 8, 8, 8, true>;
+        if (small && few) { e->tma_fn = step_kernel_tma<M_PAD, 4, 1, 2, true>; e->tma_many_fn = step_kernel_tma<M_PAD, 4, 1, 2, true, true>; }
+        else if (small)   { e->tma_fn = step_kernel_tma<M_PAD, 4, 1, 8, true>; e->tma_many_fn = step_kernel_tma<M_PAD, 4, 1, 8, true, true>; }
+        else if (few)     { e->tma_fn = step_kernel_tma<M_PAD, 8, 8, 2, true>; e->tma_many_fn = step_kernel_tma<M_PAD, 8, 8, 2, true, true>; }
+        else              { e->tma_fn = step_kernel_tma<M_PAD, 8, 8, 8, true>; e->tma_many_fn = step_kernel_tma<M_PAD, 8, 8, 8, true, true>; }
         if (small && few) { e->step_fn = step_kernel<M_PAD, 4, 1, 2, true>; e->rollout_fn = rollout_kernel<M_PAD, 4, 2, true>; }
         else if (small)   { e->step_fn = step_kernel<M_PAD, 4, 1, 8, true>; e->rollout_fn = rollout_kernel<M_PAD, 4, 8, true>; }
         else if (few)     { e->step_fn = step_kernel<M_PAD, 8, 8, 2, true>; e->rollout_fn = rollout_kernel<M_PAD, 8, 2, true>; }
         else              { e->step_fn = step_kernel<M_PAD, 8, 8, 8, true>; e->rollout_fn = rollout_kernel<M_PAD, 8, 8, true>; }
     } else {
         e->tma_fn = small ? step_kernel_tma<M_PAD, 4, 1, 1, false> : step_kernel_tma<M_PAD, 8, 8, 1, false>;
+        e->tma_many_fn = small ? step_kernel_tma<M_PAD, 4, 1, 1, false, true> : step_kernel_tma<M_PAD, 8, 8, 1, false, true>;
         if (small) { e->step_fn = step_kernel<M_PAD, 4, 1, 1, false>; e->rollout_fn = rollout_kernel<M_PAD, 4, 1, false>; }
         else       { e->step_fn = step_kernel<M_PAD, 8, 8, 1, false>; e->rollout_fn = rollout_kernel<M_PAD, 8, 1, false>; }
     }
@@ -165,10 +168,18 @@ static void compute_tile(const imx_env* e, TileLayout& L, int tile_width) {
     L.off_obs = take(E * m * e->O * (e->cfg.obs_f32 ? 4 : 8));
     L.off_rew = take(E * m * 8);
     L.total = off;
+    // multi-period launches double-buffer the per-period inputs and outputs; the extra regions sit behind the
+    // single-period layout so that a plain step launches the same kernel with `total` bytes only
+    L.off_act2 = take(E * m * 8);
+    L.off_dem2 = take(e->R * E * 4);
+    L.off_obs2 = take(E * m * e->O * (e->cfg.obs_f32 ? 4 : 8));
+    L.off_rew2 = take(E * m * 8);
+    L.total2 = off;
 }
 
 // -D options and template instantiations of the runtime-specialised build (imx_jit.cuh)
-static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, std::string& step_name, std::string& rollout_name) {
+static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, std::string& step_name, std::string& many_name,
+                     std::string& rollout_name) {
     const imx_config& c = e->cfg;
     const bool always_std = (c.kind == IMX_KIND_MAIM_DIV);
     const int std_state = always_std ? 1 : (c.standardise_state != 0);
@@ -190,6 +201,7 @@ static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, s
     addt("E", L.E); addt("off_act", L.off_act); addt("off_inv", L.off_inv); addt("off_bl", L.off_bl); addt("off_ou", L.off_ou);
     addt("off_pipe", L.off_pipe); addt("off_hd", L.off_hd); addt("off_ho", L.off_ho); addt("off_carry", L.off_carry);
     addt("off_bt", L.off_bt); addt("off_dem", L.off_dem); addt("off_obs", L.off_obs); addt("off_rew", L.off_rew); addt("total", L.total);
+    addt("off_act2", L.off_act2); addt("off_dem2", L.off_dem2); addt("off_obs2", L.off_obs2); addt("off_rew2", L.off_rew2); addt("total2", L.total2);
     defs.push_back("IMX_TMA_THREADS=" + std::to_string(e->tma_threads));
     const int mp = e->step_dense ? e->m : m_pad_of(e);     // step kernel: power-of-two tile width (see select_kernels)
     const int pmax = (e->need_hd || e->need_ho) ? e->P : 1;
@@ -197,6 +209,7 @@ static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, s
     const std::string dv = e->div ? "true" : "false";
     step_name = "imx::step_kernel_tma<" + std::to_string(mp) + ", " + std::to_string(e->D) + ", " + std::to_string(pmax) + ", " +
                 std::to_string(e->div ? maxc : 1) + ", " + dv + ">";
+    many_name = step_name.substr(0, step_name.size() - 1) + ", true>";
     rollout_name = "imx::rollout_kernel<" + std::to_string(e->m) + ", " + std::to_string(e->D) + ", " + std::to_string(e->div ? maxc : 1) +
                    ", " + dv + ">";
 }
@@ -209,9 +222,11 @@ static void ensure_jit(imx_env* e) {
     if (e->jit_policy == 0 && e->N < 4096) return;
     std::vector<std::string> defs;
     std::string sn, rn;
-    jit_spec(e, e->TL, defs, sn, rn);
+    std::string mn;
+    jit_spec(e, e->TL, defs, sn, mn, rn);
     if (e->tile_jit.total > 200 * 1024) return;
-    e->jit = imxjit::get(defs, sn, rn, e->tile_jit.total, e->cfg.device);
+    e->jit = imxjit::get(defs, sn, mn, rn, e->tile_jit.total, e->tile_jit.total2 <= 200 * 1024 ? e->tile_jit.total2 : e->tile_jit.total,
+                         e->cfg.device);
     if (e->jit) e->jit_state = 1;
 }
 
@@ -254,8 +269,11 @@ static int select_kernels(imx_env* e) {
     // ranges (e.g. 40 envs x 6 nodes x 4 B = 960 B) straddle 128-byte lines, measured slower at 262144 envs;
     // the issue-bound ROLLOUT kernel is specialised with tile width = m (dense lane packing, +21% on div2)
     compute_tile(e, e->tile_jit, e->step_dense ? e->m : m_pad_of(e));
-    if (e->tile.total <= 200 * 1024)
+    if (e->tile.total <= 200 * 1024) {
         IMX_CUDA(cudaFuncSetAttribute((const void*)e->tma_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->tile.total));
+        if (e->tile.total2 <= 200 * 1024)
+            IMX_CUDA(cudaFuncSetAttribute((const void*)e->tma_many_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->tile.total2));
+    }
     else
         e->tma_fn = nullptr;
     {
@@ -265,6 +283,8 @@ static int select_kernels(imx_env* e) {
         e->host_zero_copy = (zc && !strcmp(zc, "0")) ? 0 : 1;
         const char* pd = getenv("IMX_PDL");
         e->use_pdl = (pd && !strcmp(pd, "0")) ? 0 : 1;
+        const char* fu = getenv("IMX_FUSE_PERIODS");
+        e->fuse_periods = (fu && !strcmp(fu, "0")) ? 0 : 1;
         const char* jp = getenv("IMX_JIT");
         e->jit_policy = (jp && !strcmp(jp, "1")) ? 1 : (jp && !strcmp(jp, "0")) ? -1 : 0;
     }
@@ -705,11 +725,19 @@ extern "C" int imx_reset(imx_env* e, const int32_t* demand_dev, const uint8_t* d
     return 0;
 }
 
+// periods > 1 (imx_step_many): the TMA kernel advances that many periods in one launch with the tiles' state resident
+// in shared memory; *done receives how many periods the call really advanced (1 when the fused form is not applicable:
+// tail tiles, diagnostics, the direct path, a layout that does not fit).
 static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, double* reward_dev,
-                       const imx_info_out* info, cudaStream_t s) {
+                       const imx_info_out* info, cudaStream_t s, int periods = 1, int* done = nullptr) {
     if (e->t >= e->T) return fail(-6, "step() past the end of the episode (period %d of %d)", e->t, e->T);
     StepArgs A;
     fill_args(e, A);
+    const size_t cells_all = (size_t)e->N * e->m;
+    A.periods = 1;
+    A.act_stride = (int64_t)cells_all;
+    A.obs_stride_bytes = (int64_t)(cells_all * e->O * (e->cfg.obs_f32 ? 4 : 8));
+    A.rew_stride = (int64_t)(e->multi ? cells_all : (size_t)e->N);
     A.actions = actions_dev;
     A.obs = obs_dev;
     A.reward = reward_dev;
@@ -735,6 +763,10 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
         while (n_tma > 0 && (n_tma % epw_direct) != 0) n_tma -= TL_use.E;      // the tail kernel starts on a warp-tile boundary
     }
     e->last_variant = 0;
+    const bool fused = periods > 1 && n_tma == e->N && !A.has_info && TL_use.total2 <= 200 * 1024 && e->fuse_periods;
+    if (fused) A.periods = periods;
+    if (done) *done = A.periods;
+    const unsigned tma_smem = (unsigned)(fused ? TL_use.total2 : TL_use.total);
     if (n_tma > 0) {
         if (use_jit) {
             void* params[] = {(void*)&A, (void*)&e->tile_jit};
@@ -742,14 +774,14 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
             memset(&lc, 0, sizeof(lc));
             lc.gridDimX = (unsigned)(n_tma / TL_use.E); lc.gridDimY = 1; lc.gridDimZ = 1;
             lc.blockDimX = (unsigned)e->tma_threads; lc.blockDimY = 1; lc.blockDimZ = 1;
-            lc.sharedMemBytes = (unsigned)TL_use.total;
+            lc.sharedMemBytes = tma_smem;
             lc.hStream = (CUstream)s;
             CUlaunchAttribute at[1];
             at[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
             at[0].value.programmaticStreamSerializationAllowed = 1;
             lc.attrs = at;
             lc.numAttrs = e->use_pdl ? 1 : 0;
-            const CUresult cr = imxjit::g_api.LaunchKernelEx(&lc, e->jit->step, params, nullptr);
+            const CUresult cr = imxjit::g_api.LaunchKernelEx(&lc, fused ? e->jit->step_many : e->jit->step, params, nullptr);
             if (cr != CUDA_SUCCESS) return fail(-3, "launch of the specialised step kernel failed (CUresult %d)", (int)cr);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             e->last_variant = 2;
@@ -758,14 +790,14 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
             memset(&lc, 0, sizeof(lc));
             lc.gridDim = dim3((unsigned)(n_tma / TL_use.E));
             lc.blockDim = dim3((unsigned)e->tma_threads);
-            lc.dynamicSmemBytes = (size_t)TL_use.total;
+            lc.dynamicSmemBytes = (size_t)tma_smem;
             lc.stream = s;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[0].val.programmaticStreamSerializationAllowed = 1;
             lc.attrs = at;
             lc.numAttrs = e->use_pdl ? 1 : 0;
-            IMX_CUDA(cudaLaunchKernelEx(&lc, e->tma_fn, A, e->tile));
+            IMX_CUDA(cudaLaunchKernelEx(&lc, fused ? e->tma_many_fn : e->tma_fn, A, e->tile));
             IMX_CHECK_LAUNCH("step_kernel_tma");
             e->last_variant = 1;
         }
@@ -779,7 +811,7 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
         e->step_fn<<<grid, STEP_THREADS, e->step_smem, s>>>(A);
         IMX_CHECK_LAUNCH("step_kernel");
     }
-    e->t += 1;
+    e->t += A.periods;
     return 0;
 }
 
@@ -788,6 +820,29 @@ extern "C" int imx_step(imx_env* e, const double* actions_dev, double* obs_dev, 
     if (!e || !actions_dev || !reward_dev) return fail(-1, "null argument");
     IMX_CUDA(cudaSetDevice(e->cfg.device));
     return launch_step(e, actions_dev, obs_dev, reward_dev, info, (cudaStream_t)stream);
+}
+
+// K consecutive periods on pre-computed actions: one launch that keeps every tile's state in shared memory for all K
+// periods (actions / demand prefetched two periods ahead, observations / rewards streamed out behind the compute)
+// wherever the whole batch goes through the TMA kernel; otherwise K plain launches.  Same results either way.
+extern "C" int imx_step_many(imx_env* e, const double* actions_dev, int K, void* obs_dev, double* reward_dev, void* stream) {
+    if (!e || !actions_dev || !reward_dev) return fail(-1, "null argument");
+    if (K < 1) return fail(-1, "K must be >= 1");
+    if (e->t + K > e->T) return fail(-6, "imx_step_many: %d periods from period %d run past the end of the episode (%d)", K, e->t, e->T);
+    IMX_CUDA(cudaSetDevice(e->cfg.device));
+    const size_t cells = (size_t)e->N * e->m;
+    const size_t obs_stride = cells * e->O * (e->cfg.obs_f32 ? 4 : 8);
+    const size_t rew_stride = e->multi ? cells : (size_t)e->N;
+    int j = 0;
+    while (j < K) {
+        int adv = 1;
+        const int rc = launch_step(e, actions_dev + (size_t)j * cells,
+                                   obs_dev ? (double*)((unsigned char*)obs_dev + (size_t)j * obs_stride) : nullptr,
+                                   reward_dev + (size_t)j * rew_stride, nullptr, (cudaStream_t)stream, K - j, &adv);
+        if (rc) return rc;
+        j += adv;
+    }
+    return 0;
 }
 
 // --------------------------------------------------------------------------------------
@@ -1010,9 +1065,10 @@ extern "C" int imx_jit_compile_check(const imx_config* cfg, char* log, int cap) 
     build_tables(&tmp, &TL);
     std::vector<std::string> defs;
     std::string sn, rn, lg;
-    jit_spec(&tmp, TL, defs, sn, rn);
+    std::string mn;
+    jit_spec(&tmp, TL, defs, sn, mn, rn);
     std::vector<char> cubin;
-    const size_t n = imxjit::compile_only(defs, sn, rn, lg, &cubin);
+    const size_t n = imxjit::compile_only(defs, sn, mn, rn, lg, &cubin);
     if (n > 0 && getenv("IMX_JIT_DUMP")) {              // for cuobjdump -sass inspection
         FILE* f = fopen(getenv("IMX_JIT_DUMP"), "wb");
         if (f) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }

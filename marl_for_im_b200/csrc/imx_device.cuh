@@ -131,6 +131,13 @@ struct StepArgs {
     double* __restrict__ obs;               // [N][m][O]
     double* __restrict__ reward;            // [N][m] or [N]
     imx_info_out info;
+    // multi-period replay (imx_step_many): the TMA kernel advances `periods` periods per launch with the tile's state
+    // resident in shared memory; period j reads actions + j * act_stride and writes obs / reward slices j
+    int32_t periods;                        // >= 1 (1 = plain step)
+    int32_t pad_periods;
+    int64_t act_stride;                     // doubles between consecutive periods' action blocks
+    int64_t obs_stride_bytes;               // bytes between consecutive periods' observation blocks
+    int64_t rew_stride;                     // doubles between consecutive periods' reward blocks
 };
 
 // ------------------------------------------------------------------------------------

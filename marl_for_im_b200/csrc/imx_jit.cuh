@@ -42,7 +42,7 @@ struct Api {
 
 struct Kernels {
     CUmodule mod = nullptr;
-    CUfunction step = nullptr, rollout = nullptr;
+    CUfunction step = nullptr, rollout = nullptr, step_many = nullptr;
     int step_regs = 0, rollout_regs = 0;
     std::string log;
 };
@@ -100,8 +100,8 @@ static bool read_file(const std::string& path, std::string& out) {
 
 // Compiles (or fetches from the in-process cache) the kernels specialised by `defines`.
 // step_name / rollout_name are C++ name expressions of the template instantiations.
-static const Kernels* get(const std::vector<std::string>& defines, const std::string& step_name,
-                          const std::string& rollout_name, int step_smem_bytes, int device) {
+static const Kernels* get(const std::vector<std::string>& defines, const std::string& step_name, const std::string& many_name,
+                          const std::string& rollout_name, int step_smem_bytes, int many_smem_bytes, int device) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (!load_api()) return nullptr;
     // a CUmodule belongs to the context it was loaded in: one cache entry per (device, specialisation)
@@ -125,6 +125,7 @@ static const Kernels* get(const std::vector<std::string>& defines, const std::st
     nvrtcProgram prog;
     if (g_api.CreateProgram(&prog, tu, "imx_jit.cu", 5, inc_ptr, inc_names) != NVRTC_SUCCESS) { g_last_log = "nvrtcCreateProgram failed"; return nullptr; }
     g_api.AddNameExpression(prog, step_name.c_str());
+    g_api.AddNameExpression(prog, many_name.c_str());
     g_api.AddNameExpression(prog, rollout_name.c_str());
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DIMX_JIT=1"};
     for (const auto& d : defines) opts.push_back("-D" + d);
@@ -135,7 +136,8 @@ static const Kernels* get(const std::vector<std::string>& defines, const std::st
     g_api.GetProgramLogSize(prog, &logn);
     if (logn > 1) { K.log.resize(logn); g_api.GetProgramLog(prog, &K.log[0]); }
     if (rc != NVRTC_SUCCESS) { g_last_log = "NVRTC compile failed: " + K.log.substr(0, 1500); g_api.DestroyProgram(&prog); return nullptr; }
-    const char *low_step = nullptr, *low_roll = nullptr;
+    const char *low_step = nullptr, *low_roll = nullptr, *low_many = nullptr;
+    g_api.GetLoweredName(prog, many_name.c_str(), &low_many);
     g_api.GetLoweredName(prog, step_name.c_str(), &low_step);
     g_api.GetLoweredName(prog, rollout_name.c_str(), &low_roll);
     size_t n = 0;
@@ -144,24 +146,27 @@ static const Kernels* get(const std::vector<std::string>& defines, const std::st
     g_api.GetCUBIN(prog, cubin.data());
     CUmodule mod = nullptr;
     CUresult cr = g_api.ModuleLoadData(&mod, cubin.data());
-    if (cr != CUDA_SUCCESS || !low_step || !low_roll) { g_last_log = "cuModuleLoadData failed for the specialised cubin"; g_api.DestroyProgram(&prog); return nullptr; }
-    CUfunction fs = nullptr, fr = nullptr;
-    if (g_api.ModuleGetFunction(&fs, mod, low_step) != CUDA_SUCCESS || g_api.ModuleGetFunction(&fr, mod, low_roll) != CUDA_SUCCESS) {
+    if (cr != CUDA_SUCCESS || !low_step || !low_roll || !low_many) { g_last_log = "cuModuleLoadData failed for the specialised cubin"; g_api.DestroyProgram(&prog); return nullptr; }
+    CUfunction fs = nullptr, fr = nullptr, fm = nullptr;
+    if (g_api.ModuleGetFunction(&fs, mod, low_step) != CUDA_SUCCESS || g_api.ModuleGetFunction(&fr, mod, low_roll) != CUDA_SUCCESS ||
+        g_api.ModuleGetFunction(&fm, mod, low_many) != CUDA_SUCCESS) {
         g_last_log = "specialised kernel symbol not found";
         g_api.DestroyProgram(&prog);
         return nullptr;
     }
     g_api.DestroyProgram(&prog);
     g_api.FuncSetAttribute(fs, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, step_smem_bytes);
+    g_api.FuncSetAttribute(fm, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, many_smem_bytes);
     g_api.FuncGetAttribute(&K.step_regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fs);
     g_api.FuncGetAttribute(&K.rollout_regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fr);
-    K.mod = mod; K.step = fs; K.rollout = fr;
+    K.mod = mod; K.step = fs; K.rollout = fr; K.step_many = fm;
     return &K;
 }
 
 // Compile only (no driver needed): used by the CPU-side build check to prove that the specialised
 // translation unit compiles for sm_100a.  Returns cubin size or 0.
-static size_t compile_only(const std::vector<std::string>& defines, const std::string& step_name, const std::string& rollout_name,
+static size_t compile_only(const std::vector<std::string>& defines, const std::string& step_name, const std::string& many_name,
+                           const std::string& rollout_name,
                            std::string& log, std::vector<char>* cubin_out) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (!g_api.h_nvrtc) {
@@ -189,6 +194,7 @@ static size_t compile_only(const std::vector<std::string>& defines, const std::s
     nvrtcProgram prog;
     if (a.CreateProgram(&prog, tu, "imx_jit.cu", 5, inc_ptr, inc_names) != NVRTC_SUCCESS) { log = "nvrtcCreateProgram failed"; return 0; }
     a.AddNameExpression(prog, step_name.c_str());
+    a.AddNameExpression(prog, many_name.c_str());
     a.AddNameExpression(prog, rollout_name.c_str());
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DIMX_JIT=1"};
     for (const auto& d : defines) opts.push_back("-D" + d);

@@ -33,6 +33,9 @@ struct TileLayout {
     int32_t E;                 // envs per tile
     int32_t off_act, off_inv, off_bl, off_ou, off_pipe, off_hd, off_ho, off_carry, off_bt, off_dem, off_obs, off_rew;
     int32_t total;             // dynamic shared memory bytes
+    // second buffers of the per-period inputs (actions, demand) and outputs (obs, reward), used by multi-period launches
+    int32_t off_act2, off_dem2, off_obs2, off_rew2;
+    int32_t total2;            // dynamic shared memory bytes of a multi-period launch (second buffers sit behind `total`)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -64,6 +67,8 @@ __device__ __forceinline__ void bulk_store_only(void* gdst, const void* ssrc, ui
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the most recent bulk group have finished reading shared memory
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // Programmatic dependent launch (sm_90+): back-to-back step() launches are chained with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so the next grid may start its prologue
@@ -72,11 +77,13 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV>
+// MANY = false: one period per launch (the loop below folds away); MANY = true: A.periods periods per launch with the
+// tile's state resident in shared memory (imx_step_many) — a separate instantiation because the loop costs registers.
+template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV, bool MANY = false>
 __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_constant__ StepArgs A,
                                                                 const __grid_constant__ TileLayout TLY) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar[2];         // bar[b]: inputs of the periods with parity b (bar[0] also the state)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -91,8 +98,8 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
     const bool ok = i < m && sub < EPW;               // full tiles only: every env slot is live
     const int cell = e_loc * m + i;                  // index inside a [E][m] tile
     const int64_t n0 = (int64_t)blockIdx.x * E;      // first env of the tile
+    const int K = MANY ? A.periods : 1;              // periods this launch advances
 
-    double* s_act = reinterpret_cast<double*>(smem + KT(off_act));
     int32_t* s_inv = reinterpret_cast<int32_t*>(smem + KT(off_inv));
     int32_t* s_bl = reinterpret_cast<int32_t*>(smem + KT(off_bl));
     int32_t* s_ou = reinterpret_cast<int32_t*>(smem + KT(off_ou));
@@ -101,37 +108,46 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
     int32_t* s_ho = reinterpret_cast<int32_t*>(smem + KT(off_ho));
     int32_t* s_carry = reinterpret_cast<int32_t*>(smem + KT(off_carry));
     int32_t* s_bt = reinterpret_cast<int32_t*>(smem + KT(off_bt));
-    int32_t* s_dem = reinterpret_cast<int32_t*>(smem + KT(off_dem));
-    unsigned char* s_obs = smem + KT(off_obs);
     const int es = KF(obs_f32) ? 4 : 8;              // observation element size
-    double* s_rew = reinterpret_cast<double*>(smem + KT(off_rew));
 
     const uint32_t b_cell4 = (uint32_t)E * m * 4u, b_cell8 = (uint32_t)E * m * 8u;
     const uint32_t b_pipe = (uint32_t)E * KF(L) * 4u, b_hist = b_cell4 * (uint32_t)KF(P);
     const uint32_t b_bt = (uint32_t)E * KF(NB) * 4u, b_dem = (uint32_t)E * 4u;
+    const uint32_t b_in = b_cell8 + (uint32_t)KF(R) * b_dem;       // per-period inputs: actions + demand rows
+
+    // per-period inputs of period j (actions block j, demand rows of period t0 + j) into input buffer j & 1
+    auto load_inputs = [&](int j) {
+        double* sa = reinterpret_cast<double*>(smem + ((j & 1) ? KT(off_act2) : KT(off_act)));
+        int32_t* sd = reinterpret_cast<int32_t*>(smem + ((j & 1) ? KT(off_dem2) : KT(off_dem)));
+        bulk_load_g2s(sa, A.actions + (int64_t)j * A.act_stride + n0 * m, b_cell8, &bar[j & 1]);
+        for (int r = 0; r < KF(R); ++r)
+            bulk_load_g2s(sd + r * E, A.demand_T + ((int64_t)(A.t + j) * KF(R) + r) * A.N + n0, b_dem, &bar[j & 1]);
+    };
 
     pdl_launch_dependents();
-    if (tid == 0) mbar_init(&bar, 1);
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
     __syncthreads();
     if (tid == 0) {
         pdl_wait();                                  // state written by the previous step must be complete and visible
-        uint32_t bytes = b_cell8 + 3u * b_cell4 + b_pipe + (uint32_t)KF(R) * b_dem;
+        uint32_t bytes = b_in + 3u * b_cell4 + b_pipe;
         if (KF(need_hd)) bytes += b_hist;
         if (KF(need_ho)) bytes += b_hist;
         if (KF(has_carry)) bytes += b_cell4;
         if (DIV && KF(NB) > 0) bytes += b_bt;
-        mbar_expect_tx(&bar, bytes);
-        bulk_load_g2s(s_act, A.actions + n0 * m, b_cell8, &bar);
-        bulk_load_g2s(s_inv, A.inv + n0 * m, b_cell4, &bar);
-        bulk_load_g2s(s_bl, A.backlog + n0 * m, b_cell4, &bar);
-        bulk_load_g2s(s_ou, A.order_u + n0 * m, b_cell4, &bar);
-        bulk_load_g2s(s_pipe, A.pipe + n0 * KF(L), b_pipe, &bar);
-        if (KF(need_hd)) bulk_load_g2s(s_hd, A.hist_d + n0 * m * KF(P), b_hist, &bar);
-        if (KF(need_ho)) bulk_load_g2s(s_ho, A.hist_o + n0 * m * KF(P), b_hist, &bar);
-        if (KF(has_carry)) bulk_load_g2s(s_carry, A.carry + n0 * m, b_cell4, &bar);
-        if (DIV && KF(NB) > 0) bulk_load_g2s(s_bt, A.bt + n0 * KF(NB), b_bt, &bar);
-        for (int r = 0; r < KF(R); ++r)
-            bulk_load_g2s(s_dem + r * E, A.demand_T + ((int64_t)A.t * KF(R) + r) * A.N + n0, b_dem, &bar);
+        mbar_expect_tx(&bar[0], bytes);
+        load_inputs(0);
+        bulk_load_g2s(s_inv, A.inv + n0 * m, b_cell4, &bar[0]);
+        bulk_load_g2s(s_bl, A.backlog + n0 * m, b_cell4, &bar[0]);
+        bulk_load_g2s(s_ou, A.order_u + n0 * m, b_cell4, &bar[0]);
+        bulk_load_g2s(s_pipe, A.pipe + n0 * KF(L), b_pipe, &bar[0]);
+        if (KF(need_hd)) bulk_load_g2s(s_hd, A.hist_d + n0 * m * KF(P), b_hist, &bar[0]);
+        if (KF(need_ho)) bulk_load_g2s(s_ho, A.hist_o + n0 * m * KF(P), b_hist, &bar[0]);
+        if (KF(has_carry)) bulk_load_g2s(s_carry, A.carry + n0 * m, b_cell4, &bar[0]);
+        if (DIV && KF(NB) > 0) bulk_load_g2s(s_bt, A.bt + n0 * KF(NB), b_bt, &bar[0]);
+        if (K > 1) {                                 // period 1's inputs land while period 0 computes
+            mbar_expect_tx(&bar[1], b_in);
+            load_inputs(1);
+        }
     }
 
     // per-lane constants (overlaps the bulk loads)
@@ -146,11 +162,24 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
     const int delay_m1 = np.delay - 1;
     const double om_d = (double)np.order_max;
     const double* __restrict__ tabrow = KHAS(tab) ? A.tab + (size_t)(ok ? i : 0) * 4 * KF(TL) : nullptr;
+    int32_t* my_pipe = s_pipe + e_loc * KF(L) + np.pipe_off;
     pdl_wait();
-    bool delayed = false;
-    if (KF(noisy) && ok) delayed = A.mask_T[((int64_t)A.t * A.N + n0 + e_loc) * m + i] != 0;
 
-    mbar_wait(&bar, 0);
+    for (int j = 0; j < K; ++j) {
+    const int t = A.t + j;                           // period being simulated
+    const int b = j & 1;
+    const double* s_act = reinterpret_cast<const double*>(smem + (b ? KT(off_act2) : KT(off_act)));
+    const int32_t* s_dem = reinterpret_cast<const int32_t*>(smem + (b ? KT(off_dem2) : KT(off_dem)));
+    unsigned char* s_obs = smem + (b ? KT(off_obs2) : KT(off_obs));
+    double* s_rew = reinterpret_cast<double*>(smem + (b ? KT(off_rew2) : KT(off_rew)));
+    if (j >= 2) {                                    // output buffer b was last read by the bulk stores of period j - 2
+        if (tid == 0) bulk_wait_read_1();
+        __syncthreads();
+    }
+    bool delayed = false;
+    if (KF(noisy) && ok) delayed = A.mask_T[((int64_t)t * A.N + n0 + e_loc) * m + i] != 0;
+
+    mbar_wait(&bar[b], (uint32_t)((j >> 1) & 1));
 
     // ---- read the tile ----------------------------------------------------------------------
     double act = 0.0;
@@ -159,10 +188,9 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
 #pragma unroll
     for (int k = 0; k < DMAX; ++k) pipe[k] = 0;
 #pragma unroll
-    for (int j = 0; j < PMAX; ++j) { hd[j] = 0; ho[j] = 0; }
+    for (int jj = 0; jj < PMAX; ++jj) { hd[jj] = 0; ho[jj] = 0; }
 #pragma unroll
     for (int k = 0; k < MAXC; ++k) bt[k] = 0;
-    int32_t* my_pipe = s_pipe + e_loc * KF(L) + np.pipe_off;
     if (ok) {
         act = s_act[cell];
         inv = s_inv[cell];
@@ -173,13 +201,13 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
             if (k < np.delay) pipe[k] = my_pipe[k];
         if (KF(need_hd)) {
 #pragma unroll
-            for (int j = 0; j < PMAX; ++j)
-                if (j < KF(P)) hd[j] = s_hd[cell * KF(P) + j];
+            for (int jj = 0; jj < PMAX; ++jj)
+                if (jj < KF(P)) hd[jj] = s_hd[cell * KF(P) + jj];
         }
         if (KF(need_ho)) {
 #pragma unroll
-            for (int j = 0; j < PMAX; ++j)
-                if (j < KF(P)) ho[j] = s_ho[cell * KF(P) + j];
+            for (int jj = 0; jj < PMAX; ++jj)
+                if (jj < KF(P)) ho[jj] = s_ho[cell * KF(P) + jj];
         }
         if (np.retailer_idx >= 0) cust = s_dem[np.retailer_idx * E + e_loc];
         if (KF(has_carry)) carry = s_carry[cell];
@@ -197,26 +225,26 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
     int demand;
     int od[MAXC];
     if constexpr (DIV) {
-        int s = 0;
+        int sum = 0;
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
             od[k] = 0;
             if (k < KF(maxc)) {
                 const int v = __shfl_sync(0xffffffffu, order, tbase + (child_lane[k] < 0 ? 0 : child_lane[k]));
                 od[k] = child_lane[k] < 0 ? 0 : v;
-                s += od[k];
+                sum += od[k];
             }
         }
-        demand = (np.retailer_idx >= 0) ? min(cust, np.inv_max) : s;
+        demand = (np.retailer_idx >= 0) ? min(cust, np.inv_max) : sum;
     } else {
         const int down = __shfl_up_sync(0xffffffffu, order, 1);
         demand = (i == 0) ? min(cust, np.inv_max) : down;
     }
     int acq = carry;
     int carry_new = 0;
-    if (A.t >= np.delay) {
+    if (t >= np.delay) {
         acq += pipe[0];
-        if (delayed && A.t < KF(T) - 1) { carry_new = acq; acq = 0; }
+        if (delayed && t < KF(T) - 1) { carry_new = acq; acq = 0; }
     }
     const int ship = min(backlog + demand, inv + acq);
     int incoming;
@@ -250,7 +278,7 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
         pipe[k] = (k == delay_m1) ? incoming : nxt;
     }
 #pragma unroll
-    for (int j = PMAX - 1; j > 0; --j) { hd[j] = hd[j - 1]; ho[j] = ho[j - 1]; }
+    for (int jj = PMAX - 1; jj > 0; --jj) { hd[jj] = hd[jj - 1]; ho[jj] = ho[jj - 1]; }
     hd[0] = demand;
     ho[0] = order;
 
@@ -273,13 +301,13 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
             if (k < np.delay) my_pipe[k] = pipe[k];
         if (KF(need_hd)) {
 #pragma unroll
-            for (int j = 0; j < PMAX; ++j)
-                if (j < KF(P)) s_hd[cell * KF(P) + j] = hd[j];
+            for (int jj = 0; jj < PMAX; ++jj)
+                if (jj < KF(P)) s_hd[cell * KF(P) + jj] = hd[jj];
         }
         if (KF(need_ho)) {
 #pragma unroll
-            for (int j = 0; j < PMAX; ++j)
-                if (j < KF(P)) s_ho[cell * KF(P) + j] = ho[j];
+            for (int jj = 0; jj < PMAX; ++jj)
+                if (jj < KF(P)) s_ho[cell * KF(P) + jj] = ho[jj];
         }
         if (KF(has_carry)) s_carry[cell] = carry_new;
         if constexpr (DIV) {
@@ -293,7 +321,7 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
         if (KF(multi)) s_rew[cell] = reward_out;
         else if (i == 0) s_rew[e_loc] = reward_out;
         if (KHAS(obs)) write_obs_row<DMAX, PMAX>(s_obs + (size_t)cell * O * es, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
-        // optional diagnostics go straight to global memory (off the fast path)
+        // optional diagnostics go straight to global memory (off the fast path; single-period launches only)
         if (KF(has_info)) {
         const int64_t gcell = (n0 + e_loc) * m + i;
         if (A.info.demand_dev) A.info.demand_dev[gcell] = demand;
@@ -304,21 +332,28 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
         }
     }
     fence_proxy_async_smem();          // every writer orders its generic-proxy stores before the bulk copies
-    __syncthreads();
+    __syncthreads();                   // ... and everybody is done reading input buffer b
     if (tid == 0) {
-        bulk_store_only(A.inv + n0 * m, s_inv, b_cell4);
-        bulk_store_only(A.backlog + n0 * m, s_bl, b_cell4);
-        bulk_store_only(A.order_u + n0 * m, s_ou, b_cell4);
-        bulk_store_only(A.pipe + n0 * KF(L), s_pipe, b_pipe);
-        if (KF(need_hd)) bulk_store_only(A.hist_d + n0 * m * KF(P), s_hd, b_hist);
-        if (KF(need_ho)) bulk_store_only(A.hist_o + n0 * m * KF(P), s_ho, b_hist);
-        if (KF(has_carry)) bulk_store_only(A.carry + n0 * m, s_carry, b_cell4);
-        if (DIV && KF(NB) > 0) bulk_store_only(A.bt + n0 * KF(NB), s_bt, b_bt);
-        if (KHAS(obs)) bulk_store_only(reinterpret_cast<unsigned char*>(A.obs) + n0 * m * O * es, s_obs, (uint32_t)E * m * O * es);
-        bulk_store_only(A.reward + (KF(multi) ? n0 * m : n0), s_rew, KF(multi) ? b_cell8 : (uint32_t)E * 8u);
+        if (KHAS(obs)) bulk_store_only(reinterpret_cast<unsigned char*>(A.obs) + (int64_t)j * A.obs_stride_bytes + n0 * m * O * es, s_obs, (uint32_t)E * m * O * es);
+        bulk_store_only(A.reward + (int64_t)j * A.rew_stride + (KF(multi) ? n0 * m : n0), s_rew, KF(multi) ? b_cell8 : (uint32_t)E * 8u);
+        if (j == K - 1) {              // the tile's state leaves the SM once per launch
+            bulk_store_only(A.inv + n0 * m, s_inv, b_cell4);
+            bulk_store_only(A.backlog + n0 * m, s_bl, b_cell4);
+            bulk_store_only(A.order_u + n0 * m, s_ou, b_cell4);
+            bulk_store_only(A.pipe + n0 * KF(L), s_pipe, b_pipe);
+            if (KF(need_hd)) bulk_store_only(A.hist_d + n0 * m * KF(P), s_hd, b_hist);
+            if (KF(need_ho)) bulk_store_only(A.hist_o + n0 * m * KF(P), s_ho, b_hist);
+            if (KF(has_carry)) bulk_store_only(A.carry + n0 * m, s_carry, b_cell4);
+            if (DIV && KF(NB) > 0) bulk_store_only(A.bt + n0 * KF(NB), s_bt, b_bt);
+        }
         bulk_commit();
-        bulk_wait_read_all();            // shared memory must outlive the bulk engine's reads
+        if (j + 2 < K) {               // input buffer b is free again: fetch the inputs of period j + 2
+            mbar_expect_tx(&bar[b], b_in);
+            load_inputs(j + 2);
+        }
     }
+    }   // periods
+    if (tid == 0) bulk_wait_read_all();  // shared memory must outlive the bulk engine's reads
 }
 
 }  // namespace imx

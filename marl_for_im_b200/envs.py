@@ -455,6 +455,30 @@ class _ImxEnvBase:
         self.state = self._shape_obs(obs_buf)
         return self.state, self._shape_reward(rew_buf), self._shape_done(done_flag), self._shape_info(t, info_bufs)
 
+    def step_many(self, actions, obs_out=None, reward_out=None, want_obs=True):
+        """K consecutive ``step()`` calls on a stored plan ``actions [K, N, m]`` (the LP scripts' replay loops,
+        DSHLP_4.py:905-925) in one call: returns ``(obs [K, N, m, O] or None, reward [K, N, m] / [K, N], done)``.
+        Same results as K ``step()`` calls; one launch with the state resident on chip where the batch allows it."""
+        if not self.batched:
+            raise _lib.ImxError("step_many is a batched-mode call (construct the env with num_envs=N)")
+        N, m, O = self.num_envs, self.num_nodes, self.obs_len
+        act = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions, dtype=np.float64))
+        act = act.to(device=self.device, dtype=torch.float64).reshape(-1, N, m).contiguous()
+        K = act.shape[0]
+        if want_obs and obs_out is None:
+            obs_out = torch.empty((K, N, m, O), dtype=self.obs_dtype, device=self.device)
+        if reward_out is None:
+            reward_out = torch.empty((K, N, m) if self.MULTI else (K, N), dtype=torch.float64, device=self.device)
+        _lib.check(self._lib.imx_step_many(self._handle, C.c_void_p(act.data_ptr()), K,
+                                           C.c_void_p(obs_out.data_ptr()) if obs_out is not None else None,
+                                           C.c_void_p(reward_out.data_ptr()), self._stream()))
+        self._keepalive_many = act
+        if obs_out is not None:
+            self.last_obs, self.last_reward = obs_out[K - 1], reward_out[K - 1]
+            self.state = self._shape_obs(obs_out[K - 1])
+        done = self.period >= self.num_periods
+        return obs_out, reward_out, (self._shape_done(done))
+
     # ------------------------------------------------------------------ drop-in mode histories
     def _alloc_histories(self):
         T, m = self.num_periods, self.num_nodes
