@@ -200,3 +200,49 @@ def test_host_buffer_path_matches_device_path(monkeypatch):
             _lib.check(env._lib.imx_step_host(env._handle, ptr(act_h[t]), ptr(obs_h), ptr(rew_h)))
             np.testing.assert_array_equal(view(obs_h), want_obs[t], err_msg=f"{mode} obs t={t}")
             np.testing.assert_array_equal(view(rew_h), want_rew[t], err_msg=f"{mode} reward t={t}")
+
+
+@pytest.mark.parametrize("kind,preset,n,obs_dtype", [("MAIM", "serial4", 65536, "float64"), ("MAIM", "serial4", 16384 + 4096, "float32"),
+                                                      ("MAIM_div", "div2", 32768, "float64"), ("IM", "serial8", 24576, "float64")])
+def test_host_buffer_path_large_batches(kind, preset, n, obs_dtype, monkeypatch):
+    """Large batches on pinned buffers (zero-copy: the TMA kernel addresses host memory) and with staged copies must
+    equal the device path, including the period counter and the past-the-end error."""
+    import ctypes as C
+    from marl_for_im_b200 import _lib
+    from marl_for_im_b200.envs import ENV_CLASSES
+    from harness import copy_config
+    cfg = presets.PRESETS[preset]()
+    ref_env = ENV_CLASSES[kind](dict(copy_config(cfg), num_envs=n, obs_dtype=obs_dtype))
+    m, T, O, R = ref_env.num_nodes, ref_env.num_periods, ref_env.obs_len, len(ref_env._retailers)
+    rng = np.random.default_rng(n)
+    demand = rng.poisson(5, size=(n, R, T)).astype(np.int32)
+    actions = np.clip(rng.normal(-0.4, 0.6, size=(T, n, m)), -1.1, 1.1)
+    ref_env.reset(customer_demand=demand)
+    want_obs, want_rew = [ref_env.last_obs.cpu().numpy()], []
+    a_dev = torch.as_tensor(actions, device="cuda:0")
+    for t in range(T):
+        ref_env.step(a_dev[t])
+        want_obs.append(ref_env.last_obs.cpu().numpy())
+        want_rew.append(ref_env.last_reward.cpu().numpy())
+    want_state = {k: v.cpu().numpy() for k, v in ref_env.state_dict().items()}
+    odt = torch.float32 if obs_dtype == "float32" else torch.float64
+    for pipeline in ("1", "0"):
+        monkeypatch.setenv("IMX_HOST_ZERO_COPY", pipeline)
+        env = ENV_CLASSES[kind](dict(copy_config(cfg), num_envs=n, obs_dtype=obs_dtype))
+        dem_h, act_h = torch.as_tensor(demand).pin_memory(), torch.as_tensor(actions).pin_memory()
+        obs_h = torch.empty((n, m, O), dtype=odt).pin_memory()
+        rew_h = torch.empty((n, m) if env.MULTI else (n,), dtype=torch.float64).pin_memory()
+        p = lambda a: C.c_void_p(a.data_ptr())   # noqa: E731
+        _lib.check(env._lib.imx_reset_host(env._handle, p(dem_h), None, 0, 3, p(obs_h)))
+        np.testing.assert_array_equal(obs_h.numpy(), want_obs[0])
+        for t in range(T):
+            obs_h.zero_()
+            rew_h.zero_()
+            _lib.check(env._lib.imx_step_host(env._handle, p(act_h[t]), p(obs_h), p(rew_h)))
+            np.testing.assert_array_equal(obs_h.numpy(), want_obs[t + 1], err_msg=f"zero_copy={pipeline} obs t={t}")
+            np.testing.assert_array_equal(rew_h.numpy(), want_rew[t], err_msg=f"zero_copy={pipeline} reward t={t}")
+        assert env.period == T
+        for k, v in env.state_dict().items():
+            np.testing.assert_array_equal(v.cpu().numpy(), want_state[k], err_msg=k)
+        with pytest.raises(IndexError):
+            _lib.check(env._lib.imx_step_host(env._handle, p(act_h[0]), p(obs_h), p(rew_h)))
