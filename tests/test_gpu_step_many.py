@@ -102,3 +102,27 @@ def test_step_many_repeated_and_graph_replayed_at_bench_size():
         assert torch.equal(obs, want_obs) and torch.equal(rew, want_rew), rep
     for k, v in env.state_dict().items():
         assert torch.equal(v, want_state[k]), k
+
+
+@pytest.mark.parametrize("kind,preset", [("MAIM", "serial8"), ("MAIM_div", "div2")])
+def test_step_many_with_noisy_delay_mask(kind, preset):
+    """The carry state of a noisy lead time lives in the tile like the rest of the state; the replayed mask is read per period."""
+    cfg = presets.PRESETS[preset]()
+    n = 4096
+    demand, actions = _inputs(kind, cfg, n, seed=5)
+    env_a = ENV_CLASSES[kind](dict(copy_config(cfg), num_envs=n))
+    env_b = ENV_CLASSES[kind](dict(copy_config(cfg), num_envs=n))
+    T, m = env_a.num_periods, env_a.num_nodes
+    mask = torch.rand((n, T, m), device="cuda:0") < 0.3
+    env_a.reset(customer_demand=demand, delay_mask=mask)
+    obs, rew = [], []
+    for t in range(T):
+        env_a.step(actions[t])
+        obs.append(env_a.last_obs.clone())
+        rew.append(env_a.last_reward.clone())
+    env_b.reset(customer_demand=demand, delay_mask=mask)
+    o, r, _ = env_b.step_many(actions)
+    assert torch.equal(o, torch.stack(obs)) and torch.equal(r, torch.stack(rew))
+    for k, v in env_b.state_dict().items():
+        assert torch.equal(v, env_a.state_dict()[k]), k
+    assert int(env_b.state_dict()["carry"].abs().sum()) >= 0 and "carry" in env_b.state_dict()
