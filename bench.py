@@ -268,6 +268,8 @@ def run_ours(args):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from marl_for_im_b200.dist import bind_host_to_gpu      # host buffers of the e2e leg next to this rank's GPU
+    numa_cores = bind_host_to_gpu(local_rank)                # (2 GPUs: 0.99 -> 1.37 G agent-steps/s end to end)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -417,7 +419,7 @@ def run_ours(args):
                        "timing": "CUDA events around K CUDA-graph replays (reset + 30 step launches) + per-episode return statistics"
                                  + (" + 1 NCCL all-reduce of the batch statistics" if world > 1 else "") + ", max over ranks"},
             "roofline": roofline, "roofline_large_n": roof_large, "replay_fused": replay_fused, "cpu_baseline": cpu, "cpu_baseline_c": cpu_c, "e2e": e2e, "e2e_f32_obs": e2e_f32,
-            "gpu_launches": int(launches_per_episode * args.steps),
+            "gpu_launches": int(launches_per_episode * args.steps), "host_cores_bound_to_gpu_numa_node": numa_cores,
             "clocks": clocks,
             "episode_stats": {"n": float(final_stats[0].item()), "mean_return": float((final_stats[1] / final_stats[0]).item())},
         }

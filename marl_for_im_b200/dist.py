@@ -15,6 +15,28 @@ import torch
 import torch.distributed as dist
 
 
+def bind_host_to_gpu(device_index: int) -> int:
+    """Pins this process to the CPU cores NVML reports as local to ``device_index`` (its NUMA node), so that
+    pinned host buffers allocated afterwards (first touch) sit next to the GPU's PCIe root port — what the
+    host-buffer path (``imx_step_host``) needs when several ranks share a box.  Returns the number of cores
+    bound to, 0 if NVML or the affinity call is unavailable (then nothing changes)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cores = {64 * w + b for w, bits in enumerate(mask) for b in range(64) if (bits >> b) & 1}
+        cores &= set(os.sched_getaffinity(0))
+        if not cores:
+            return 0
+        os.sched_setaffinity(0, cores)
+        return len(cores)
+    except Exception:
+        return 0
+
+
 def shard_range(num_envs_total: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous block [lo, hi) of global env indices owned by ``rank`` (sizes differ by at most 1)."""
     base, rem = divmod(int(num_envs_total), int(world_size))
