@@ -124,17 +124,17 @@ static void pick_kernels(imx_env* e) {
     const bool small = (e->D <= 4 && e->P <= 1);
     if constexpr (DIV) {
         const bool few = e->maxc <= 2;
-        if (small && few) { e->tma_fn = step_kernel_tma<M_PAD, 4, 1, 2, true>; e->tma_many_fn = step_kernel_tma<M_PAD, 4, 1, 2, true, true>; }
-        else if (small)   { e->tma_fn = step_kernel_tma<M_PAD, 4, 1, 8, true>; e->tma_many_fn = step_kernel_tma<M_PAD, 4, 1, 8, true, true>; }
-        else if (few)     { e->tma_fn = step_kernel_tma<M_PAD, 8, 8, 2, true>; e->tma_many_fn = step_kernel_tma<M_PAD, 8, 8, 2, true, true>; }
-        else              { e->tma_fn = step_kernel_tma<M_PAD, 8, 8, 8, true>; e->tma_many_fn = step_kernel_tma<M_PAD, 8, 8, 8, true, true>; }
+        if (small && few) { e->tma_fn = step_kernel_tma<M_PAD, 4, 1, 2, true>; e->tma_many_fn = step_kernel_tma_many<M_PAD, 4, 1, 2, true>; }
+        else if (small)   { e->tma_fn = step_kernel_tma<M_PAD, 4, 1, 8, true>; e->tma_many_fn = step_kernel_tma_many<M_PAD, 4, 1, 8, true>; }
+        else if (few)     { e->tma_fn = step_kernel_tma<M_PAD, 8, 8, 2, true>; e->tma_many_fn = step_kernel_tma_many<M_PAD, 8, 8, 2, true>; }
+        else              { e->tma_fn = step_kernel_tma<M_PAD, 8, 8, 8, true>; e->tma_many_fn = step_kernel_tma_many<M_PAD, 8, 8, 8, true>; }
         if (small && few) { e->step_fn = step_kernel<M_PAD, 4, 1, 2, true>; e->rollout_fn = rollout_kernel<M_PAD, 4, 2, true>; }
         else if (small)   { e->step_fn = step_kernel<M_PAD, 4, 1, 8, true>; e->rollout_fn = rollout_kernel<M_PAD, 4, 8, true>; }
         else if (few)     { e->step_fn = step_kernel<M_PAD, 8, 8, 2, true>; e->rollout_fn = rollout_kernel<M_PAD, 8, 2, true>; }
         else              { e->step_fn = step_kernel<M_PAD, 8, 8, 8, true>; e->rollout_fn = rollout_kernel<M_PAD, 8, 8, true>; }
     } else {
         e->tma_fn = small ? step_kernel_tma<M_PAD, 4, 1, 1, false> : step_kernel_tma<M_PAD, 8, 8, 1, false>;
-        e->tma_many_fn = small ? step_kernel_tma<M_PAD, 4, 1, 1, false, true> : step_kernel_tma<M_PAD, 8, 8, 1, false, true>;
+        e->tma_many_fn = small ? step_kernel_tma_many<M_PAD, 4, 1, 1, false> : step_kernel_tma_many<M_PAD, 8, 8, 1, false>;
         if (small) { e->step_fn = step_kernel<M_PAD, 4, 1, 1, false>; e->rollout_fn = rollout_kernel<M_PAD, 4, 1, false>; }
         else       { e->step_fn = step_kernel<M_PAD, 8, 8, 1, false>; e->rollout_fn = rollout_kernel<M_PAD, 8, 1, false>; }
     }
@@ -168,12 +168,10 @@ static void compute_tile(const imx_env* e, TileLayout& L, int tile_width) {
     L.off_obs = take(E * m * e->O * (e->cfg.obs_f32 ? 4 : 8));
     L.off_rew = take(E * m * 8);
     L.total = off;
-    // multi-period launches double-buffer the per-period inputs and outputs; the extra regions sit behind the
+    // multi-period launches double-buffer the per-period inputs; the extra regions sit behind the
     // single-period layout so that a plain step launches the same kernel with `total` bytes only
     L.off_act2 = take(E * m * 8);
     L.off_dem2 = take(e->R * E * 4);
-    L.off_obs2 = take(E * m * e->O * (e->cfg.obs_f32 ? 4 : 8));
-    L.off_rew2 = take(E * m * 8);
     L.total2 = off;
 }
 
@@ -191,7 +189,7 @@ static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, s
     add("td", c.time_dependency != 0); add("pd", c.prev_demand != 0); add("pa", c.prev_actions != 0);
     add("write_hd", e->write_hd); add("noisy", 0); add("has_carry", e->has_carry); add("need_hd", e->need_hd);
     add("need_ho", e->need_ho); add("wd_mult1", e->multi ? 2 : 4); add("wd_mult", e->multi ? 1 : 2); add("TL", TL);
-    add("has_info", 0); add("has_obs", 1); add("has_tab", TL > 0); add("obs_f32", c.obs_f32 != 0);
+    add("noisy_demand", (e->div && c.noisy_demand_threshold > 0.0) ? 1 : 0); add("has_info", 0); add("has_obs", 1); add("has_tab", TL > 0); add("obs_f32", c.obs_f32 != 0);
     int ex = 0;
     const double fr = std::frexp(c.b - c.a, &ex);
     add("bma_pow2", (fr == 0.5 && ex > -1000 && ex < 1000) ? 1 : 0);
@@ -201,7 +199,16 @@ static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, s
     addt("E", L.E); addt("off_act", L.off_act); addt("off_inv", L.off_inv); addt("off_bl", L.off_bl); addt("off_ou", L.off_ou);
     addt("off_pipe", L.off_pipe); addt("off_hd", L.off_hd); addt("off_ho", L.off_ho); addt("off_carry", L.off_carry);
     addt("off_bt", L.off_bt); addt("off_dem", L.off_dem); addt("off_obs", L.off_obs); addt("off_rew", L.off_rew); addt("total", L.total);
-    addt("off_act2", L.off_act2); addt("off_dem2", L.off_dem2); addt("off_obs2", L.off_obs2); addt("off_rew2", L.off_rew2); addt("total2", L.total2);
+    addt("off_act2", L.off_act2); addt("off_dem2", L.off_dem2); addt("total2", L.total2);
+    {   // optional register cap of the multi-period kernel (min CTAs per SM).  Measured: capping to 32 registers makes the
+        // benchmark batch a single wave but spills (16-96 B of stack), 66.7 vs 76.6 G agent-steps/s — so no cap by default.
+        const char* mb = getenv("IMX_MANY_MIN_BLOCKS");
+        int blocks = mb ? atoi(mb) : 1;
+        const int by_threads = 2048 / e->tma_threads;
+        if (blocks > by_threads) blocks = by_threads;
+        if (blocks < 1) blocks = 1;
+        defs.push_back("IMX_MANY_MIN_BLOCKS=" + std::to_string(blocks));
+    }
     defs.push_back("IMX_TMA_THREADS=" + std::to_string(e->tma_threads));
     const int mp = e->step_dense ? e->m : m_pad_of(e);     // step kernel: power-of-two tile width (see select_kernels)
     const int pmax = (e->need_hd || e->need_ho) ? e->P : 1;
@@ -209,7 +216,7 @@ static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, s
     const std::string dv = e->div ? "true" : "false";
     step_name = "imx::step_kernel_tma<" + std::to_string(mp) + ", " + std::to_string(e->D) + ", " + std::to_string(pmax) + ", " +
                 std::to_string(e->div ? maxc : 1) + ", " + dv + ">";
-    many_name = step_name.substr(0, step_name.size() - 1) + ", true>";
+    many_name = "imx::step_kernel_tma_many" + step_name.substr(strlen("imx::step_kernel_tma"));
     rollout_name = "imx::rollout_kernel<" + std::to_string(e->m) + ", " + std::to_string(e->D) + ", " + std::to_string(e->div ? maxc : 1) +
                    ", " + dv + ">";
 }

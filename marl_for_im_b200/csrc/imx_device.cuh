@@ -27,12 +27,14 @@ typedef unsigned long uintptr_t;
 #define KHAS(ptr) (IMX_K_has_##ptr)
 #define KBMA_POW2 (IMX_K_bma_pow2)
 #define KM_POW2 (IMX_K_m_pow2)
+#define KNOISY_DEMAND(g) (IMX_K_noisy_demand)
 #else
 #define KF(name) (A.name)
 #define KT(name) (TLY.name)
 #define KHAS(ptr) (A.ptr != nullptr)
 #define KBMA_POW2 (A.inv_bma != 0.0)
 #define KM_POW2 (A.inv_m != 0.0)
+#define KNOISY_DEMAND(g) ((g).noise_thr > 0.0)
 #endif
 
 namespace imx {
@@ -284,7 +286,7 @@ __device__ __forceinline__ void draw_demand_pair(const DemandGen& g, int64_t n_l
                                   (uint32_t)(t_even >> 1), g.episode);
     d0 = demand_from_uniform(g, u53(v.x, v.y));
     d1 = demand_from_uniform(g, u53(v.z, v.w));
-    if (g.noise_thr > 0.0) {
+    if (KNOISY_DEMAND(g)) {                // a literal in the specialised build: the second Philox call must not bloat the rollout loop
         d0 = demand_noise(g, n_local, r, t_even, d0);
         d1 = demand_noise(g, n_local, r, t_even + 1, d1);
     }

@@ -21,7 +21,7 @@ struct ResetArgs {
 
 template <int DMAX, int PMAX>
 __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ ResetArgs Z, int div) {
-    extern __shared__ double s_tmpl[];                  // [m][O] observation template (8 bytes reserved per element), then int init_inv[m]
+    extern __shared__ __align__(16) double s_tmpl[];                  // [m][O] observation template (8 bytes reserved per element), then int init_inv[m]
     const int m = A.m, O = A.O;
     const int es = A.obs_f32 ? 4 : 8;
     int32_t* s_init = reinterpret_cast<int32_t*>(s_tmpl + m * O);
@@ -49,14 +49,35 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
     for (int64_t k = n4 * 4 + gtid; k < Z.zero_words; k += stride) Z.zero_base[k] = 0;
     for (int64_t k = gtid; k < A.N; k += stride) Z.err[k] = 0;
     if (A.obs) {
-        const int64_t total = A.N * m * O;
-        const int mo = m * O;
-        if (A.obs_f32) {
-            float* dst = reinterpret_cast<float*>(A.obs);
-            const float* src = reinterpret_cast<const float*>(s_tmpl);
-            for (int64_t k = gtid; k < total; k += stride) dst[k] = src[(int)(k % mo)];
+        // every env's initial observation is the same m*O-element template: 16-byte stores where the template
+        // length allows it, and the position inside the template advances by (stride mod len) per iteration
+        // instead of a 64-bit modulo per element
+        const int es = A.obs_f32 ? 4 : 8;
+        const int64_t bytes = A.N * m * O * es;
+        const int tmpl_bytes = m * O * es;
+        if ((tmpl_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(A.obs) & 15) == 0) {
+            const int len = tmpl_bytes / 16;
+            const int64_t total = bytes / 16;
+            const int4* src = reinterpret_cast<const int4*>(s_tmpl);
+            int4* dst = reinterpret_cast<int4*>(A.obs);
+            const int step = (int)(stride % len);
+            int rem = (int)(gtid % len);
+            for (int64_t k = gtid; k < total; k += stride) {
+                dst[k] = src[rem];
+                rem += step;
+                if (rem >= len) rem -= len;
+            }
         } else {
-            for (int64_t k = gtid; k < total; k += stride) A.obs[k] = s_tmpl[(int)(k % mo)];
+            const int len = m * O;
+            const int64_t total = A.N * len;
+            const int step = (int)(stride % len);
+            int rem = (int)(gtid % len);
+            for (int64_t k = gtid; k < total; k += stride) {
+                if (A.obs_f32) reinterpret_cast<float*>(A.obs)[k] = reinterpret_cast<const float*>(s_tmpl)[rem];
+                else A.obs[k] = s_tmpl[rem];
+                rem += step;
+                if (rem >= len) rem -= len;
+            }
         }
     }
     // inv lives inside the zeroed block: a grid-wide ordering is needed between the zero fill and the
@@ -64,10 +85,12 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
     // inv is the FIRST field of the block (offset 0), words [0, N*m)
     const int64_t cells = A.N * m;
     for (int64_t k = gtid; k < (cells + 3) / 4; k += stride) {
+        int rem = (int)((k * 4) % m);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int64_t c = k * 4 + q;
-            if (c < cells) A.inv[c] = s_init[(int)(c % m)];
+            if (c < cells) A.inv[c] = s_init[rem];
+            if (++rem == m) rem = 0;
         }
     }
 }

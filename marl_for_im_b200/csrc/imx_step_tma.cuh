@@ -33,8 +33,8 @@ struct TileLayout {
     int32_t E;                 // envs per tile
     int32_t off_act, off_inv, off_bl, off_ou, off_pipe, off_hd, off_ho, off_carry, off_bt, off_dem, off_obs, off_rew;
     int32_t total;             // dynamic shared memory bytes
-    // second buffers of the per-period inputs (actions, demand) and outputs (obs, reward), used by multi-period launches
-    int32_t off_act2, off_dem2, off_obs2, off_rew2;
+    // second buffers of the per-period inputs (actions, demand), used by multi-period launches
+    int32_t off_act2, off_dem2;
     int32_t total2;            // dynamic shared memory bytes of a multi-period launch (second buffers sit behind `total`)
 };
 
@@ -67,8 +67,6 @@ __device__ __forceinline__ void bulk_store_only(void* gdst, const void* ssrc, ui
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// all but the most recent bulk group have finished reading shared memory
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // Programmatic dependent launch (sm_90+): back-to-back step() launches are chained with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so the next grid may start its prologue
@@ -78,10 +76,9 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // MANY = false: one period per launch (the loop below folds away); MANY = true: A.periods periods per launch with the
-// tile's state resident in shared memory (imx_step_many) — a separate instantiation because the loop costs registers.
-template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV, bool MANY = false>
-__global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_constant__ StepArgs A,
-                                                                const __grid_constant__ TileLayout TLY) {
+// tile's state resident in shared memory (imx_step_many) — separate kernels because the loop costs registers.
+template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV, bool MANY>
+__device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& TLY) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar[2];         // bar[b]: inputs of the periods with parity b (bar[0] also the state)
 
@@ -170,12 +167,8 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
     const int b = j & 1;
     const double* s_act = reinterpret_cast<const double*>(smem + (b ? KT(off_act2) : KT(off_act)));
     const int32_t* s_dem = reinterpret_cast<const int32_t*>(smem + (b ? KT(off_dem2) : KT(off_dem)));
-    unsigned char* s_obs = smem + (b ? KT(off_obs2) : KT(off_obs));
-    double* s_rew = reinterpret_cast<double*>(smem + (b ? KT(off_rew2) : KT(off_rew)));
-    if (j >= 2) {                                    // output buffer b was last read by the bulk stores of period j - 2
-        if (tid == 0) bulk_wait_read_1();
-        __syncthreads();
-    }
+    unsigned char* s_obs = smem + KT(off_obs);       // ONE output buffer: period j - 1's bulk stores have long finished
+    double* s_rew = reinterpret_cast<double*>(smem + KT(off_rew));   // reading it when period j's dynamics are done (waited below)
     bool delayed = false;
     if (KF(noisy) && ok) delayed = A.mask_T[((int64_t)t * A.N + n0 + e_loc) * m + i] != 0;
 
@@ -292,6 +285,10 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
     }
 
     // ---- write the tile back (in place) ----------------------------------------------------------
+    if (MANY && j > 0) {                             // the previous period's stores must be done reading the output buffer
+        if (tid == 0) bulk_wait_read_all();
+        __syncthreads();
+    }
     if (ok) {
         s_inv[cell] = inv_new;
         s_bl[cell] = backlog_new;
@@ -354,6 +351,23 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
     }
     }   // periods
     if (tid == 0) bulk_wait_read_all();  // shared memory must outlive the bulk engine's reads
+}
+
+// One period per launch (step()).
+template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV>
+__global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_constant__ StepArgs A, const __grid_constant__ TileLayout TLY) {
+    step_tile<M_PAD, DMAX, PMAX, MAXC, DIV, false>(A, TLY);
+}
+
+// A.periods periods per launch (imx_step_many).  IMX_MANY_MIN_BLOCKS (runtime-specialised build, set by the host) can cap
+// its registers for more resident CTAs; measured slower (spills), so the default is no cap.
+#ifndef IMX_MANY_MIN_BLOCKS
+#define IMX_MANY_MIN_BLOCKS 1
+#endif
+template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV>
+__global__ void __launch_bounds__(TMA_THREADS, IMX_MANY_MIN_BLOCKS) step_kernel_tma_many(const __grid_constant__ StepArgs A,
+                                                                                      const __grid_constant__ TileLayout TLY) {
+    step_tile<M_PAD, DMAX, PMAX, MAXC, DIV, true>(A, TLY);
 }
 
 }  // namespace imx
