@@ -200,14 +200,10 @@ static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, s
     addt("off_pipe", L.off_pipe); addt("off_hd", L.off_hd); addt("off_ho", L.off_ho); addt("off_carry", L.off_carry);
     addt("off_bt", L.off_bt); addt("off_dem", L.off_dem); addt("off_obs", L.off_obs); addt("off_rew", L.off_rew); addt("total", L.total);
     addt("off_act2", L.off_act2); addt("off_dem2", L.off_dem2); addt("total2", L.total2);
-    {   // optional register cap of the multi-period kernel (min CTAs per SM).  Measured: capping to 32 registers makes the
-        // benchmark batch a single wave but spills (16-96 B of stack), 66.7 vs 76.6 G agent-steps/s — so no cap by default.
-        const char* mb = getenv("IMX_MANY_MIN_BLOCKS");
-        int blocks = mb ? atoi(mb) : 1;
-        const int by_threads = 2048 / e->tma_threads;
-        if (blocks > by_threads) blocks = by_threads;
-        if (blocks < 1) blocks = 1;
-        defs.push_back("IMX_MANY_MIN_BLOCKS=" + std::to_string(blocks));
+    {   // register bound of the multi-period kernel (IMX_MANY_MAXNREG=0: none)
+        const char* mr = getenv("IMX_MANY_MAXNREG");
+        const int maxnreg = mr ? atoi(mr) : 0;             // 0: the per-config default in imx_step_tma.cuh
+        if (maxnreg > 0) defs.push_back("IMX_MANY_MAXNREG=" + std::to_string(maxnreg));
     }
     defs.push_back("IMX_TMA_THREADS=" + std::to_string(e->tma_threads));
     const int mp = e->step_dense ? e->m : m_pad_of(e);     // step kernel: power-of-two tile width (see select_kernels)

@@ -75,6 +75,48 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Shared-memory bank conflicts of the observation tile.  A lane writes its agent's row (O elements) into the tile, whose
+// layout must equal the global [E][m][O] block (it leaves as one linear bulk copy), so consecutive lanes are one row apart.
+// When the row is c = O * es / 16 chunks of 16 bytes and g = gcd(c, 8) > 1, the lanes of a quarter-warp that are 8 / g
+// apart hit the same banks with the same chunk (O = 8 float64: 64-byte rows, 4-way conflict, 16 wavefronts per STS.128
+// instead of 4 — 60 % of all shared-memory wavefronts of the 8-stage kernel, profiles/r1_ncu_step_kernel_8stage_1Mi_envs.txt).
+// Cure: every lane stores the SAME chunks in a ROTATED order — at store q lane l writes chunk (q + r) mod c with
+// r = (l mod 8) / (8 / g) — which makes the eight lanes of a quarter-warp cover eight different 16-byte bank groups.
+// The rotation is a barrel of selects on registers (static indices only).  Runtime-specialised build only (O is a literal).
+#if defined(IMX_JIT) && ((IMX_K_O * (IMX_K_obs_f32 ? 4 : 8)) % 32 == 0) && ((IMX_K_O * (IMX_K_obs_f32 ? 4 : 8)) <= 256)
+#define IMX_OBS_ROTATE 1          // the row is an even number (<= 16) of 16-byte chunks: gcd(c, 8) > 1
+#endif
+#ifdef IMX_OBS_ROTATE
+__host__ __device__ constexpr int obs_gcd8(int c) { return (c % 8 == 0) ? 8 : (c % 4 == 0) ? 4 : (c % 2 == 0) ? 2 : 1; }
+constexpr int OBS_ROW_BYTES = IMX_K_O * (IMX_K_obs_f32 ? 4 : 8);
+constexpr int OBS_ROW_CHUNKS = OBS_ROW_BYTES / 16;
+constexpr int OBS_ROT_G = obs_gcd8(OBS_ROW_CHUNKS);
+
+struct ObsChunk { unsigned long long lo, hi; };
+__device__ __forceinline__ ObsChunk obs_sel(bool c, const ObsChunk& a, const ObsChunk& b) { ObsChunk r; r.lo = c ? a.lo : b.lo; r.hi = c ? a.hi : b.hi; return r; }
+
+__device__ __forceinline__ void store_row_rotated(unsigned char* dst, const unsigned long long (&w)[OBS_ROW_BYTES / 8], int lane) {
+    constexpr int C = OBS_ROW_CHUNKS, G = OBS_ROT_G;
+    const int r = (lane & 7) / (8 / G);                 // 0 .. G-1
+    ObsChunk cur[C], nxt[C];
+#pragma unroll
+    for (int q = 0; q < C; ++q) { cur[q].lo = w[2 * q]; cur[q].hi = w[2 * q + 1]; }
+#pragma unroll
+    for (int bit = 1; bit < G; bit <<= 1) {             // cur[q] <- chunk (q + r) mod C, built bit by bit
+#pragma unroll
+        for (int q = 0; q < C; ++q) nxt[q] = obs_sel((r & bit) != 0, cur[(q + bit) % C], cur[q]);
+#pragma unroll
+        for (int q = 0; q < C; ++q) cur[q] = nxt[q];
+    }
+#pragma unroll
+    for (int q = 0; q < C; ++q) {
+        int j = q + r;
+        if (j >= C) j -= C;
+        *reinterpret_cast<ulonglong2*>(dst + 16 * j) = make_ulonglong2(cur[q].lo, cur[q].hi);
+    }
+}
+#endif
+
 // MANY = false: one period per launch (the loop below folds away); MANY = true: A.periods periods per launch with the
 // tile's state resident in shared memory (imx_step_many) — separate kernels because the loop costs registers.
 template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV, bool MANY>
@@ -317,7 +359,29 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
         }
         if (KF(multi)) s_rew[cell] = reward_out;
         else if (i == 0) s_rew[e_loc] = reward_out;
+#ifdef IMX_OBS_ROTATE
+        {
+            if (KHAS(obs)) {
+                // build the row in registers (typed like the output elements), then store its chunks in rotated order
+                unsigned long long w[OBS_ROW_BYTES / 8];
+                if (KF(obs_f32)) {
+                    float rowf[IMX_K_O];
+                    write_obs_row<DMAX, PMAX>(rowf, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
+#pragma unroll
+                    for (int k = 0; k < OBS_ROW_BYTES / 8; ++k)
+                        w[k] = (unsigned long long)__float_as_uint(rowf[2 * k]) | ((unsigned long long)__float_as_uint(rowf[2 * k + 1]) << 32);
+                } else {
+                    double rowd[IMX_K_O];
+                    write_obs_row<DMAX, PMAX>(rowd, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
+#pragma unroll
+                    for (int k = 0; k < OBS_ROW_BYTES / 8; ++k) w[k] = (unsigned long long)__double_as_longlong(rowd[k]);
+                }
+                store_row_rotated(s_obs + (size_t)cell * OBS_ROW_BYTES, w, lane);
+            }
+        }
+#else
         if (KHAS(obs)) write_obs_row<DMAX, PMAX>(s_obs + (size_t)cell * O * es, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
+#endif
         // optional diagnostics go straight to global memory (off the fast path; single-period launches only)
         if (KF(has_info)) {
         const int64_t gcell = (n0 + e_loc) * m + i;
@@ -359,14 +423,17 @@ __global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_cons
     step_tile<M_PAD, DMAX, PMAX, MAXC, DIV, false>(A, TLY);
 }
 
-// A.periods periods per launch (imx_step_many).  IMX_MANY_MIN_BLOCKS (runtime-specialised build, set by the host) can cap
-// its registers for more resident CTAs; measured slower (spills), so the default is no cap.
-#ifndef IMX_MANY_MIN_BLOCKS
-#define IMX_MANY_MIN_BLOCKS 1
+// A.periods periods per launch (imx_step_many).  The runtime-specialised build bounds its registers (IMX_MANY_MAXNREG,
+// set by the host; measured: the loop wants 40-70, a cap at 32 spills and loses 13 %).
+#if defined(IMX_JIT) && defined(IMX_MANY_MAXNREG)
+#define IMX_MANY_BOUNDS __maxnreg__(IMX_MANY_MAXNREG)
+#elif defined(IMX_JIT)
+#define IMX_MANY_BOUNDS __launch_bounds__(TMA_THREADS, 1)
+#else
+#define IMX_MANY_BOUNDS __launch_bounds__(TMA_THREADS)
 #endif
 template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV>
-__global__ void __launch_bounds__(TMA_THREADS, IMX_MANY_MIN_BLOCKS) step_kernel_tma_many(const __grid_constant__ StepArgs A,
-                                                                                      const __grid_constant__ TileLayout TLY) {
+__global__ void IMX_MANY_BOUNDS step_kernel_tma_many(const __grid_constant__ StepArgs A, const __grid_constant__ TileLayout TLY) {
     step_tile<M_PAD, DMAX, PMAX, MAXC, DIV, true>(A, TLY);
 }
 
