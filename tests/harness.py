@@ -202,3 +202,28 @@ def load_golden(name):
     g = {k: z[k] for k in ("obs", "reward", "demand", "ship", "acq", "order", "profit", "inv", "backlog", "order_u")}
     return dict(kind=str(z["kind"]), config=cfg, demand_trace=z["demand_trace"], actions=z["actions"],
                 delay_mask=(mask if mask.size else None), ref=g)
+
+
+# --------------------------------------------------------------------------------------
+# random divergent networks (breadth-first numbering: a child never has a smaller index than its parent,
+# utils.py:87-92, and the last node is among the deepest, which the reference's price tables assume)
+# --------------------------------------------------------------------------------------
+def random_tree_config(rng, m, max_children=4, periods=20, **flags):
+    conn = {i: [] for i in range(m)}
+    nxt, frontier = 1, [0]
+    while nxt < m:
+        parent = frontier.pop(0) if frontier else nxt - 1
+        k = int(rng.integers(1 if (not frontier) else 0, max_children + 1))
+        k = min(k, m - nxt)
+        for _ in range(k):
+            conn[parent].append(nxt)
+            frontier.append(nxt)
+            nxt += 1
+    cfg = {"num_nodes": m, "num_periods": periods, "connections": conn,
+           "init_inv": rng.integers(5, 15, m).astype(float), "inv_target": rng.integers(0, 4, m).astype(float),
+           "inv_max": rng.integers(20, 45, m).astype(float), "stock_cost": rng.uniform(0.1, 0.5, m),
+           "backlog_cost": rng.uniform(0.3, 0.9, m), "delay": rng.integers(1, 5, m),
+           "time_dependency": True, "prev_demand": True, "prev_actions": False, "prev_length": 1,
+           "independent": False, "share_network": False}
+    cfg.update(flags)
+    return cfg

@@ -119,3 +119,28 @@ def test_runtime_specialisation_compiles_for_sm100a_without_gpu():
         buf = ctypes.create_string_buffer(8192)
         n = lib.imx_jit_compile_check(ctypes.byref(c), buf, 8192)
         assert n > 10000, (kind, n, buf.value.decode()[:500], lib.imx_last_error())
+
+
+def test_header_is_plain_c99_and_links_against_the_library(tmp_path):
+    """include/imx_b200.h must be usable from C: compile a C99 translation unit that takes the address of every declared
+    entry point with -pedantic -Werror, and link it against libimx_b200.so (no GPU call is made)."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "imx_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(imx_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 30
+    src = tmp_path / "abi.c"
+    body = "\n".join(f"    p[{k}] = (void (*)(void))&{n};" for k, n in enumerate(names))
+    src.write_text('#include "imx_b200.h"\n#include <stdio.h>\nint main(void) {\n    void (*p[%d])(void);\n%s\n'
+                   '    imx_config cfg; (void)cfg;\n    printf("%%d %%d\\n", imx_abi_version(), imx_config_size() == (int)sizeof(imx_config));\n'
+                   '    return p[0] == 0;\n}\n' % (len(names), body))
+    exe = tmp_path / "abi"
+    lib_dir = os.path.join(root, "marl_for_im_b200")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                    "-L", lib_dir, "-limx_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["1", "1"]                      # ABI version, and the C struct has the size the library was built with

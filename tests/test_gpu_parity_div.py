@@ -120,3 +120,17 @@ def test_device_generated_noisy_delay_mask():
         # a different threshold re-creates the generator state (handle rebuilt) and changes the rate
         env.reset(customer_demand=demand if R > 1 else demand[:, 0], noisy_delay=True, noisy_delay_threshold=0.6)
         assert abs(env.delay_mask_device().float().mean().item() - 0.6) < 0.01
+
+
+@pytest.mark.parametrize("kind", ["MAIM_div", "IM_div"])
+def test_cuda_random_divergent_networks(kind):
+    """Random trees (5-12 nodes, up to 5 children per node) against the oracle (itself pinned to the reference on the
+    same generator by tests/test_oracle_vs_reference.py and the *div_tree* fixtures)."""
+    from harness import random_tree_config
+    rng = np.random.default_rng(3027 if kind == "MAIM_div" else 3028)
+    for trial in range(10):
+        m = int(rng.integers(5, 13))
+        cfg = random_tree_config(rng, m, int(rng.integers(2, 6)), periods=16, prev_actions=bool(trial % 2), prev_length=1 + trial % 3,
+                                 independent=bool(trial % 3 == 0), share_network=(kind == "MAIM_div" and trial % 4 == 0))
+        demand, actions = random_case(kind, cfg, rng, mu=4, action_mode="near_eq" if trial % 2 else "uniform")
+        assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=40), f"{kind} tree {cfg['connections']}")

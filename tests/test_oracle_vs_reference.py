@@ -106,3 +106,17 @@ def test_base_stock_rollout_and_dfo():
                 _, r, _, _ = ref_env.step(R.base_stock_policy(z, ref_env))
                 assert r == rewards[t]
             np.testing.assert_allclose([im_oracle.poisson_pmf(int(k), 5.0) for k in demand], pmf, rtol=1e-13)
+
+
+@pytest.mark.parametrize("kind", ["MAIM_div", "IM_div"])
+def test_random_divergent_networks(kind):
+    """Random trees (5-12 nodes, up to 5 children per node): the round-robin split with more than two children."""
+    from harness import random_tree_config
+    rng = np.random.default_rng(2027 if kind == "MAIM_div" else 2028)
+    for trial in range(12):
+        m = int(rng.integers(5, 13))
+        cfg = random_tree_config(rng, m, int(rng.integers(2, 6)), periods=16, prev_actions=bool(trial % 2), prev_length=1 + trial % 3,
+                                 independent=bool(trial % 3 == 0), share_network=(kind == "MAIM_div" and trial % 4 == 0))
+        for amode in ("near_eq", "uniform"):
+            demand, actions = random_case(kind, cfg, rng, mu=4, action_mode=amode)
+            assert_same(run_reference(kind, cfg, demand, actions), run_oracle(kind, cfg, demand, actions), f"{kind} tree {cfg['connections']}")
