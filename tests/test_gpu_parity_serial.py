@@ -246,3 +246,26 @@ def test_host_buffer_path_large_batches(kind, preset, n, obs_dtype, monkeypatch)
             np.testing.assert_array_equal(v.cpu().numpy(), want_state[k], err_msg=k)
         with pytest.raises(IndexError):
             _lib.check(env._lib.imx_step_host(env._handle, p(act_h[0]), p(obs_h), p(rew_h)))
+
+
+def test_long_episode_and_demand_layout():
+    """150-period episodes on distinct envs: the stored trace is the
+    caller's [N][R][T] tensor transposed to [T][R][N], and the dynamics match the oracle to the last period."""
+    from marl_for_im_b200.envs import MultiAgentInvManagement, MultiAgentInvManagementDiv
+    rng = np.random.default_rng(150)
+    for cls, kind, cfg, R in ((MultiAgentInvManagement, "MAIM", presets.serial4(), 1), (MultiAgentInvManagementDiv, "MAIM_div", presets.div2(), 3)):
+        cfg = dict(cfg, num_periods=150)
+        N, T = 333, 150
+        m = cfg.get("num_nodes", cfg.get("num_stages"))
+        demand = rng.poisson(5, size=(N, R, T)).astype(np.int32)
+        actions = np.clip(rng.normal(-0.5, 0.5, size=(T, N, m)), -1, 1)
+        env = cls(dict(cfg, num_envs=N))
+        env.reset(customer_demand=demand if R > 1 else demand[:, 0])
+        np.testing.assert_array_equal(env.customer_demand_device().cpu().numpy(), demand.transpose(2, 1, 0))
+        a_dev = torch.as_tensor(actions, device="cuda:0")
+        for t in range(T):
+            env.step(a_dev[t])
+        obs = env.last_obs.cpu().numpy()
+        for n in (0, 127, 128, 332):
+            want = run_oracle(kind, cfg, demand[n] if R > 1 else demand[n, 0], actions[:, n])
+            np.testing.assert_array_equal(obs[n], want["obs"][-1])
