@@ -113,3 +113,25 @@ def div2(time_dependency=True, prev_demand=True, prev_actions=False, prev_length
 
 PRESETS = {"serial4": serial4, "serial4_dfo": serial4_dfo, "serial8": serial8, "serial2": serial2,
            "div1": div1, "div2": div2}
+
+
+# hyperparams.py:3-1010 — the 36 named experiment configurations ("S_k" single-agent PPO, "MA_k" independent / shared
+# multi-agent PPO, "CC_k" centralised critic; k = 1..12).  Their env_config is always the 4-stage chain above; k selects
+# the observation mode (k and k + 6 differ only in trainer hyper-parameters, which are not part of this path).
+_NAMED_OBS_MODES = {1: (False, False, False), 2: (True, False, False), 3: (False, True, True),
+                    4: (False, True, False), 5: (True, True, True), 0: (True, True, False)}
+NAMED_ENV_CLASS = {"S": "InvManagement", "MA": "MultiAgentInvManagement", "CC": "MultiAgentInvManagement"}
+NAMED_CONFIGS = [f"{p}_{k}" for p in ("S", "MA", "CC") for k in range(1, 13)]
+
+
+def named_env_config(name):
+    """``hyperparams.get_hyperparams(name)['env_config']`` for the reference's named configurations, e.g. ``"MA_6"``
+    (BASELINE config 2) or ``"CC_5"``.  Returns ``(env class name, env_config dict)``."""
+    prefix, _, k = name.partition("_")
+    if prefix not in NAMED_ENV_CLASS or not k.isdigit() or not 1 <= int(k) <= 12:
+        raise KeyError(f"unknown configuration {name!r}")
+    td, pd, pa = _NAMED_OBS_MODES[int(k) % 6]
+    cfg = serial4(time_dependency=td, prev_demand=pd, prev_actions=pa, prev_length=1)
+    if prefix == "S":
+        del cfg["independent"]                  # the single-agent configurations carry no such key (hyperparams.py:6)
+    return NAMED_ENV_CLASS[prefix], cfg

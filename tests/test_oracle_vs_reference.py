@@ -120,3 +120,20 @@ def test_random_divergent_networks(kind):
         for amode in ("near_eq", "uniform"):
             demand, actions = random_case(kind, cfg, rng, mu=4, action_mode=amode)
             assert_same(run_reference(kind, cfg, demand, actions), run_oracle(kind, cfg, demand, actions), f"{kind} tree {cfg['connections']}")
+
+
+def test_named_configurations_match_hyperparams_py():
+    """presets.named_env_config reproduces the env_config of every named configuration in hyperparams.py."""
+    import sys
+    from oracle.ref_import import load_reference
+    load_reference()                                    # puts the reference tree on sys.path
+    import hyperparams
+    for name in presets.NAMED_CONFIGS:
+        want = hyperparams.get_hyperparams(name)
+        cls, got = presets.named_env_config(name)
+        assert {"InventoryManagement": "InvManagement", "MultiAgentInventoryManagement": "MultiAgentInvManagement"}[want["env"]] == cls
+        assert set(got) == set(want["env_config"]), name
+        for k, v in want["env_config"].items():
+            np.testing.assert_array_equal(np.asarray(got[k]), np.asarray(v), err_msg=f"{name}.{k}")
+    with pytest.raises(KeyError):
+        presets.named_env_config("MA_13")
