@@ -38,7 +38,9 @@ def main():
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     N, T = args.envs, 30
-    env = MultiAgentInvManagement(dict(presets.serial2(), num_envs=N, reuse_buffers=True))
+    torch.backends.cuda.matmul.allow_tf32 = True         # the policy / critic GEMMs are plumbing here: tensor-core TF32
+    torch.backends.cudnn.allow_tf32 = True
+    env = MultiAgentInvManagement(dict(presets.serial2(), num_envs=N, reuse_buffers=True, obs_dtype="float32"))
     m, O = env.num_nodes, env.obs_len
     W = (m - 1) * (1 + O) + O
     torch.manual_seed(0)
@@ -48,10 +50,10 @@ def main():
 
     @torch.no_grad()
     def episode():
-        obs = env.reset()                                    # Philox Poisson(5) demand drawn on the device
-        full = torch.stack([obs[n] for n in env.agent_names], dim=1)
+        env.reset()                                          # Philox Poisson(5) demand drawn on the device
+        full = env.last_obs                                  # packed [N, m, O] float32 tensor behind the per-agent views
         for t in range(T):
-            own32 = full.float()
+            own32 = full
             acts = []
             for i in range(m):
                 out = actors[i](own32[:, i])
@@ -64,9 +66,9 @@ def main():
             cc = cc_observe(env, full, actions=action, dtype=torch.float32)     # critic input of the CURRENT obs + actions
             for i in range(m):
                 traj["value"][t, :, i] = critics[i](cc[:, i]).squeeze(-1)
-            obs, rew, done, _ = env.step(action.double())
-            full = torch.stack([obs[n] for n in env.agent_names], dim=1)
-            traj["reward"][t] = torch.stack([rew[n] for n in env.agent_names], dim=1)
+            _, _, done, _ = env.step(action.double())
+            full = env.last_obs
+            traj["reward"][t] = env.last_reward
         return done
 
     episode()

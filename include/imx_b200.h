@@ -218,11 +218,11 @@ int imx_eval_stats(imx_env* env, const double* acc_dev, double* stats_dev, int a
 /* central_critic_observer + FillInActions  —  models/CC_Model.py:165-214 (and the hand-built CC
  * observation of CC_inv_management.py:516-528): for every agent the flat vector
  * [opponent_action (m-1) | opponent_obs (m-1)*O | own_obs O], W = imx_cc_obs_len() values.
- *   obs_dev      [N][m][O] float64 (what imx_step / imx_reset wrote)
+ *   obs_dev      [N][m][O] in the element type this env writes (float64, or float32 with cfg.obs_f32)
  *   actions_dev  [N][m] float64 actions of the same step, clipped to [clip_lo, clip_hi]; NULL = zeros
  *   out_dev      [N][m][W] float64, or float32 when out_is_f32 != 0 (RLlib casts observations to float32) */
 int imx_cc_obs_len(const imx_env* env);
-int imx_cc_observe(imx_env* env, const double* obs_dev, const double* actions_dev, double clip_lo, double clip_hi,
+int imx_cc_observe(imx_env* env, const void* obs_dev, const double* actions_dev, double clip_lo, double clip_hi,
                    void* out_dev, int out_is_f32, void* stream);
 
 /* End-to-end convenience calls on HOST buffers (pinned memory recommended): copy in, launch, copy

@@ -25,8 +25,8 @@ def cc_observe(env, obs, actions=None, clip=(-1.0, 1.0), dtype=torch.float64):
         if isinstance(vals[0], torch.Tensor):
             obs = torch.stack([v.reshape(N, O) for v in vals], dim=1)
         else:
-            obs = torch.as_tensor(np.stack([np.asarray(v, dtype=np.float64).reshape(N, O) for v in vals], axis=1), device=env.device)
-    obs = obs.to(device=env.device, dtype=torch.float64).reshape(N, m, O).contiguous()
+            obs = torch.as_tensor(np.stack([np.asarray(v).reshape(N, O) for v in vals], axis=1), device=env.device)
+    obs = obs.to(device=env.device, dtype=env.obs_dtype).reshape(N, m, O).contiguous()   # the element type this env writes
     act = None
     if actions is not None:
         act = env._actions_to_device(actions)

@@ -142,6 +142,16 @@ static void pick_kernels(imx_env* e) {
     e->m_pad = M_PAD;
 }
 
+// The dynamic-shared-memory limit is an attribute of the FUNCTION, shared by every handle that uses the same
+// instantiation: only ever raise it (a handle with a smaller tile must not lower it under a live handle's launches).
+static cudaError_t raise_dyn_smem_limit(const void* fn, size_t bytes) {
+    cudaFuncAttributes fa;
+    cudaError_t rc = cudaFuncGetAttributes(&fa, fn);
+    if (rc != cudaSuccess) return rc;
+    if ((size_t)fa.maxDynamicSharedSizeBytes >= bytes) return cudaSuccess;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 static int m_pad_of(const imx_env* e) {
     const int m = e->m;
     if (e->div) return m <= 4 ? 4 : m <= 8 ? 8 : m <= 16 ? 16 : 32;
@@ -250,7 +260,7 @@ static int select_kernels(imx_env* e) {
     const int epw = 32 / e->m_pad;
     const int tile_bytes = (epw * m * e->O * (e->cfg.obs_f32 ? 4 : 8) + 15) & ~15;
     e->step_smem = (size_t)(STEP_THREADS / 32) * tile_bytes;
-    IMX_CUDA(cudaFuncSetAttribute((const void*)e->step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem));
+    IMX_CUDA(raise_dyn_smem_limit((const void*)e->step_fn, e->step_smem));
     int dev_sms = 0, occ = 0;
     IMX_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e->cfg.device));
     IMX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e->step_fn, STEP_THREADS, e->step_smem));
@@ -273,9 +283,9 @@ static int select_kernels(imx_env* e) {
     // the issue-bound ROLLOUT kernel is specialised with tile width = m (dense lane packing, +21% on div2)
     compute_tile(e, e->tile_jit, e->step_dense ? e->m : m_pad_of(e));
     if (e->tile.total <= 200 * 1024) {
-        IMX_CUDA(cudaFuncSetAttribute((const void*)e->tma_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->tile.total));
+        IMX_CUDA(raise_dyn_smem_limit((const void*)e->tma_fn, (size_t)e->tile.total));
         if (e->tile.total2 <= 200 * 1024)
-            IMX_CUDA(cudaFuncSetAttribute((const void*)e->tma_many_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->tile.total2));
+            IMX_CUDA(raise_dyn_smem_limit((const void*)e->tma_many_fn, (size_t)e->tile.total2));
     }
     else
         e->tma_fn = nullptr;
@@ -1086,11 +1096,10 @@ extern "C" int imx_jit_compile_check(const imx_config* cfg, char* log, int cap) 
 // --------------------------------------------------------------------------------------
 extern "C" int imx_cc_obs_len(const imx_env* e) { return e ? (e->m - 1) * (1 + e->O) + e->O : fail(-1, "null env"); }
 
-extern "C" int imx_cc_observe(imx_env* e, const double* obs_dev, const double* actions_dev, double clip_lo, double clip_hi,
+extern "C" int imx_cc_observe(imx_env* e, const void* obs_dev, const double* actions_dev, double clip_lo, double clip_hi,
                               void* out_dev, int out_is_f32, void* stream) {
     if (!e || !obs_dev || !out_dev) return fail(-1, "null argument");
     if (!e->multi) return fail(-1, "the centralised-critic observation is defined for the multi-agent kinds");
-    if (e->cfg.obs_f32) return fail(-1, "imx_cc_observe reads float64 observations; create the env with obs_f32 = 0 and ask for float32 output instead");
     IMX_CUDA(cudaSetDevice(e->cfg.device));
     const int W = (e->m - 1) * (1 + e->O) + e->O;
     const int64_t total = e->N * e->m * W;
@@ -1098,10 +1107,14 @@ extern "C" int imx_cc_observe(imx_env* e, const double* obs_dev, const double* a
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
     const int64_t want = (total + 255) / 256;
     const unsigned grid = (unsigned)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
-    if (out_is_f32)
-        cc_observer_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(obs_dev, actions_dev, (float*)out_dev, e->N, e->m, e->O, clip_lo, clip_hi);
-    else
-        cc_observer_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(obs_dev, actions_dev, (double*)out_dev, e->N, e->m, e->O, clip_lo, clip_hi);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (e->cfg.obs_f32) {                        // the env writes float32 observations: read them as such
+        if (out_is_f32) cc_observer_kernel<float, float><<<grid, 256, 0, s>>>((const float*)obs_dev, actions_dev, (float*)out_dev, e->N, e->m, e->O, clip_lo, clip_hi);
+        else cc_observer_kernel<float, double><<<grid, 256, 0, s>>>((const float*)obs_dev, actions_dev, (double*)out_dev, e->N, e->m, e->O, clip_lo, clip_hi);
+    } else {
+        if (out_is_f32) cc_observer_kernel<double, float><<<grid, 256, 0, s>>>((const double*)obs_dev, actions_dev, (float*)out_dev, e->N, e->m, e->O, clip_lo, clip_hi);
+        else cc_observer_kernel<double, double><<<grid, 256, 0, s>>>((const double*)obs_dev, actions_dev, (double*)out_dev, e->N, e->m, e->O, clip_lo, clip_hi);
+    }
     IMX_CHECK_LAUNCH("cc_observer_kernel");
     return 0;
 }

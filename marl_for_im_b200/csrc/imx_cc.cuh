@@ -12,8 +12,8 @@
 
 namespace imx {
 
-template <typename OutT>
-__global__ void __launch_bounds__(256) cc_observer_kernel(const double* __restrict__ obs, const double* __restrict__ actions,
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256) cc_observer_kernel(const InT* __restrict__ obs, const double* __restrict__ actions,
                                                           OutT* __restrict__ out, int64_t N, int m, int O, double lo, double hi) {
     const int W = (m - 1) * (1 + O) + O;
     const int64_t total = N * m * W;
@@ -30,9 +30,9 @@ __global__ void __launch_bounds__(256) cc_observer_kernel(const double* __restri
             const int q = w - (m - 1);
             const int slot = q / O, k = q - slot * O;
             const int j = slot < i ? slot : slot + 1;
-            v = obs[(n * m + j) * O + k];
+            v = (double)obs[(n * m + j) * O + k];
         } else {
-            v = obs[(n * m + i) * O + (w - (m - 1) * (1 + O))];
+            v = (double)obs[(n * m + i) * O + (w - (m - 1) * (1 + O))];
         }
         out[idx] = (OutT)v;
     }

@@ -50,6 +50,18 @@ def test_cuda_cc_observer_matches_oracle():
         assert set(d["stage_0"]) == {"own_obs", "opponent_obs", "opponent_action"}
         assert d["stage_1"]["own_obs"].shape == (N, O) and d["stage_1"]["opponent_obs"].shape == (N, (m - 1) * O)
         assert torch.equal(d["stage_1"]["own_obs"], obs["stage_1"])
+    # an env that writes float32 observations: the observer reads them as float32 (same values as casting afterwards)
+    cfg = presets.serial2()
+    e64 = MultiAgentInvManagement(dict(cfg, num_envs=512))
+    e32 = MultiAgentInvManagement(dict(cfg, num_envs=512, obs_dtype="float32"))
+    demand = rng.poisson(5, size=(512, 30)).astype(np.int32)
+    act = torch.as_tensor(rng.uniform(-1, 1, size=(512, 2)), device="cuda:0")
+    for e in (e64, e32):
+        e.reset(customer_demand=demand)
+        e.step(act)
+    want = cc_observe(e64, e64.last_obs, actions=act, dtype=torch.float32)
+    got = cc_observe(e32, e32.last_obs, actions=act, dtype=torch.float32)
+    assert e32.last_obs.dtype == torch.float32 and torch.equal(got, want)
     # drop-in (N = 1, numpy dicts) — the reference's call pattern
     env = MultiAgentInvManagement(presets.serial2())
     o = env.reset(customer_demand=np.full(30, 5))

@@ -269,3 +269,24 @@ def test_long_episode_and_demand_layout():
         for n in (0, 127, 128, 332):
             want = run_oracle(kind, cfg, demand[n] if R > 1 else demand[n, 0], actions[:, n])
             np.testing.assert_array_equal(obs[n], want["obs"][-1])
+
+
+def test_handles_sharing_a_kernel_with_different_tile_sizes():
+    """Two live handles whose configs map to the SAME kernel instantiation but need different amounts of shared memory
+    (observation length / element size): the function's dynamic-shared-memory limit must only ever be raised."""
+    from marl_for_im_b200.envs import MultiAgentInvManagement
+    rng = np.random.default_rng(12)
+    N = 512
+    demand = rng.poisson(5, size=(N, 30)).astype(np.int32)
+    act = torch.as_tensor(rng.uniform(-1, 1, size=(30, N, 2)), device="cuda:0")
+    big = MultiAgentInvManagement(dict(presets.serial2(), num_envs=N))                                   # O = 8 float64
+    small = MultiAgentInvManagement(dict(presets.serial2(prev_actions=False), num_envs=N, obs_dtype="float32"))   # created later, smaller tile
+    ref = MultiAgentInvManagement(dict(presets.serial2(), num_envs=N + 1))                               # direct kernel (N % 4 != 0)
+    d1 = np.concatenate([demand, demand[:1]])
+    for e, d in ((big, demand), (small, demand), (ref, d1)):
+        e.reset(customer_demand=d)
+    for t in range(30):
+        big.step(act[t])
+        small.step(act[t])
+        ref.step(torch.cat([act[t], act[t][:1]]))
+        assert torch.equal(big.last_obs, ref.last_obs[:N]) and torch.equal(big.last_reward, ref.last_reward[:N])
