@@ -89,7 +89,7 @@ def time_steps(kind, cfg, N, reps, action_mode="uniform"):
             "watchdog_flags": errs}
 
 
-def time_steps_many(kind, cfg, N, reps, action_mode="uniform"):
+def time_steps_many(kind, cfg, N, reps, action_mode="uniform", want_obs=True):
     """The same T periods as one imx_step_many launch (stored action plan, state resident on chip)."""
     dev = torch.device("cuda:0")
     env = ENV_CLASSES[kind](dict(cfg, num_envs=N))
@@ -101,7 +101,7 @@ def time_steps_many(kind, cfg, N, reps, action_mode="uniform"):
         actions = torch.rand((T, N, m), dtype=torch.float64, device=dev, generator=g) * 2 - 1
     else:
         actions = (torch.randn((T, N, m), dtype=torch.float64, device=dev, generator=g) * 0.5 - 0.6).clamp(-1, 1)
-    obs = torch.empty((T, N, m, O), dtype=torch.float64, device=dev)
+    obs = torch.empty((T, N, m, O), dtype=torch.float64, device=dev) if want_obs else None
     rew = torch.empty((T, N, m) if env.MULTI else (T, N), dtype=torch.float64, device=dev)
     lib, h = env._lib, env._handle
     s = torch.cuda.current_stream().cuda_stream
@@ -109,7 +109,8 @@ def time_steps_many(kind, cfg, N, reps, action_mode="uniform"):
 
     def run():
         lib.imx_set_period(h, 0)
-        _lib.check(lib.imx_step_many(h, C.c_void_p(actions.data_ptr()), T, C.c_void_p(obs.data_ptr()), C.c_void_p(rew.data_ptr()), C.c_void_p(s)))
+        _lib.check(lib.imx_step_many(h, C.c_void_p(actions.data_ptr()), T, C.c_void_p(obs.data_ptr()) if want_obs else None,
+                                     C.c_void_p(rew.data_ptr()), C.c_void_p(s)))
 
     for _ in range(3):
         run()
@@ -122,7 +123,7 @@ def time_steps_many(kind, cfg, N, reps, action_mode="uniform"):
     torch.cuda.synchronize()
     dt = e0.elapsed_time(e1) * 1e-3 / reps
     S = env.state_words
-    B = 4 * R + 8 * m * (2 + O) + 2 * 4 * S / T
+    B = 4 * R + 8 * m * (2 + (O if want_obs else 0)) + 2 * 4 * S / T
     return {"ms_per_launch": dt * 1e3, "us_per_period": dt * 1e6 / T, "agent_steps_per_sec": N * m * T / dt,
             "algorithmic_bytes_per_env_step": B, "achieved_gbs": B * N * T / dt / 1e9, "frac_of_measured_hbm_peak": B * N * T / dt / 1e9 / PEAK,
             "kernel_variant": VARIANT[lib.imx_kernel_variant(h)], "watchdog_flags": int(env.error_flags.abs().sum())}
@@ -168,6 +169,8 @@ def main():
         ("config4 MAIM_div div2 step, 262144 envs, near-equilibrium actions", lambda: time_steps("MAIM_div", presets.div2(), 262144, args.reps, "near_eq")),
         ("config4 MAIM_div div2 step, 2097152 envs, near-equilibrium actions", lambda: time_steps("MAIM_div", presets.div2(), 1 << 21, max(3, args.reps // 4), "near_eq")),
         ("step_many config2 MAIM 4-stage, 65536 envs x 30 periods", lambda: time_steps_many("MAIM", presets.serial4(), 65536, args.reps)),
+        ("step_many rewards only (obs = NULL) config2 MAIM 4-stage, 65536 envs x 30 periods", lambda: time_steps_many("MAIM", presets.serial4(), 65536, args.reps, want_obs=False)),
+        ("step_many rewards only (obs = NULL) MAIM 4-stage, 1048576 envs x 30 periods", lambda: time_steps_many("MAIM", presets.serial4(), 1 << 20, max(3, args.reps // 4), want_obs=False)),
         ("step_many MAIM 4-stage, 1048576 envs x 30 periods", lambda: time_steps_many("MAIM", presets.serial4(), 1 << 20, max(3, args.reps // 4))),
         ("step_many MAIM 8-stage, 262144 envs x 30 periods", lambda: time_steps_many("MAIM", presets.serial8(), 262144, max(3, args.reps // 2))),
         ("step_many MAIM_div div1, 262144 envs x 30 periods, near-equilibrium", lambda: time_steps_many("MAIM_div", presets.div1(), 262144, max(3, args.reps // 2), "near_eq")),

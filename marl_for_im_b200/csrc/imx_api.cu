@@ -108,6 +108,8 @@ struct imx_env {
     int jit_policy = 0;                  // 0 auto (large batches), 1 always, -1 never (IMX_JIT)
     int jit_state = 0;                   // 0 not tried, 1 specialised kernels loaded, -1 unavailable
     const imxjit::Kernels* jit = nullptr;
+    const imxjit::Kernels* jit_noobs = nullptr;   // specialised without the observation output
+    int jit_noobs_state = 0;
     int last_variant = 0;                // 0 AOT direct, 1 AOT TMA, 2 runtime-specialised TMA
     reset_fn_t reset_fn = nullptr;
     rollout_fn_t rollout_fn = nullptr;
@@ -187,7 +189,7 @@ static void compute_tile(const imx_env* e, TileLayout& L, int tile_width) {
 
 // -D options and template instantiations of the runtime-specialised build (imx_jit.cuh)
 static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, std::string& step_name, std::string& many_name,
-                     std::string& rollout_name) {
+                     std::string& rollout_name, int has_obs = 1) {
     const imx_config& c = e->cfg;
     const bool always_std = (c.kind == IMX_KIND_MAIM_DIV);
     const int std_state = always_std ? 1 : (c.standardise_state != 0);
@@ -199,7 +201,7 @@ static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, s
     add("td", c.time_dependency != 0); add("pd", c.prev_demand != 0); add("pa", c.prev_actions != 0);
     add("write_hd", e->write_hd); add("noisy", 0); add("has_carry", e->has_carry); add("need_hd", e->need_hd);
     add("need_ho", e->need_ho); add("wd_mult1", e->multi ? 2 : 4); add("wd_mult", e->multi ? 1 : 2); add("TL", TL);
-    add("noisy_demand", (e->div && c.noisy_demand_threshold > 0.0) ? 1 : 0); add("has_info", 0); add("has_obs", 1); add("has_tab", TL > 0); add("obs_f32", c.obs_f32 != 0);
+    add("noisy_demand", (e->div && c.noisy_demand_threshold > 0.0) ? 1 : 0); add("has_info", 0); add("has_obs", has_obs); add("has_tab", TL > 0); add("obs_f32", c.obs_f32 != 0);
     int ex = 0;
     const double fr = std::frexp(c.b - c.a, &ex);
     add("bma_pow2", (fr == 0.5 && ex > -1000 && ex < 1000) ? 1 : 0);
@@ -241,6 +243,21 @@ static void ensure_jit(imx_env* e) {
     e->jit = imxjit::get(defs, sn, mn, rn, e->tile_jit.total, e->tile_jit.total2 <= 200 * 1024 ? e->tile_jit.total2 : e->tile_jit.total,
                          e->cfg.device);
     if (e->jit) e->jit_state = 1;
+}
+
+// The same kernels specialised WITHOUT an observation output (step / step_many with obs = NULL: scoring a stored plan
+// needs rewards only — the observation build and 60 % of the bytes fold away).  Compiled on first use.
+static void ensure_jit_noobs(imx_env* e) {
+    if (e->jit_noobs_state != 0) return;
+    e->jit_noobs_state = -1;
+    ensure_jit(e);
+    if (e->jit_state != 1) return;
+    std::vector<std::string> defs;
+    std::string sn, rn, mn;
+    jit_spec(e, e->TL, defs, sn, mn, rn, 0);
+    e->jit_noobs = imxjit::get(defs, sn, mn, rn, e->tile_jit.total, e->tile_jit.total2 <= 200 * 1024 ? e->tile_jit.total2 : e->tile_jit.total,
+                               e->cfg.device);
+    if (e->jit_noobs) e->jit_noobs_state = 1;
 }
 
 static int select_kernels(imx_env* e) {
@@ -764,9 +781,11 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
     const bool tma_legal = e->tma_fn && e->step_path != 1 && (e->N % 4) == 0 && aligned16(actions_dev) && aligned16(obs_dev) &&
                            aligned16(reward_dev);
     bool use_jit = false;
-    if (tma_legal && obs_dev && !A.has_info && !A.noisy) {
-        ensure_jit(e);
-        use_jit = (e->jit_state == 1);
+    const imxjit::Kernels* jk = nullptr;
+    if (tma_legal && !A.has_info && !A.noisy) {
+        if (obs_dev) { ensure_jit(e); if (e->jit_state == 1) jk = e->jit; }
+        else { ensure_jit_noobs(e); if (e->jit_noobs_state == 1) jk = e->jit_noobs; }
+        use_jit = jk != nullptr;
     }
     const TileLayout& TL_use = use_jit ? e->tile_jit : e->tile;
     const int epw_direct = 32 / e->m_pad;
@@ -794,7 +813,7 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
             at[0].value.programmaticStreamSerializationAllowed = 1;
             lc.attrs = at;
             lc.numAttrs = e->use_pdl ? 1 : 0;
-            const CUresult cr = imxjit::g_api.LaunchKernelEx(&lc, fused ? e->jit->step_many : e->jit->step, params, nullptr);
+            const CUresult cr = imxjit::g_api.LaunchKernelEx(&lc, fused ? jk->step_many : jk->step, params, nullptr);
             if (cr != CUDA_SUCCESS) return fail(-3, "launch of the specialised step kernel failed (CUresult %d)", (int)cr);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             e->last_variant = 2;

@@ -126,3 +126,29 @@ def test_step_many_with_noisy_delay_mask(kind, preset):
     for k, v in env_b.state_dict().items():
         assert torch.equal(v, env_a.state_dict()[k]), k
     assert int(env_b.state_dict()["carry"].abs().sum()) >= 0 and "carry" in env_b.state_dict()
+
+
+@pytest.mark.parametrize("kind,preset,n", [("MAIM", "serial4", 8192), ("IM_div", "div2", 4096), ("MAIM", "serial8", 100)])
+def test_without_observation_output(kind, preset, n):
+    """obs = NULL (a caller that only wants rewards, e.g. scoring a stored plan): same rewards and final state as with
+    observations, through imx_step and through imx_step_many."""
+    import ctypes as C
+    from marl_for_im_b200 import _lib
+    cfg = presets.PRESETS[preset]()
+    demand, actions = _inputs(kind, cfg, n, seed=3)
+    want_obs, want_rew, want_state = _plain(kind, cfg, demand, actions, n)
+    env = ENV_CLASSES[kind](dict(copy_config(cfg), num_envs=n))
+    T = env.num_periods
+    env.reset(customer_demand=demand)
+    o, r, _ = env.step_many(actions, want_obs=False)
+    assert o is None and torch.equal(r, want_rew)
+    for k, v in env.state_dict().items():
+        assert torch.equal(v, want_state[k]), k
+    env.reset(customer_demand=demand)
+    rew = torch.empty_like(want_rew)
+    for t in range(T):
+        _lib.check(env._lib.imx_step(env._handle, C.c_void_p(actions[t].data_ptr()), None, C.c_void_p(rew[t].data_ptr()), None,
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert torch.equal(rew, want_rew)
+    for k, v in env.state_dict().items():
+        assert torch.equal(v, want_state[k]), k
