@@ -10,8 +10,10 @@ actions pre-staged on the device.  One bench *step* = one 30-period episode of t
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract: ``roofline`` (step kernel:
 algorithmic bytes / CUDA-event time vs. the measured HBM copy peak), ``roofline_large_n`` (same
-kernel at 4 Mi envs, working set >> L2), ``cpu_baseline`` (the oracle port on the host cores),
-``e2e`` (same metric through the host-buffer ABI with H2D/D2H inside the timed region).
+kernel at 4 Mi envs, working set >> L2), ``replay_fused`` (the same 30 periods as ONE imx_step_many launch),
+``cpu_baseline`` (the oracle port on the host cores; ``cpu_baseline_c``: the plain-C OpenMP restatement),
+``e2e`` (same metric through the host-buffer ABI with H2D/D2H inside the timed region; ``e2e_f32_obs``: the same
+with float32 observations).
 """
 from __future__ import annotations
 
@@ -36,7 +38,7 @@ KERNEL_VARIANTS = {0: "imx::step_kernel (ahead-of-time, direct global accesses)"
                    1: "imx::step_kernel_tma (ahead-of-time, TMA-staged tiles)",
                    2: "imx::step_kernel_tma<4,3,1,1,false> (NVRTC-specialised, TMA-staged tiles)"}
 ENVS_PER_GPU = 65536
-NCU_TRAFFIC_BYTES_65536 = 8402432        # dram__bytes_read.sum + dram__bytes_write.sum, one launch (cold L2), profiles/r1_ncu_step_kernel_tma_specialised_pdl_final.txt
+NCU_TRAFFIC_BYTES_65536 = 8402176        # dram__bytes_read.sum + dram__bytes_write.sum, one launch (cold L2), profiles/r1_ncu_step_kernel_final.txt
 NCU_TRAFFIC_BYTES_4MI = 537099264 + 1402789000   # same counters at 4 Mi envs, profiles/r1_ncu_step_kernel_tma_specialised_4Mi_envs.txt
 WORKLOAD = ("MAIM_env 4-stage serial, MA_6 obs mode (td=T,pd=T,pa=F,P=1, shared reward), step() on "
             "65536 envs per GPU, 30-period episodes, replayed Poisson(5) demand, uniform(-1,1) actions pre-staged")
@@ -384,7 +386,7 @@ def run_ours(args):
                            "ahead, outputs streamed behind the compute; bit-identical to 30 imx_step calls (tests/test_gpu_step_many.py)"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_TRAFFIC_BYTES_65536 if N == ENVS_PER_GPU else None,
-                "traffic_source": "profiles/r1_ncu_step_kernel_tma_specialised_pdl_final.txt (ncu --set full: dram__bytes_read+write per launch; "
+                "traffic_source": "profiles/r1_ncu_step_kernel_final.txt (ncu --set full: dram__bytes_read+write per launch; "
                                   "the 31 MB working set of one launch is L2-resident, hence traffic << algorithmic bytes)", "kernel": KERNEL_VARIANTS[env._lib.imx_kernel_variant(env._handle)], "us_per_launch": dt * 1e6,
                 "algorithmic_bytes_per_env_step": B, "envs_per_launch": N, "peak_source": peak_src,
                 "note": "per-launch time = steps-only graph of 30 dependent launches / 30 (includes inter-kernel gaps)"}
