@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define IMX_ABI_VERSION 1
+#define IMX_ABI_VERSION 2     /* 2: imx_config gained obs_f32 + noisy_demand_threshold; imx_step_many, imx_eval_*; imx_cc_observe takes void* */
 #define IMX_MAX_NODES 32     /* agents (stages / nodes) per env: one lane each            */
 #define IMX_MAX_CHILDREN 8   /* children per node in a divergent network                  */
 #define IMX_MAX_DELAY 8      /* lead time per stage (shipped configs use <= 4)            */

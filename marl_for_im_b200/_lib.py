@@ -9,6 +9,7 @@ import ctypes as C
 import os
 
 MAX_NODES, MAX_CHILDREN, MAX_DELAY, MAX_HIST = 32, 8, 8, 8
+ABI_VERSION = 2          # IMX_ABI_VERSION of include/imx_b200.h this binding mirrors
 KIND = {"IM": 0, "MAIM": 1, "IM_div": 2, "MAIM_div": 3}
 DIST = {"replay": 0, "custom": 0, "poisson": 1, "uniform": 2}
 F_INV, F_BACKLOG, F_ORDER_U, F_PIPE, F_HIST_D, F_HIST_O, F_CARRY, F_BACKLOG_TO, F_ERROR, F_DEMAND, F_DELAY_MASK = range(11)
@@ -100,7 +101,7 @@ def load():
         fn.argtypes = argtypes
     if lib.imx_config_size() != C.sizeof(ImxConfig):
         raise ImxError(f"imx_config layout mismatch: C {lib.imx_config_size()} vs ctypes {C.sizeof(ImxConfig)}")
-    if lib.imx_abi_version() != 1:
+    if lib.imx_abi_version() != ABI_VERSION:
         raise ImxError(f"unexpected ABI version {lib.imx_abi_version()}")
     _lib = lib
     return lib
