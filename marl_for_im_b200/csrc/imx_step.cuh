@@ -107,7 +107,10 @@ __device__ __forceinline__ int ceil_div_pos(int a, int b) {
 template <int MAXC>
 __device__ __forceinline__ int drain_round_robin(int nchild, int (&cnt)[MAXC], int (&st)[MAXC], int& amt, int limit) {
     int passes = 0;
-    while (true) {
+    // every batch ends with a counter emptied, the goods gone or the total gone, so nchild batches suffice: a bounded,
+    // fully unrolled loop (MAXC = 2 for div1 / div2) instead of a data-dependent back edge
+#pragma unroll
+    for (int it = 0; it < MAXC; ++it) {
         int sum = 0, active = 0, lo = 0x7fffffff;
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
