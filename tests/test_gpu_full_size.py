@@ -91,3 +91,33 @@ def test_config3_rollout_8stage_131072_envs_bit_exact():
     r_lo = e_lo.rollout_basestock(np.full(m, 25.0))["returns"]
     r_hi = e_hi.rollout_basestock(np.full(m, 25.0))["returns"]
     assert torch.equal(r_all[:half], r_lo) and torch.equal(r_all[half:], r_hi)
+
+
+def test_very_large_batch_indexing():
+    """8 Mi + 40 envs (1.5 GB of observations per step, a tail tile behind 262 145 full tiles): 64-bit indexing end to end.
+    Every env gets one of 64 distinct traces, so env n must equal env n mod 64 — checked over the whole batch on the device —
+    and the 64 prototypes are checked against the oracle."""
+    from marl_for_im_b200.envs import MultiAgentInvManagement
+    from harness import run_oracle
+    cfg = dict(presets.serial4(), num_periods=6)
+    N, T, m, K = (8 << 20) + 40, 6, 4, 64
+    rng = np.random.default_rng(8)
+    proto_d = rng.poisson(5, size=(K, T)).astype(np.int32)
+    proto_a = rng.uniform(-1, 1, size=(T, K, m))
+    idx = torch.arange(N, device="cuda:0") % K
+    demand = torch.as_tensor(proto_d, device="cuda:0")[idx]                     # [N, T]
+    env = MultiAgentInvManagement(dict(cfg, num_envs=N, reuse_buffers=True))
+    env.reset(customer_demand=demand)
+    pa = torch.as_tensor(proto_a, device="cuda:0")
+    for t in range(T):
+        env.step(pa[t][idx])
+        obs, rew = env.last_obs, env.last_reward
+        assert torch.equal(obs, obs[:K][idx]) and torch.equal(rew, rew[:K][idx]), t
+    for k in (0, 17, 63):
+        want = run_oracle("MAIM", cfg, proto_d[k], proto_a[:, k])
+        np.testing.assert_array_equal(env.last_obs[k].cpu().numpy(), want["obs"][-1])
+        np.testing.assert_array_equal(env.last_obs[N - 40 + k % 40].cpu().numpy(), run_oracle("MAIM", cfg, proto_d[(N - 40 + k % 40) % K], proto_a[:, (N - 40 + k % 40) % K])["obs"][-1])
+    st = env.state_dict()
+    assert torch.equal(st["inv"], st["inv"][:K][idx]) and torch.equal(st["pipe"], st["pipe"][:K][idx])
+    del env
+    torch.cuda.empty_cache()
