@@ -42,8 +42,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -166,7 +166,11 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
     };
 
     pdl_launch_dependents();
-    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    if (tid == 0) {                                  // on the critical path of the tile: one barrier for a plain step
+        mbar_init(&bar[0], 1);
+        if (MANY) mbar_init(&bar[1], 1);
+        mbar_init_fence();
+    }
     __syncthreads();
     if (tid == 0) {
         pdl_wait();                                  // state written by the previous step must be complete and visible
