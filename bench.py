@@ -254,9 +254,12 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    cpu = cpu_c = None
+    cpu = cpu_c = cpu_1 = None
     if world == 1 and not args.skip_cpu:
         cpu = cpu_baseline()                       # before CUDA is initialised (fork-safe)
+        t1 = _cpu_worker((999, 400))               # the same port on ONE core
+        cpu_1 = {"value": 400 * T_PERIODS * M_STAGES / t1, "unit": "agent-steps/s", "cores": 1, "kind": "port",
+                 "sample": f"400 episodes x {T_PERIODS} periods in this process; {t1:.2f} s"}
         try:
             cpu_c = cpu_baseline_c()
         except Exception as exc:
@@ -385,6 +388,7 @@ def run_ours(args):
                     "api": "imx_step_many(K=30): one launch per episode, state resident in shared memory, inputs prefetched two periods "
                            "ahead, outputs streamed behind the compute; bit-identical to 30 imx_step calls (tests/test_gpu_step_many.py)"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "frac_of_nominal_8000_GBs": achieved / 8000.0,
                 "traffic": NCU_TRAFFIC_BYTES_65536 if N == ENVS_PER_GPU else None,
                 "traffic_source": "profiles/r1_ncu_step_kernel_final.txt (ncu --set full: dram__bytes_read+write per launch; "
                                   "the 31 MB working set of one launch is L2-resident, hence traffic << algorithmic bytes)", "kernel": KERNEL_VARIANTS[env._lib.imx_kernel_variant(env._handle)], "us_per_launch": dt * 1e6,
@@ -420,7 +424,7 @@ def run_ours(args):
                               f"({(T * N * m * (2 + O) * 8) / 1e6:.0f} MB > 126 MB L2); the {env.state_words * 4 * N / 1e6:.1f} MB state stays cached by design"),
                        "timing": "CUDA events around K CUDA-graph replays (reset + 30 step launches) + per-episode return statistics"
                                  + (" + 1 NCCL all-reduce of the batch statistics" if world > 1 else "") + ", max over ranks"},
-            "roofline": roofline, "roofline_large_n": roof_large, "replay_fused": replay_fused, "cpu_baseline": cpu, "cpu_baseline_c": cpu_c, "e2e": e2e, "e2e_f32_obs": e2e_f32,
+            "roofline": roofline, "roofline_large_n": roof_large, "replay_fused": replay_fused, "cpu_baseline": cpu, "cpu_baseline_1core": cpu_1, "cpu_baseline_c": cpu_c, "e2e": e2e, "e2e_f32_obs": e2e_f32,
             "gpu_launches": int(launches_per_episode * args.steps), "host_cores_bound_to_gpu_numa_node": numa_cores,
             "clocks": clocks,
             "episode_stats": {"n": float(final_stats[0].item()), "mean_return": float((final_stats[1] / final_stats[0]).item())},
