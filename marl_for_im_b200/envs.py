@@ -430,8 +430,38 @@ class _ImxEnvBase:
         arr = np.ascontiguousarray(np.asarray(act, dtype=np.float64).reshape(N, m))   # np.squeeze semantics of IM_env.py:299
         return torch.as_tensor(arr, device=self.device)
 
+    def step_packed(self, action):
+        """Lean batched step for device-side loops (an RL loop with a GPU policy): ``action`` a contiguous float64
+        ``[N, m]`` CUDA tensor (anything else is converted like ``step`` does), returns the packed tensors
+        ``(obs [N, m, O], reward [N, m] / [N], done)`` — no per-agent dicts, no diagnostics.  With
+        ``reuse_buffers=True`` the same two output tensors are overwritten every call and nothing is allocated."""
+        if isinstance(action, torch.Tensor) and action.dtype == torch.float64 and action.is_cuda and action.is_contiguous() \
+                and action.numel() == self.num_envs * self.num_nodes:
+            act = action
+        else:
+            act = self._actions_to_device(action)
+        obs_buf, rew_buf = self._new_obs(), self._new_reward()
+        _lib.check(self._lib.imx_step(self._handle, act.data_ptr(), obs_buf.data_ptr(), rew_buf.data_ptr(), None,
+                                      torch.cuda.current_stream(self.device).cuda_stream))
+        self.last_obs, self.last_reward = obs_buf, rew_buf
+        return obs_buf, rew_buf, self.period >= self.num_periods
+
+    def _cached_views(self, obs_buf, rew_buf):
+        """Per-agent dict views of the packed outputs; built once per buffer pair (reuse_buffers keeps the pair alive)."""
+        key = (obs_buf.data_ptr(), rew_buf.data_ptr())
+        if getattr(self, "_view_key", None) != key:
+            self._view_key, self._view_obs, self._view_rew = key, self._shape_obs(obs_buf), self._shape_reward(rew_buf)
+        return self._view_obs, self._view_rew
+
     def step(self, action):
         """step — IM_env.py:287-360, MAIM_env.py:330-411, IM_div_env.py:361-549, MAIM_div_env.py:441-630."""
+        if self.batched and not self.return_info:           # fast path: one ctypes call, cached views when buffers are reused
+            obs_buf, rew_buf, done_flag = self.step_packed(action)
+            if self.reuse_buffers:
+                self.state, rew = self._cached_views(obs_buf, rew_buf)
+            else:
+                self.state, rew = self._shape_obs(obs_buf), self._shape_reward(rew_buf)
+            return self.state, rew, self._shape_done(done_flag), {}
         N, m = self.num_envs, self.num_nodes
         t = self.period
         act = self._actions_to_device(action)
@@ -781,13 +811,13 @@ class _MultiAgentShape:
 
     def _shape_obs(self, obs_buf):
         if self.batched:
-            return {name: obs_buf[:, i, :] for i, name in enumerate(self._agent_names)}
+            return dict(zip(self._agent_names, obs_buf.unbind(1)))          # m views from one call
         host = obs_buf[0].cpu().numpy()
         return {name: host[i].copy() for i, name in enumerate(self._agent_names)}
 
     def _shape_reward(self, rew_buf):
         if self.batched:
-            return {name: rew_buf[:, i] for i, name in enumerate(self._agent_names)}
+            return dict(zip(self._agent_names, rew_buf.unbind(1)))
         host = rew_buf[0].cpu().numpy()
         return {name: np.float64(host[i]) for i, name in enumerate(self._agent_names)}
 

@@ -88,3 +88,31 @@ def test_vector_env_surface(kind, preset):
         assert env._episode == before + 1                         # ... which is ONE batch reset
     with pytest.raises(ValueError):
         BatchedMultiAgentEnv(env)
+
+
+def test_step_packed_and_reused_buffers():
+    """The lean device-loop entry (step_packed) and the cached per-agent views of reuse_buffers=True: same numbers as the
+    allocating path, the returned views alias the reused buffers (overwritten every step, by design)."""
+    cfg = presets.serial4()
+    N, T, m = 4096, 30, 4
+    rng = np.random.default_rng(4)
+    demand = rng.poisson(5, size=(N, T)).astype(np.int32)
+    actions = torch.as_tensor(rng.uniform(-1, 1, size=(T, N, m)), device="cuda:0")
+    fresh = ENV_CLASSES["MAIM"](dict(copy_config(cfg), num_envs=N))
+    reuse = ENV_CLASSES["MAIM"](dict(copy_config(cfg), num_envs=N, reuse_buffers=True))
+    lean = ENV_CLASSES["MAIM"](dict(copy_config(cfg), num_envs=N, reuse_buffers=True))
+    for e in (fresh, reuse, lean):
+        e.reset(customer_demand=demand)
+    first_views = None
+    for t in range(T):
+        o1, r1, d1, i1 = fresh.step(actions[t])
+        o2, r2, d2, i2 = reuse.step({a: actions[t][:, i] for i, a in enumerate(reuse.agent_names)})      # dict actions too
+        o3, r3, d3 = lean.step_packed(actions[t])
+        assert d1 == d2 == {"__all__": t == T - 1} and d3 == (t == T - 1) and i1 == i2 == {}
+        for i, a in enumerate(fresh.agent_names):
+            assert torch.equal(o1[a], o2[a]) and torch.equal(r1[a], r2[a])
+            assert torch.equal(o1[a], o3[:, i]) and torch.equal(r1[a], r3[:, i])
+        if first_views is None:
+            first_views = (o2, r2)
+        assert o2 is first_views[0] and r2 is first_views[1]              # cached dicts: nothing rebuilt per step
+        assert o2["stage_1"].data_ptr() == reuse.last_obs[:, 1].data_ptr()
