@@ -45,6 +45,25 @@ def main():
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / reps
             out["step_packed, reuse_buffers=True"] = {"us_per_step_call": dt / (T + 1) * 1e6, "agent_steps_per_sec": N * m * T / dt}
+    # drop-in mode (no num_envs key): one env, numpy in / numpy out, info dicts and history arrays like the reference
+    import numpy as np
+    env = MultiAgentInvManagement(presets.serial4())
+    rng = np.random.default_rng(0)
+    acts = rng.uniform(-1, 1, size=(T, m))
+    demand = rng.poisson(5, size=T)
+    for _ in range(2):
+        env.reset(customer_demand=demand)
+        for t in range(T):
+            env.step({f"stage_{i}": np.array([acts[t, i]]) for i in range(m)})
+    reps = 10
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        env.reset(customer_demand=demand)
+        for t in range(T):
+            env.step({f"stage_{i}": np.array([acts[t, i]]) for i in range(m)})
+    dt = (time.perf_counter() - t0) / reps
+    out["drop-in N=1 (numpy dicts, info, histories)"] = {"us_per_step_call": dt / (T + 1) * 1e6, "agent_steps_per_sec": m * T / dt,
+                                                         "reference_cpu_us_per_step": 241}
     print(json.dumps(out))
 
 

@@ -196,6 +196,7 @@ class _ImxEnvBase:
         h = C.c_void_p()
         _lib.check(lib.imx_create(C.byref(c), C.byref(h)))
         self._handle, self._lib, self._has_carry = h, lib, bool(with_carry)
+        self._mail = None                                    # the drop-in mailbox holds pointers into the old handle's state
         self._handle_threshold = float(self.noisy_delay_threshold)
         self._dev_index = c.device
         self.obs_len = lib.imx_obs_len(h)
@@ -453,8 +454,93 @@ class _ImxEnvBase:
             self._view_key, self._view_obs, self._view_rew = key, self._shape_obs(obs_buf), self._shape_reward(rew_buf)
         return self._view_obs, self._view_rew
 
+    # ------------------------------------------------------------------ drop-in mode (N = 1): one launch, one synchronisation
+    def _mailbox(self):
+        """Pinned host buffer the step kernel reads its actions from and writes every output into directly (the pinned
+        allocation is device-addressable at the same address under UVA): observation, reward, the five info fields;
+        the three state fields the history arrays record follow by ONE small copy.  A drop-in step is then one kernel
+        launch + one copy + one stream synchronisation instead of a dozen device->host reads."""
+        if getattr(self, "_mail", None) is not None and self._mail_handle == self._handle.value:
+            return self._mail_views
+        m, O = self.num_nodes, self.obs_len
+        es = 4 if self.obs_dtype == torch.float32 else 8
+        ptr = {}
+        for f in (_lib.F_INV, _lib.F_BACKLOG, _lib.F_ORDER_U):
+            p_, c_ = C.c_void_p(), C.c_int64()
+            _lib.check(self._lib.imx_state_field(self._handle, f, C.byref(p_), C.byref(c_)))
+            ptr[f] = p_.value
+        lo = min(ptr.values())
+        span = max(ptr.values()) + m * 4 - lo                         # the three fields sit in one block, 256-byte aligned each
+        sizes = [("act", m * 8), ("obs", m * O * es), ("rew", (m if self.MULTI else 1) * 8), ("profit", m * 8), ("demand", m * 4),
+                 ("ship", m * 4), ("acq", m * 4), ("order", m * 4), ("state", span), ("err", 4)]
+        off, offs = 0, {}
+        for name, nbytes in sizes:
+            offs[name] = (off, nbytes)
+            off += (nbytes + 63) & ~63
+        self._mail = torch.zeros(off, dtype=torch.uint8).pin_memory()
+        host = self._mail.numpy()
+        base = self._mail.data_ptr()
+        dt = {"act": np.float64, "obs": np.float32 if es == 4 else np.float64, "rew": np.float64, "profit": np.float64, "demand": np.int32,
+              "ship": np.int32, "acq": np.int32, "order": np.int32, "state": np.int32, "err": np.int32}
+        v = {k: host[o:o + n].view(dt[k]) for k, (o, n) in offs.items()}
+        v["addr"] = {k: base + o for k, (o, n) in offs.items()}
+        v["state_dst"] = self._mail[offs["state"][0]:offs["state"][0] + span].view(torch.int32)
+        v["state_src"] = torch.as_tensor(_DevView(lo, (span // 4,), "<i4"), device=self.device)
+        v["state_idx"] = {f: (ptr[f] - lo) // 4 for f in ptr}
+        v["err_dst"] = self._mail[offs["err"][0]:offs["err"][0] + 4].view(torch.int32)
+        v["info"] = _lib.ImxInfoOut(v["addr"]["demand"], v["addr"]["ship"], v["addr"]["acq"], v["addr"]["order"], v["addr"]["profit"])
+        self._mail_views, self._mail_handle = v, self._handle.value
+        return v
+
+    def _step_dropin(self, action):
+        m, O = self.num_nodes, self.obs_len
+        v = self._mailbox()
+        t = self.period
+        if isinstance(action, dict):
+            for i, name in enumerate(self._agent_names):
+                a = action[name]
+                v["act"][i] = float(a.item() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64).reshape(-1)[0])
+        else:
+            v["act"][:] = (action.detach().cpu().numpy() if isinstance(action, torch.Tensor) else np.asarray(action, dtype=np.float64)).reshape(m)
+        stream = torch.cuda.current_stream(self.device)
+        _lib.check(self._lib.imx_step(self._handle, v["addr"]["act"], v["addr"]["obs"], v["addr"]["rew"], C.byref(v["info"]), stream.cuda_stream))
+        with torch.cuda.stream(stream):
+            v["state_dst"].copy_(v["state_src"], non_blocking=True)
+            if self.DIV:
+                v["err_dst"].copy_(self.error_flags[:1], non_blocking=True)
+        stream.synchronize()
+        if self.DIV and int(v["err"][0]) != 0:
+            raise Exception(f"Infinite Loop {int(v['err'][0])}")             # MAIM_div_env.py:503-505 etc.
+        idx = v["state_idx"]
+        self.inv[t + 1, :] = v["state"][idx[_lib.F_INV]:idx[_lib.F_INV] + m]
+        self.backlog[t + 1, :] = v["state"][idx[_lib.F_BACKLOG]:idx[_lib.F_BACKLOG] + m]
+        self.order_u[t + 1, :] = v["state"][idx[_lib.F_ORDER_U]:idx[_lib.F_ORDER_U] + m]
+        self.demand[t, :] = v["demand"]
+        self.ship[t, :] = v["ship"]
+        self.acquisition[t, :] = v["acq"]
+        self.order_r[t, :] = v["order"]
+        obs = v["obs"].reshape(m, O).copy()
+        rew, profit = v["rew"].copy(), v["profit"].copy()
+        self.last_obs = torch.as_tensor(obs).unsqueeze(0)
+        self.last_reward = torch.as_tensor(rew).reshape((1, m) if self.MULTI else (1,))
+        done_flag = (t + 1) >= self.num_periods
+        if self.MULTI:
+            self.state = {name: obs[i] for i, name in enumerate(self._agent_names)}
+            reward = {name: np.float64(rew[i]) for i, name in enumerate(self._agent_names)}
+            info = {name: {"period": t + 1, "demand": self.demand[t, i], "ship": self.ship[t, i], "acquisition": self.acquisition[t, i],
+                           "actual order": self.order_r[t, i], "profit": np.float64(profit[i])}           # post-increment period (quirk 7)
+                    for i, name in enumerate(self._agent_names)}
+        else:
+            self.state = obs
+            reward = np.float64(rew[0])
+            info = {"period": t, "demand": self.demand[t, :], "ship": self.ship[t, :],                      # pre-increment period (quirk 7)
+                    "acquisition": self.acquisition[t, :], "profit": profit}
+        return self.state, reward, self._shape_done(done_flag), (info if self.return_info else {})
+
     def step(self, action):
         """step — IM_env.py:287-360, MAIM_env.py:330-411, IM_div_env.py:361-549, MAIM_div_env.py:441-630."""
+        if not self.batched:
+            return self._step_dropin(action)
         if self.batched and not self.return_info:           # fast path: one ctypes call, cached views when buffers are reused
             obs_buf, rew_buf, done_flag = self.step_packed(action)
             if self.reuse_buffers:
