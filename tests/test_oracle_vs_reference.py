@@ -137,3 +137,27 @@ def test_named_configurations_match_hyperparams_py():
             np.testing.assert_array_equal(np.asarray(got[k]), np.asarray(v), err_msg=f"{name}.{k}")
     with pytest.raises(KeyError):
         presets.named_env_config("MA_13")
+
+
+def test_topology_helpers_match_utils_py():
+    """marl_for_im_b200.topology against utils.py:87-130 on random trees."""
+    from harness import random_tree_config
+    from marl_for_im_b200 import topology
+    from oracle.ref_import import load_reference
+    R = load_reference()
+    rng = np.random.default_rng(9)
+    for _ in range(25):
+        m = int(rng.integers(3, 14))
+        conn = random_tree_config(rng, m, int(rng.integers(1, 6)))["connections"]
+        R.check_connections(conn)
+        topology.check_connections(conn)
+        want = R.create_network(conn)
+        got = topology.create_network(conn)
+        np.testing.assert_array_equal(got, want)
+        assert topology.get_retailers(got) == R.get_retailers(want)
+        assert [topology.get_stage(i, got) for i in range(m)] == [R.get_stage(i, want) for i in range(m)]
+    bad = {0: [1], 2: [1], 1: []}
+    with pytest.raises(Exception):
+        R.check_connections(bad)
+    with pytest.raises(Exception):
+        topology.check_connections(bad)
