@@ -134,3 +134,35 @@ def test_cuda_random_divergent_networks(kind):
                                  independent=bool(trial % 3 == 0), share_network=(kind == "MAIM_div" and trial % 4 == 0))
         demand, actions = random_case(kind, cfg, rng, mu=4, action_mode="near_eq" if trial % 2 else "uniform")
         assert_same(run_oracle(kind, cfg, demand, actions), run_cuda(kind, cfg, demand, actions, n_copies=40), f"{kind} tree {cfg['connections']}")
+
+
+@pytest.mark.parametrize("obs_dtype", ["float64", "float32"])
+def test_rotated_observation_rows_wide(obs_dtype, monkeypatch):
+    """Observation rows of 16 elements (128 bytes in float64: eight 16-byte chunks, rotation over all 8 lanes of a
+    quarter-warp; 64 bytes in float32: four chunks) through the runtime-specialised kernels, plain and multi-period."""
+    import torch
+    from harness import copy_config, random_tree_config
+    from marl_for_im_b200.envs import ENV_CLASSES
+    monkeypatch.setenv("IMX_JIT", "1")
+    rng = np.random.default_rng(16)
+    cfg = random_tree_config(rng, 7, 3, periods=12, prev_actions=True, prev_length=4, share_network=True)
+    cfg["delay"] = np.array([4, 1, 2, 4, 3, 1, 2])
+    kind, n = "MAIM_div", 256
+    env = ENV_CLASSES[kind](dict(copy_config(cfg), num_envs=n, obs_dtype=obs_dtype))
+    assert env.obs_len == 16
+    demand, actions = random_case(kind, cfg, rng, mu=4, action_mode="near_eq")
+    want = run_oracle(kind, cfg, demand, actions)
+    d = np.broadcast_to(np.asarray(demand)[None], (n,) + np.asarray(demand).shape)
+    a = torch.as_tensor(np.broadcast_to(actions[:, None, :], (actions.shape[0], n, 7)).copy(), device="cuda:0")
+    cast = (lambda x: x.astype(np.float32)) if obs_dtype == "float32" else (lambda x: x)
+    env.reset(customer_demand=d)
+    for t in range(12):
+        env.step(a[t])
+        assert env._lib.imx_kernel_variant(env._handle) == 2
+        got = env.last_obs.cpu().numpy()
+        for k in (0, 3, 8, 255):
+            np.testing.assert_array_equal(got[k], cast(want["obs"][t + 1]), err_msg=f"t={t} env={k}")
+    env.reset(customer_demand=d)
+    o, r, _ = env.step_many(a)
+    np.testing.assert_array_equal(o[:, 5].cpu().numpy(), cast(want["obs"][1:]))
+    np.testing.assert_array_equal(r[:, 5].cpu().numpy(), want["reward"])
