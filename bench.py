@@ -215,7 +215,7 @@ class RawEpisode:
         """the same periods as ONE imx_step_many call on the stored plan; needs the per-period observation / reward
         buffers to be consecutive slices of one tensor"""
         self._lib.check(self.lib.imx_step_many(self.env._handle, C.c_void_p(self.actions.data_ptr()), periods,
-                                               C.c_void_p(self.obs[0].data_ptr()), C.c_void_p(self.rew[0].data_ptr()), C.c_void_p(stream)))
+                                               C.c_void_p(self.obs[0].data_ptr()), C.c_void_p(self.rew[0].data_ptr()), None, C.c_void_p(stream)))
 
     def steps(self, stream, periods):
         h = self.env._handle

@@ -110,7 +110,7 @@ def time_steps_many(kind, cfg, N, reps, action_mode="uniform", want_obs=True):
     def run():
         lib.imx_set_period(h, 0)
         _lib.check(lib.imx_step_many(h, C.c_void_p(actions.data_ptr()), T, C.c_void_p(obs.data_ptr()) if want_obs else None,
-                                     C.c_void_p(rew.data_ptr()), C.c_void_p(s)))
+                                     C.c_void_p(rew.data_ptr()), None, C.c_void_p(s)))
 
     for _ in range(3):
         run()

@@ -79,7 +79,7 @@ int main(int argc, char** argv) {
             for (t = 0; t < T; ++t)                                               /* obs, reward, done, info = env.step(action) */
                 CHECK_IMX(imx_step(env, d_actions + t * cells, d_obs + t * cells * O, d_rew + t * cells, NULL, stream));
         } else {
-            CHECK_IMX(imx_step_many(env, d_actions, (int)T, d_obs, d_rew, stream));   /* the same episode as one call */
+            CHECK_IMX(imx_step_many(env, d_actions, (int)T, d_obs, d_rew, NULL, stream));   /* the same episode as one call */
         }
         if (imx_period(env) != T) { fprintf(stderr, "period %d after the episode\n", imx_period(env)); return 4; }
         CHECK_CUDA(cudaMemcpyAsync(rew, d_rew, (size_t)T * cells * sizeof(double), cudaMemcpyDeviceToHost, stream));

@@ -171,8 +171,11 @@ int imx_step(imx_env* env, const double* actions_dev, double* obs_dev, double* r
  * Where the whole batch goes through the TMA-staged kernel this is ONE launch: every tile's state stays in shared
  * memory for the K periods, actions / demand are prefetched two periods ahead and observations / rewards stream out
  * behind the compute, so state moves once per launch instead of once per period; otherwise K plain launches.
- *   actions_dev [K][N][m], obs_dev [K][N][m][O] or NULL, reward_dev [K][N][m] (MAIM kinds) / [K][N]. */
-int imx_step_many(imx_env* env, const double* actions_dev, int K, void* obs_dev, double* reward_dev, void* stream);
+ *   actions_dev [K][N][m], obs_dev [K][N][m][O] or NULL, reward_dev [K][N][m] (MAIM kinds) / [K][N];
+ *   info: NULL, or diagnostics arrays of K consecutive [N][m] blocks each (the array_profit / array_demand / array_ship /
+ *   array_acquisition records of the LP replay loops, DSHLP_4.py:918-923). */
+int imx_step_many(imx_env* env, const double* actions_dev, int K, void* obs_dev, double* reward_dev,
+                  const imx_info_out* info, void* stream);
 
 /* dfo_func's loop  —  base_restock_policy.py:24-45 with base_stock_policy :4-21 fused in: a whole
  * K = T period episode per env in ONE kernel, state on chip.

@@ -61,7 +61,7 @@ SYMBOLS = {
     "imx_set_period": (C.c_int, [_P, C.c_int]),
     "imx_reset": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint64, _P, _P]),
     "imx_step": (C.c_int, [_P, _P, _P, _P, C.POINTER(ImxInfoOut), _P]),
-    "imx_step_many": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
+    "imx_step_many": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(ImxInfoOut), _P]),
     "imx_rollout_basestock": (C.c_int, [_P, _P, C.c_int, _P, C.c_uint64, _P, _P, _P, _P, C.c_int, _P]),
     "imx_return_stats": (C.c_int, [_P, _P, _P, _P]),
     "imx_reset_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint64, _P]),

@@ -795,7 +795,7 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
         while (n_tma > 0 && (n_tma % epw_direct) != 0) n_tma -= TL_use.E;      // the tail kernel starts on a warp-tile boundary
     }
     e->last_variant = 0;
-    const bool fused = periods > 1 && n_tma == e->N && !A.has_info && TL_use.total2 <= 200 * 1024 && e->fuse_periods;
+    const bool fused = periods > 1 && n_tma == e->N && TL_use.total2 <= 200 * 1024 && e->fuse_periods;
     if (fused) A.periods = periods;
     if (done) *done = A.periods;
     const unsigned tma_smem = (unsigned)(fused ? TL_use.total2 : TL_use.total);
@@ -857,7 +857,8 @@ extern "C" int imx_step(imx_env* e, const double* actions_dev, double* obs_dev, 
 // K consecutive periods on pre-computed actions: one launch that keeps every tile's state in shared memory for all K
 // periods (actions / demand prefetched two periods ahead, observations / rewards streamed out behind the compute)
 // wherever the whole batch goes through the TMA kernel; otherwise K plain launches.  Same results either way.
-extern "C" int imx_step_many(imx_env* e, const double* actions_dev, int K, void* obs_dev, double* reward_dev, void* stream) {
+extern "C" int imx_step_many(imx_env* e, const double* actions_dev, int K, void* obs_dev, double* reward_dev,
+                             const imx_info_out* info, void* stream) {
     if (!e || !actions_dev || !reward_dev) return fail(-1, "null argument");
     if (K < 1) return fail(-1, "K must be >= 1");
     if (e->t + K > e->T) return fail(-6, "imx_step_many: %d periods from period %d run past the end of the episode (%d)", K, e->t, e->T);
@@ -868,9 +869,17 @@ extern "C" int imx_step_many(imx_env* e, const double* actions_dev, int K, void*
     int j = 0;
     while (j < K) {
         int adv = 1;
+        imx_info_out at;                                   // the diagnostics blocks of period j
+        if (info) {
+            at.demand_dev = info->demand_dev ? info->demand_dev + (size_t)j * cells : nullptr;
+            at.ship_dev = info->ship_dev ? info->ship_dev + (size_t)j * cells : nullptr;
+            at.acquisition_dev = info->acquisition_dev ? info->acquisition_dev + (size_t)j * cells : nullptr;
+            at.order_dev = info->order_dev ? info->order_dev + (size_t)j * cells : nullptr;
+            at.profit_dev = info->profit_dev ? info->profit_dev + (size_t)j * cells : nullptr;
+        }
         const int rc = launch_step(e, actions_dev + (size_t)j * cells,
                                    obs_dev ? (double*)((unsigned char*)obs_dev + (size_t)j * obs_stride) : nullptr,
-                                   reward_dev + (size_t)j * rew_stride, nullptr, (cudaStream_t)stream, K - j, &adv);
+                                   reward_dev + (size_t)j * rew_stride, info ? &at : nullptr, (cudaStream_t)stream, K - j, &adv);
         if (rc) return rc;
         j += adv;
     }

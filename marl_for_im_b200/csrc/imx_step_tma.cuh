@@ -388,9 +388,9 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
 #else
         if (KHAS(obs)) write_obs_row<DMAX, PMAX>(s_obs + (size_t)cell * O * es, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
 #endif
-        // optional diagnostics go straight to global memory (off the fast path; single-period launches only)
+        // optional diagnostics go straight to global memory (off the fast path)
         if (KF(has_info)) {
-        const int64_t gcell = (n0 + e_loc) * m + i;
+        const int64_t gcell = (int64_t)j * A.N * m + (n0 + e_loc) * m + i;      // [periods][N][m] blocks in a multi-period launch
         if (A.info.demand_dev) A.info.demand_dev[gcell] = demand;
         if (A.info.ship_dev) A.info.ship_dev[gcell] = ship;
         if (A.info.acquisition_dev) A.info.acquisition_dev[gcell] = acq;

@@ -571,9 +571,10 @@ class _ImxEnvBase:
         self.state = self._shape_obs(obs_buf)
         return self.state, self._shape_reward(rew_buf), self._shape_done(done_flag), self._shape_info(t, info_bufs)
 
-    def step_many(self, actions, obs_out=None, reward_out=None, want_obs=True):
+    def step_many(self, actions, obs_out=None, reward_out=None, want_obs=True, return_info=False):
         """K consecutive ``step()`` calls on a stored plan ``actions [K, N, m]`` (the LP scripts' replay loops,
-        DSHLP_4.py:905-925) in one call: returns ``(obs [K, N, m, O] or None, reward [K, N, m] / [K, N], done)``.
+        DSHLP_4.py:905-925) in one call: returns ``(obs [K, N, m, O] or None, reward [K, N, m] / [K, N], done)``, plus with ``return_info=True`` a
+        dict of ``[K, N, m]`` tensors ``demand, ship, acquisition, actual order, profit`` (DSHLP_4.py:918-923).
         Same results as K ``step()`` calls; one launch with the state resident on chip where the batch allows it."""
         if not self.batched:
             raise _lib.ImxError("step_many is a batched-mode call (construct the env with num_envs=N)")
@@ -585,14 +586,23 @@ class _ImxEnvBase:
             obs_out = torch.empty((K, N, m, O), dtype=self.obs_dtype, device=self.device)
         if reward_out is None:
             reward_out = torch.empty((K, N, m) if self.MULTI else (K, N), dtype=torch.float64, device=self.device)
+        info_struct, info = None, None
+        if return_info:                                        # [K, N, m] blocks: what the LP replay loops record per period
+            info = {k: torch.empty((K, N, m), dtype=torch.int32, device=self.device) for k in ("demand", "ship", "acquisition", "actual order")}
+            info["profit"] = torch.empty((K, N, m), dtype=torch.float64, device=self.device)
+            info_struct = _lib.ImxInfoOut(info["demand"].data_ptr(), info["ship"].data_ptr(), info["acquisition"].data_ptr(),
+                                          info["actual order"].data_ptr(), info["profit"].data_ptr())
         _lib.check(self._lib.imx_step_many(self._handle, C.c_void_p(act.data_ptr()), K,
                                            C.c_void_p(obs_out.data_ptr()) if obs_out is not None else None,
-                                           C.c_void_p(reward_out.data_ptr()), self._stream()))
+                                           C.c_void_p(reward_out.data_ptr()),
+                                           C.byref(info_struct) if info_struct is not None else None, self._stream()))
         self._keepalive_many = act
         if obs_out is not None:
             self.last_obs, self.last_reward = obs_out[K - 1], reward_out[K - 1]
             self.state = self._shape_obs(obs_out[K - 1])
         done = self.period >= self.num_periods
+        if return_info:
+            return obs_out, reward_out, self._shape_done(done), info
         return obs_out, reward_out, (self._shape_done(done))
 
     # ------------------------------------------------------------------ drop-in mode histories

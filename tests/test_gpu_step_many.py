@@ -85,7 +85,7 @@ def test_step_many_repeated_and_graph_replayed_at_bench_size():
     def episode(stream):
         _lib.check(lib.imx_reset(h, C.c_void_p(demand.data_ptr()), None, 0, 1, None, C.c_void_p(stream)))
         _lib.check(lib.imx_step_many(h, C.c_void_p(actions.data_ptr()), T, C.c_void_p(obs.data_ptr()), C.c_void_p(rew.data_ptr()),
-                                     C.c_void_p(stream)))
+                                     None, C.c_void_p(stream)))
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         episode(side.cuda_stream)
@@ -152,3 +152,25 @@ def test_without_observation_output(kind, preset, n):
     assert torch.equal(rew, want_rew)
     for k, v in env.state_dict().items():
         assert torch.equal(v, want_state[k]), k
+
+
+@pytest.mark.parametrize("kind,preset,n", [("IM", "serial4", 4096), ("MAIM_div", "div2", 4096), ("MAIM", "serial8", 100)])
+def test_step_many_with_diagnostics(kind, preset, n):
+    """return_info=True: the per-period demand / ship / acquisition / order / profit blocks equal what K step() calls report."""
+    cfg = presets.PRESETS[preset]()
+    demand, actions = _inputs(kind, cfg, n, seed=9)
+    ref = ENV_CLASSES[kind](dict(copy_config(cfg), num_envs=n, return_info=True))
+    ref.reset(customer_demand=demand)
+    want = {k: [] for k in ("demand", "ship", "acquisition", "actual order", "profit")}
+    rew = []
+    for t in range(ref.num_periods):
+        _, r, _, info = ref.step(actions[t])
+        for k in want:
+            want[k].append(torch.stack([info[a][k] for a in ref.agent_names], dim=1) if ref.MULTI else info[k])
+        rew.append(ref.last_reward.clone())
+    env = ENV_CLASSES[kind](dict(copy_config(cfg), num_envs=n))
+    env.reset(customer_demand=demand)
+    o, r, done, info = env.step_many(actions, return_info=True)
+    assert torch.equal(r, torch.stack(rew))
+    for k in want:
+        assert torch.equal(info[k], torch.stack(want[k]).to(info[k].dtype)), k
