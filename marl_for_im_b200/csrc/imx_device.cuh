@@ -163,9 +163,11 @@ __device__ __forceinline__ int decode_order(double x, double om, bool std_action
         if (bma_pow2) x = __dmul_rn(__dmul_rn(__dsub_rn(x, a), om), inv_bma);
         else x = rev_scale(x, om, a, bma);
     }
-    if (multi) x = fmin(fmax(rint(x), 0.0), om);
-    else x = rint(fmin(fmax(x, 0.0), om));
-    return (int)x;
+    // round-half-to-even then clip (MAIM) and clip then round (IM) give the same integer for an integral order_max
+    // (rounding is monotone and fixes 0 and order_max), so one saturating convert + an integer clamp replaces the float64
+    // rint / fmin / fmax sequence (19 instructions per lane in the rollout loop); NaN converts to 0 like fmax(NaN, 0) did
+    (void)multi;
+    return min(max(__double2int_rn(x), 0), (int)om);
 }
 // Rescaled observation value.  The integer domain of every scaled field is bounded (inventory and
 // unfulfilled orders by inv_max, capped backlog and demand by demand_max, pipeline entries by

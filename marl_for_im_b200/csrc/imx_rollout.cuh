@@ -95,8 +95,10 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
 
         for (int t = 0; t < T; ++t) {
             // base_stock_policy: z - (inv + order_u - backlog), clipped to [0, order_max]  (base_restock_policy.py:12-20)
-            const double inv_ech = __dsub_rn(__dadd_rn((double)inv, (double)order_u), (double)backlog);
-            const double act = fmin(om_d, fmax(__dsub_rn(z, inv_ech), 0.0));
+            // (the three integers are exact in float64, so is their sum: one conversion instead of three + two additions)
+            const double raw = __dsub_rn(z, (double)(inv + order_u - backlog));
+            // with raw (non-standardised) actions the policy's clip to [0, order_max] is subsumed by the env's own clip
+            const double act = KF(std_actions) ? fmin(om_d, fmax(raw, 0.0)) : raw;
             const int order = ok ? decode_order(act, om_d, KF(std_actions) != 0, KF(multi) != 0, A.a, A.bma, A.inv_bma, KBMA_POW2) : 0;
 
             int cust = 0;
