@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
                                                                   const __grid_constant__ RolloutArgs Rg) {
     constexpr int EPW = 32 / M_PAD;
     extern __shared__ int32_t s_draws[];            // [warps][EPW][R][T_even] when Rg.coop_demand
+    __shared__ __align__(16) double s_profit[ROLLOUT_THREADS / 32][2][32];   // per warp, per period parity: the lanes' profits
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int i = lane % M_PAD;
@@ -162,7 +163,18 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
 
             const double profit = ok ? profit_of(np.p, np.c, np.h, np.bc, np.target, ship, order, inv, backlog) : 0.0;
             double r;
-            if (KF(multi)) r = KF(independent) ? profit : div_by_m(tile_seq_sum<M_PAD>(profit, m, tbase), m, A.inv_m, KM_POW2);
+            if (KF(multi)) {
+                if (KF(independent)) {
+                    r = profit;
+                } else if constexpr ((M_PAD & (M_PAD - 1)) != 0) {   // m-wide tiles (m = 6: measured faster with shuffles)
+                    r = div_by_m(tile_seq_sum<M_PAD>(profit, m, tbase), m, A.inv_m, KM_POW2);
+                } else {                                     // shared reward: the tile's profits through shared memory
+                    double* wbuf = s_profit[warp][t & 1];
+                    wbuf[lane] = profit;
+                    __syncwarp();                            // (two buffers: a lane can run at most one period ahead)
+                    r = div_by_m(tile_seq_sum_smem<M_PAD>(wbuf, m, tbase), m, A.inv_m, KM_POW2);
+                }
+            }
             else r = tile_np_sum<M_PAD>(profit, m, tbase);
             ret = __dadd_rn(ret, r);
             if (ok && Rg.step_reward) {
@@ -182,6 +194,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
                 }
             }
         }
+        __syncwarp();                                    // the next episode's period 0 reuses a profit buffer (odd T: the last one read)
 
         if (ok) {
             if (KF(multi)) Rg.ret[cell] = ret;

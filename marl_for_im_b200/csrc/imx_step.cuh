@@ -78,6 +78,28 @@ __device__ __forceinline__ double tile_seq_sum(double v, int m, int tb) {
     return s;
 }
 
+// The same sum with the tile's profits exchanged through shared memory instead of shuffles (the rollout loop: one 8-byte
+// store per lane and M_PAD / 2 16-byte broadcast loads instead of 2 * M_PAD 32-bit shuffles).  `wbuf` is this warp's
+// 32-double buffer of the current period parity; the caller synchronises the warp between the store and the loads.
+template <int M_PAD>
+__device__ __forceinline__ double tile_seq_sum_smem(const double* wbuf, int m, int tb) {
+    double s = 0.0;
+    if constexpr (M_PAD % 2 == 0) {
+        const double2* p = reinterpret_cast<const double2*>(wbuf + tb);       // tb * 8 bytes is a multiple of 16
+#pragma unroll
+        for (int j = 0; j < M_PAD / 2; ++j) {
+            const double2 q = p[j];
+            if (2 * j < m) s = __dadd_rn(s, q.x);
+            if (2 * j + 1 < m) s = __dadd_rn(s, q.y);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < M_PAD; ++j)
+            if (j < m) s = __dadd_rn(s, wbuf[tb + j]);
+    }
+    return s;
+}
+
 // One period of the divergent split for a node with > 1 child — MAIM_div_env.py:483-579 /
 // IM_div_env.py:403-502.  The reference hands out goods one unit per child per round-robin pass
 // (whole passes: the shipped amount may go negative inside a pass, the ledger may go negative; both
