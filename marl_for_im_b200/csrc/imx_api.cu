@@ -455,7 +455,8 @@ static void fill_args(const imx_env* e, StepArgs& A) {
         int ex = 0;
         const double fr = std::frexp(A.bma, &ex);          // power of two <=> mantissa exactly 0.5
         A.inv_bma = (fr == 0.5 && ex > -1000 && ex < 1000) ? 1.0 / A.bma : 0.0;
-        A.inv_m = ((e->m & (e->m - 1)) == 0) ? 1.0 / (double)e->m : 0.0;
+        A.inv_m = 1.0 / (double)e->m;
+        A.m_pow2 = ((e->m & (e->m - 1)) == 0) ? 1 : 0;
     }
     A.TL = e->TL;
     A.tab = e->d_tab;

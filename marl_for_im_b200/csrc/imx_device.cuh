@@ -33,7 +33,7 @@ typedef unsigned long uintptr_t;
 #define KT(name) (TLY.name)
 #define KHAS(ptr) (A.ptr != nullptr)
 #define KBMA_POW2 (A.inv_bma != 0.0)
-#define KM_POW2 (A.inv_m != 0.0)
+#define KM_POW2 (A.m_pow2 != 0)
 #define KNOISY_DEMAND(g) ((g).noise_thr > 0.0)
 #endif
 
@@ -110,7 +110,7 @@ struct StepArgs {
     int32_t wd_mult1, wd_mult;   // watchdog multipliers: LOOP1(A) and the other three
     double a, b, bma;          // bma = b - a
     double inv_bma;            // 1/(b-a) when b-a is a power of two (the division is then an exact scaling), else 0
-    double inv_m;              // 1/m when m is a power of two, else 0 (shared-reward mean)
+    double inv_m;              // RN(1/m) (shared-reward mean: an exact scaling when m is a power of two, else the reciprocal of the division below)
     // tables
     int32_t TL;                // entries per rescale table row (0: no tables, compute)
     int32_t pad_tl;
@@ -136,7 +136,7 @@ struct StepArgs {
     // multi-period replay (imx_step_many): the TMA kernel advances `periods` periods per launch with the tile's state
     // resident in shared memory; period j reads actions + j * act_stride and writes obs / reward slices j
     int32_t periods;                        // >= 1 (1 = plain step)
-    int32_t pad_periods;
+    int32_t m_pow2;                         // m is a power of two
     int64_t act_stride;                     // doubles between consecutive periods' action blocks
     int64_t obs_stride_bytes;               // bytes between consecutive periods' observation blocks
     int64_t rew_stride;                     // doubles between consecutive periods' reward blocks
@@ -181,7 +181,14 @@ __device__ __forceinline__ double scaled(bool has_tab, const double* __restrict_
 }
 // mean of the shared reward: reward_sum / num_stages (MAIM_env.py:434)
 __device__ __forceinline__ double div_by_m(double s, int m, double inv_m, bool m_pow2) {
-    return m_pow2 ? __dmul_rn(s, inv_m) : __ddiv_rn(s, (double)m);
+    if (m_pow2) return __dmul_rn(s, inv_m);
+    // Correctly rounded s / m in three instructions instead of the ~16 of the general division (which also handles
+    // exponent extremes that cannot occur here): with y = RN(1/m) and q0 = RN(s * y), RN(q0 + y * RN(s - m * q0)) is the
+    // correctly rounded quotient (Markstein 1990; the residual s - m * q0 is exact in an FMA).  |s| is a sum of a few
+    // cost * quantity products — far from overflow, underflow and subnormals; s = 0 gives +0 like the division.
+    const double q0 = __dmul_rn(s, inv_m);
+    const double rem = __fma_rn(-q0, (double)m, s);
+    return __fma_rn(rem, inv_m, q0);
 }
 // One observation element.  `row` addresses the agent's vector in the output element type.
 #define OBS_PUT(row, k, v)                                                           \
