@@ -212,6 +212,13 @@ static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, s
     addt("off_pipe", L.off_pipe); addt("off_hd", L.off_hd); addt("off_ho", L.off_ho); addt("off_carry", L.off_carry);
     addt("off_bt", L.off_bt); addt("off_dem", L.off_dem); addt("off_obs", L.off_obs); addt("off_rew", L.off_rew); addt("total", L.total);
     addt("off_act2", L.off_act2); addt("off_dem2", L.off_dem2); addt("total2", L.total2);
+    {   // register bound of the rollout kernel.  Measured (profiles/r1_other_configs_1gpu.jsonl): the divergent kernel wants
+        // ~90 registers and is latency-bound at 6 CTAs/SM — 72 buys occupancy (+6 %); the serial multi-agent kernel spills at
+        // its natural 72 — 96 removes the spills (+3 %); the single-agent kernel is best left alone.  IMX_ROLLOUT_MAXNREG overrides.
+        const char* rr = getenv("IMX_ROLLOUT_MAXNREG");
+        const int bound = rr ? atoi(rr) : (e->div ? 72 : (e->multi ? 96 : 0));
+        if (bound > 0) defs.push_back("IMX_ROLLOUT_MAXNREG=" + std::to_string(bound));
+    }
     {   // register bound of the multi-period kernel (IMX_MANY_MAXNREG=0: none)
         const char* mr = getenv("IMX_MANY_MAXNREG");
         const int maxnreg = mr ? atoi(mr) : 0;             // 0: the per-config default in imx_step_tma.cuh

@@ -26,8 +26,13 @@ struct RolloutArgs {
     DemandGen gen;
 };
 
+#if defined(IMX_JIT) && defined(IMX_ROLLOUT_MAXNREG)
+#define IMX_ROLLOUT_BOUNDS __maxnreg__(IMX_ROLLOUT_MAXNREG)      /* experiment knob of the specialised build (host: IMX_ROLLOUT_MAXNREG) */
+#else
+#define IMX_ROLLOUT_BOUNDS __launch_bounds__(ROLLOUT_THREADS)
+#endif
 template <int M_PAD, int DMAX, int MAXC, bool DIV>
-__global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_constant__ StepArgs A,
+__global__ void IMX_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ StepArgs A,
                                                                   const __grid_constant__ RolloutArgs Rg) {
     constexpr int EPW = 32 / M_PAD;
     extern __shared__ int32_t s_draws[];            // [warps][EPW][R][T_even] when Rg.coop_demand
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(const __grid_c
             // (the three integers are exact in float64, so is their sum: one conversion instead of three + two additions)
             const double raw = __dsub_rn(z, (double)(inv + order_u - backlog));
             // with raw (non-standardised) actions the policy's clip to [0, order_max] is subsumed by the env's own clip
-            const double act = KF(std_actions) ? fmin(om_d, fmax(raw, 0.0)) : raw;
+            const double act = KF(std_actions) ? (raw < 0.0 ? 0.0 : (raw > om_d ? om_d : raw)) : raw;   // z is finite
             const int order = ok ? decode_order(act, om_d, KF(std_actions) != 0, KF(multi) != 0, A.a, A.bma, A.inv_bma, KBMA_POW2) : 0;
 
             int cust = 0;
