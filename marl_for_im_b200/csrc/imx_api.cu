@@ -212,6 +212,12 @@ static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, s
     addt("off_pipe", L.off_pipe); addt("off_hd", L.off_hd); addt("off_ho", L.off_ho); addt("off_carry", L.off_carry);
     addt("off_bt", L.off_bt); addt("off_dem", L.off_dem); addt("off_obs", L.off_obs); addt("off_rew", L.off_rew); addt("total", L.total);
     addt("off_act2", L.off_act2); addt("off_dem2", L.off_dem2); addt("total2", L.total2);
+    {   // register bound of the plain step kernel, measured per family: the divergent kernels (natural 47) gain occupancy at 40
+        // (div1 +5 %, div2 +1.5 %), the 2-wide chain is faster unconstrained (+8 % at 64), the others are best at their natural 32
+        const char* sr = getenv("IMX_STEP_MAXNREG");
+        const int bound = sr ? atoi(sr) : (e->div ? 40 : (m_pad_of(e) == 2 ? 64 : 0));
+        if (bound > 0) defs.push_back("IMX_STEP_MAXNREG=" + std::to_string(bound));
+    }
     {   // register bound of the rollout kernel.  Measured (profiles/r1_other_configs_1gpu.jsonl): the divergent kernel wants
         // ~90 registers and is latency-bound at 6 CTAs/SM — 72 buys occupancy (+6 %); the serial multi-agent kernel spills at
         // its natural 72 — 96 removes the spills (+3 %); the single-agent kernel is best left alone.  IMX_ROLLOUT_MAXNREG overrides.

@@ -424,8 +424,13 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
 }
 
 // One period per launch (step()).
+#if defined(IMX_JIT) && defined(IMX_STEP_MAXNREG)
+#define IMX_STEP_BOUNDS __maxnreg__(IMX_STEP_MAXNREG)            /* experiment knob of the specialised build (host: IMX_STEP_MAXNREG) */
+#else
+#define IMX_STEP_BOUNDS __launch_bounds__(TMA_THREADS)
+#endif
 template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV>
-__global__ void __launch_bounds__(TMA_THREADS) step_kernel_tma(const __grid_constant__ StepArgs A, const __grid_constant__ TileLayout TLY) {
+__global__ void IMX_STEP_BOUNDS step_kernel_tma(const __grid_constant__ StepArgs A, const __grid_constant__ TileLayout TLY) {
     step_tile<M_PAD, DMAX, PMAX, MAXC, DIV, false>(A, TLY);
 }
 
