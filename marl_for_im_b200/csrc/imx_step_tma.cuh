@@ -324,20 +324,22 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
     ho[0] = order;
 
     const double profit = ok ? profit_of(np.p, np.c, np.h, np.bc, np.target, ship, order, inv_new, backlog_new) : 0.0;
-    if (MANY && j > 0) {                             // the previous period's stores must be done reading the output buffer
-        if (tid == 0) bulk_wait_read_all();
-        __syncthreads();
-    }
     double reward_out;
     if (KF(multi)) {
         if (KF(independent)) {
             reward_out = profit;
+        } else if (!(MANY && (m >= 6 || !KHAS(obs)))) {
+            // shared reward by shuffles: measured faster for the plain step kernels and for 4-wide chains
+            reward_out = div_by_m(tile_seq_sum<M_PAD>(profit, m, tbase), m, A.inv_m, KM_POW2);
         } else {
-            // shared reward: the env's m profits meet in ITS row of the reward tile (one 8-byte store per lane, then
-            // 16-byte broadcast loads) instead of 2 m shuffles; the row is overwritten with the reward below
-            if (ok) s_rew[cell] = profit;
+            // multi-period kernels of wider networks (8-stage 0.90 -> 0.96 of peak) and the rewards-only replay (+7-12 %):
+            // shared reward: the env's m profits meet in ITS row of this period's ACTION tile — already consumed, same
+            // [E][m] float64 shape, refilled only after the CTA barrier below — one 8-byte store per lane, then 16-byte
+            // broadcast loads, instead of 2 m shuffles
+            double* scratch = const_cast<double*>(s_act);
+            if (ok) scratch[cell] = profit;
             __syncwarp();
-            const double* row = s_rew + e_loc * m;
+            const double* row = scratch + e_loc * m;
             double sum = 0.0;                        // reward_sum starts at 0 and adds in stage order (MAIM_env.py:418-426)
             if ((m & 1) == 0) {
                 for (int q = 0; q < m / 2; ++q) {
@@ -347,7 +349,6 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
             } else {
                 for (int q = 0; q < m; ++q) sum = __dadd_rn(sum, row[q]);
             }
-            __syncwarp();                            // every lane of the env has read the row
             reward_out = div_by_m(sum, m, A.inv_m, KM_POW2);
         }
     } else {
@@ -355,6 +356,10 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
     }
 
     // ---- write the tile back (in place) ----------------------------------------------------------
+    if (MANY && j > 0) {                             // the previous period's stores must be done reading the output buffer
+        if (tid == 0) bulk_wait_read_all();
+        __syncthreads();
+    }
     if (ok) {
         s_inv[cell] = inv_new;
         s_bl[cell] = backlog_new;
