@@ -227,3 +227,18 @@ def random_tree_config(rng, m, max_children=4, periods=20, **flags):
            "independent": False, "share_network": False}
     cfg.update(flags)
     return cfg
+
+
+def random_serial_config(rng, m, periods=16):
+    """A random serial chain: heterogeneous capacities, targets, costs, lead times, a random rescale interval and a random
+    legal observation mode (prices strictly decreasing, MAIM_env.py:167-168)."""
+    a, b = [(-1, 1), (0, 1), (-2, 2), (0, 3)][int(rng.integers(0, 4))]
+    td, pd, pa = bool(rng.integers(0, 2)), bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+    cfg = {"num_stages": m, "num_periods": periods, "init_inv": rng.integers(3, 15, m).astype(float),
+           "inv_target": rng.integers(0, 5, m).astype(float) + rng.choice([0.0, 0.5], m),
+           "inv_max": rng.integers(15, 45, m).astype(float), "price": np.arange(m + 1, 0, -1).astype(float) + rng.uniform(0, 0.9),
+           "stock_cost": rng.uniform(0.1, 0.5, m), "backlog_cost": rng.uniform(0.3, 0.9, m), "delay": rng.integers(1, 6, m),
+           "time_dependency": td, "prev_demand": pd, "prev_actions": pa, "prev_length": int(rng.integers(1, 5)),
+           "independent": bool(rng.integers(0, 2)), "standardise_state": True, "standardise_actions": bool(rng.integers(0, 2)),
+           "a": a, "b": b}
+    return cfg

@@ -290,3 +290,40 @@ def test_handles_sharing_a_kernel_with_different_tile_sizes():
         small.step(act[t])
         ref.step(torch.cat([act[t], act[t][:1]]))
         assert torch.equal(big.last_obs, ref.last_obs[:N]) and torch.equal(big.last_reward, ref.last_reward[:N])
+
+
+@pytest.mark.parametrize("kind", ["MAIM", "IM"])
+def test_cuda_random_serial_chains(kind, monkeypatch):
+    """Random chains (2-12 stages, lead times up to 5, histories up to 4, rescale intervals other than [-1, 1], raw and
+    standardised actions) against the oracle — pinned to the reference on the same generator by
+    tests/test_oracle_vs_reference.py — through the ahead-of-time and the runtime-specialised kernels."""
+    from harness import random_serial_config
+    rng = np.random.default_rng(5050 if kind == "MAIM" else 5051)
+    done = 0
+    while done < 16:
+        cfg = random_serial_config(rng, int(rng.integers(2, 13)))
+        if kind == "MAIM" and (not cfg["time_dependency"]) and cfg["prev_actions"] and (not cfg["prev_demand"]):
+            continue
+        T, m = cfg["num_periods"], cfg["num_stages"]
+        demand = rng.poisson(rng.uniform(3, 12), T)
+        if cfg["standardise_actions"]:
+            span = cfg["b"] - cfg["a"]
+            actions = rng.uniform(cfg["a"] - 0.1 * span, cfg["b"] + 0.1 * span, size=(T, m))
+        else:
+            actions = rng.uniform(-3, 50, size=(T, m))
+        want = run_oracle(kind, cfg, demand, actions)
+        monkeypatch.setenv("IMX_JIT", "0")
+        assert_same(want, run_cuda(kind, cfg, demand, actions, n_copies=72), f"{kind} {cfg}")
+        # the runtime-specialised kernels serve steps without diagnostics: observations and rewards through them
+        monkeypatch.setenv("IMX_JIT", "1")
+        from harness import copy_config
+        from marl_for_im_b200.envs import ENV_CLASSES
+        env = ENV_CLASSES[kind](dict(copy_config(cfg), num_envs=64, return_info=False))
+        env.reset(customer_demand=np.broadcast_to(demand[None], (64, T)))
+        for t in range(T):
+            env.step(torch.as_tensor(np.broadcast_to(actions[t][None], (64, m)).copy(), device="cuda:0"))
+            assert env._lib.imx_kernel_variant(env._handle) == 2, env._lib.imx_jit_log()
+            np.testing.assert_array_equal(env.last_obs[37].cpu().numpy(), want["obs"][t + 1], err_msg=f"jit obs t={t} {cfg}")
+            r = env.last_reward[37].cpu().numpy()
+            np.testing.assert_array_equal(r if env.MULTI else np.array([r]), want["reward"][t][:m if env.MULTI else 1], err_msg=f"jit reward t={t}")
+        done += 1

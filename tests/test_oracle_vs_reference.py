@@ -161,3 +161,24 @@ def test_topology_helpers_match_utils_py():
         R.check_connections(bad)
     with pytest.raises(Exception):
         topology.check_connections(bad)
+
+
+@pytest.mark.parametrize("kind", ["MAIM", "IM"])
+def test_random_serial_chains(kind):
+    """Random chains (2-12 stages, lead times up to 5, histories up to 4, rescale intervals other than [-1, 1])."""
+    from harness import random_serial_config
+    rng = np.random.default_rng(4040 if kind == "MAIM" else 4041)
+    done = 0
+    while done < 20:
+        cfg = random_serial_config(rng, int(rng.integers(2, 13)))
+        if not _legal(kind, cfg["time_dependency"], cfg["prev_demand"], cfg["prev_actions"]):
+            continue
+        T, m = cfg["num_periods"], cfg["num_stages"]
+        demand = rng.poisson(rng.uniform(3, 12), T)
+        if cfg["standardise_actions"]:
+            span = cfg["b"] - cfg["a"]
+            actions = rng.uniform(cfg["a"] - 0.1 * span, cfg["b"] + 0.1 * span, size=(T, m))
+        else:
+            actions = rng.uniform(-3, 50, size=(T, m))
+        assert_same(run_reference(kind, cfg, demand, actions), run_oracle(kind, cfg, demand, actions), f"{kind} {cfg}")
+        done += 1
