@@ -80,3 +80,37 @@ def test_cuda_eval_accumulators_match_reference_fixture(case):
     got2 = acc2.cpu().numpy()
     np.testing.assert_array_equal(got2[:, :4], got[:, :4])
     assert not got2[:, 4:].any()
+
+
+@pytest.mark.gpu
+def test_cuda_eval_accumulators_on_float32_observations():
+    """An env that writes float32 observations: the accumulators undo the scaling on the float32 values widened to float64
+    (what a script reading RLlib's float32 observations would compute), operation for operation."""
+    import torch
+    from marl_for_im_b200.envs import ENV_CLASSES
+    cfg = case_config("serial4", {})
+    N, m = 512, 4
+    rng = np.random.default_rng(32)
+    demand = rng.poisson(6, size=(N, 30)).astype(np.int32)
+    actions = torch.as_tensor(rng.uniform(-1, 1, size=(30, N, m)), device="cuda:0")
+    env = ENV_CLASSES["MAIM"](dict(copy_config(cfg), num_envs=N, obs_dtype="float32"))
+    env.reset(customer_demand=demand)
+    acc = None
+    want = torch.zeros((N, 4), dtype=torch.float64, device="cuda:0")
+    inv_max = torch.as_tensor(np.asarray(cfg["inv_max"], dtype=np.float64), device="cuda:0")
+    a, b = float(cfg["a"]), float(cfg["b"])
+    for t in range(30):
+        o, r, _, _ = env.step(actions[t])
+        acc = env.eval_accumulate(acc, o, r)
+        x = env.last_obs.double()                                   # [N, m, O]
+        undo = lambda col: (((x[:, :, col] - a) * (inv_max - 0.0)) / (b - a)) + 0.0     # noqa: E731  rev_scale, MAIM_env.py:509-519
+        step_inv = torch.zeros(N, dtype=torch.float64, device="cuda:0")
+        step_bl = torch.zeros(N, dtype=torch.float64, device="cuda:0")
+        for i in range(m):
+            want[:, 0] += env.last_reward[:, i]
+            step_inv += undo(0)[:, i]
+            step_bl += undo(1)[:, i]
+        want[:, 1] += step_inv
+        want[:, 2] += step_bl
+        want[:, 3] += undo(1)[:, 0]
+    assert torch.equal(acc[:, :4], want)
