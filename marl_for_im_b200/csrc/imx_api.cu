@@ -247,7 +247,7 @@ static void ensure_jit(imx_env* e) {
     if (e->jit_state != 0) return;
     e->jit_state = -1;
     if (e->jit_policy < 0 || !e->tma_fn) return;
-    if (e->jit_policy == 0 && e->N < 4096) return;
+    if (e->jit_policy == 0 && e->N < 1024) return;        // below ~1k envs a step is launch latency either way; the compile (1-2 s) is not worth it
     std::vector<std::string> defs;
     std::string sn, rn;
     std::string mn;
