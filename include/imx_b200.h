@@ -15,8 +15,11 @@
  *   - plain C, no C++/torch types; every `_dev` pointer is caller-owned device memory on the
  *     env's device (e.g. a torch tensor's data_ptr()), valid until the stream work finishes;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
- *   - no entry point synchronises the device or allocates memory after imx_create(), except
- *     the *_host convenience calls, so reset/step sequences can be captured in CUDA graphs;
+ *   - no entry point synchronises the device, allocates memory or loads code after imx_create() /
+ *     imx_prepare(), except the *_host convenience calls and the first dfo_dev use of
+ *     imx_rollout_basestock without a step_reward_dev buffer, so reset/step sequences can be captured
+ *     in CUDA graphs.  The runtime-specialised kernels (NVRTC) are compiled and loaded inside
+ *     imx_create() when the batch size selects them; a call issued under stream capture never compiles;
  *   - return value 0 = success, negative = error (imx_last_error() gives the message, thread
  *     local); nothing throws across the ABI;
  *   - one handle is not thread-safe; different handles are independent.
@@ -39,7 +42,9 @@
 extern "C" {
 #endif
 
-#define IMX_ABI_VERSION 2     /* 2: imx_config gained obs_f32 + noisy_demand_threshold; imx_step_many, imx_eval_*; imx_cc_observe takes void* */
+#define IMX_ABI_VERSION 3     /* 3: obs pointers are void* (float64, or float32 with cfg.obs_f32) everywhere; imx_rollout_basestock gained
+                                 delay_mask_dev / noisy and takes pmf [N][R][T]; imx_prepare; imx_step_cc.
+                                 2: imx_config gained obs_f32 + noisy_demand_threshold; imx_step_many, imx_eval_*; imx_cc_observe takes void* */
 #define IMX_MAX_NODES 32     /* agents (stages / nodes) per env: one lane each            */
 #define IMX_MAX_CHILDREN 8   /* children per node in a divergent network                  */
 #define IMX_MAX_DELAY 8      /* lead time per stage (shipped configs use <= 4)            */
@@ -130,6 +135,15 @@ int imx_config_size(void);   /* sizeof(imx_config): lets a foreign-language bind
 int imx_create(const imx_config* cfg, imx_env** out);
 int imx_destroy(imx_env* env);
 
+/* Loads every kernel variant this handle can dispatch to BEFORE the first step, so that no later call compiles,
+ * loads a module or allocates (a requirement for capturing the first step() in a CUDA graph).  imx_create() already
+ * does this for the variants its batch size selects; call imx_prepare() to force the rest.
+ *   flags: IMX_PREPARE_STEP (observation-writing step / step_many / rollout kernels), IMX_PREPARE_NOOBS (the
+ *          obs_dev = NULL specialisation), IMX_PREPARE_HOST (staging buffers + stream of the *_host calls),
+ *          IMX_PREPARE_DFO (scratch of the dfo objective); 0 = all.  Synchronous; may take seconds (NVRTC). */
+enum imx_prepare_flags { IMX_PREPARE_STEP = 1, IMX_PREPARE_NOOBS = 2, IMX_PREPARE_HOST = 4, IMX_PREPARE_DFO = 8 };
+int imx_prepare(imx_env* env, int flags);
+
 /* Derived sizes: O (observation length per agent), S (int32 state words per env), R, L, NB. */
 int imx_obs_len(const imx_env* env);
 int imx_state_words(const imx_env* env);
@@ -156,13 +170,13 @@ int imx_set_period(imx_env* env, int t);
  *   noisy           0: exact lead times for this episode
  *   obs_dev         [N][m][O] receives the initial observation (may be NULL)                      */
 int imx_reset(imx_env* env, const int32_t* demand_dev, const uint8_t* delay_mask_dev, int noisy,
-              uint64_t episode, double* obs_dev, void* stream);
+              uint64_t episode, void* obs_dev, void* stream);
 
 /* step(action)  —  IM_env.py:287-360, MAIM_env.py:330-411, IM_div_env.py:361-549,
  * MAIM_div_env.py:441-630: order clipping, demand propagation, acquisition, shipment (+ split),
  * backlog / pipeline / inventory update, profit reward, observation build.  One kernel launch.
  * done = imx_period(env) >= T after the call.  info may be NULL. */
-int imx_step(imx_env* env, const double* actions_dev, double* obs_dev, double* reward_dev,
+int imx_step(imx_env* env, const double* actions_dev, void* obs_dev, double* reward_dev,
              const imx_info_out* info, void* stream);
 
 /* K consecutive step() calls on pre-computed actions  —  the replay loops that drive an env with a stored plan
@@ -181,14 +195,21 @@ int imx_step_many(imx_env* env, const double* actions_dev, int K, void* obs_dev,
  * K = T period episode per env in ONE kernel, state on chip.
  *   z_dev          base-stock levels, [m] (z_stride = 0) or [N][m] (z_stride = m)
  *   demand_dev     [N][R][T] replayed trace or NULL (Philox, same stream as imx_reset)
- *   pmf_dev        optional [N][T] float64 probabilities of the demand trace, or NULL
+ *   delay_mask_dev [N][T][m] uint8 replayed noisy-delay outcomes or NULL; noisy != 0 with a NULL mask draws them
+ *                  from Philox exactly as imx_reset(noisy = 1) of the same episode would.  The reference's noisy flag
+ *                  is sticky (MAIM_env.py:192-194), so dfo_func after a noisy reset() rolls out WITH delays
+ *                  (MAIM_env.py:449-457); needs cfg.noisy_delay = 1
+ *   pmf_dev        optional [N][R][T] float64 probabilities of the demand trace (serial kinds: R = 1), or NULL
  *   return_dev     IM kinds [N], MAIM kinds [N][m]: sum over periods of the step reward
  *   step_reward_dev optional [T][N] (IM kinds) / [T][N][m] (MAIM kinds) per-period rewards, or NULL
- *   dfo_dev        optional [N]: -(1/T) * np.sum(pmf * reward)  (needs pmf_dev; IM kinds only)
+ *   dfo_dev        optional [N]: -1 / T * np.sum(pmf * rewards) with the rewards broadcast over the R retailer rows and
+ *                  numpy's pairwise summation order over the flattened [R, T] product, any R * T (needs pmf_dev; IM
+ *                  kinds only — the reference's dfo_func cannot run on a dict-reward env).  A second small kernel over
+ *                  step_reward_dev; when that is NULL an internal [T][N] scratch is allocated on first use
  *   write_state    non-zero: leave the final state in the env (period = T), else env is untouched */
 int imx_rollout_basestock(imx_env* env, const double* z_dev, int z_stride, const int32_t* demand_dev,
-                          uint64_t episode, const double* pmf_dev, double* return_dev,
-                          double* step_reward_dev, double* dfo_dev, int write_state, void* stream);
+                          const uint8_t* delay_mask_dev, int noisy, uint64_t episode, const double* pmf_dev,
+                          double* return_dev, double* step_reward_dev, double* dfo_dev, int write_state, void* stream);
 
 /* Episode statistics for the cross-GPU all-reduce: stats_dev[0..2] = {n, sum, sum of squares} of the
  * per-env total return, then per agent {sum, sum of squares} (MAIM kinds).  Deterministic order. */
@@ -231,8 +252,8 @@ int imx_cc_observe(imx_env* env, const void* obs_dev, const double* actions_dev,
 /* End-to-end convenience calls on HOST buffers (pinned memory recommended): copy in, launch, copy
  * out, synchronise.  These are what a per-step Python caller pays for. */
 int imx_reset_host(imx_env* env, const int32_t* demand_host, const uint8_t* delay_mask_host, int noisy,
-                   uint64_t episode, double* obs_host);
-int imx_step_host(imx_env* env, const double* actions_host, double* obs_host, double* reward_host);
+                   uint64_t episode, void* obs_host);
+int imx_step_host(imx_env* env, const double* actions_host, void* obs_host, double* reward_host);
 
 /* Poisson CDF table the Philox demand generator inverts (cdf[k] = P(X <= k), last entry a
  * sentinel > 1).  Returns the table length; copies min(len, cap) entries when out != NULL. */

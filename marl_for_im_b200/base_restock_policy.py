@@ -27,16 +27,18 @@ def base_stock_policy(policy, env):
 
 
 def dfo_func(policy, env, demand=None, *args):
-    """Negative pmf-weighted mean reward of one base-stock episode.  One kernel launch: the 30-step
-    ``while not done`` loop of the reference runs inside imx_rollout_basestock with state on chip.
-    Drop-in env → float; batched env → [N] tensor (one objective value per env / demand trace)."""
+    """Negative pmf-weighted mean reward of one base-stock episode (base_restock_policy.py:24-45).  One kernel launch:
+    the ``while not done`` loop of the reference runs inside imx_rollout_basestock with state on chip, a second small
+    kernel forms ``-1 / T * np.sum(prob * rewards)`` in numpy's summation order.  Serial envs take a ``[T]`` trace,
+    divergent envs ``[R, T]`` (inv_management_div.py:228: ``demand=test_demand[0, :]``) — ``prob`` then broadcasts against
+    the per-period rewards exactly as in the reference.  A sticky ``noisy_delay`` (MAIM_env.py:192-194) carries into the
+    rollout like it does into the reference's ``env.reset(customer_demand=demand)``.
+    Drop-in env -> float; batched env -> [N] tensor (one objective value per env / demand trace)."""
     if demand is None:
         env.reset()                       # same side effect as the reference: draws a fresh trace
         demand = env.customer_demand if env.customer_demand is not None else env.customer_demand_device().permute(2, 1, 0)
     d_host = demand.cpu().numpy() if isinstance(demand, torch.Tensor) else np.asarray(demand)
     prob = env.dist.pmf(d_host, **env.dist_param)
-    if prob.ndim > 1 and getattr(env, "DIV", False):
-        raise NotImplementedError("dfo_func is defined for the serial envs (one demand trace per episode)")
     out = env.rollout_basestock(np.asarray(policy, dtype=np.float64), customer_demand=demand, pmf=prob)
     if not env.batched:
         env.customer_demand = demand
@@ -64,7 +66,7 @@ def optimize_inventory_policy(env, fun, init_policy=None, method="Powell", deman
 def dfo_func_batch(policies, env, demands):
     """Objective of ``dfo_func`` for every (candidate, trace) pair in ONE rollout launch.
 
-    policies [K, m] base-stock levels, demands [D, T] integer traces (serial envs); ``env`` must be a
+    policies [K, m] base-stock levels, demands [D, T] (serial envs) or [D, R, T] (divergent envs) integer traces; ``env`` must be a
     batched env with ``num_envs == K * D``.  Returns a [K, D] float64 tensor whose entry (k, d) equals
     ``dfo_func(policies[k], env1, demands[d])`` of a single-env instance bit for bit."""
     policies = np.asarray(policies, dtype=np.float64)
@@ -72,10 +74,11 @@ def dfo_func_batch(policies, env, demands):
     K, D = policies.shape[0], demands.shape[0]
     if env.num_envs != K * D:
         raise ValueError(f"env.num_envs = {env.num_envs}, need K * D = {K * D}")
-    prob = env.dist.pmf(demands, **env.dist_param)                      # [D, T]
+    prob = env.dist.pmf(demands, **env.dist_param)                      # [D, T] or [D, R, T]
     z = np.repeat(policies, D, axis=0)                                   # env index = k * D + d
-    dem = np.tile(demands, (K, 1))
-    pmf = np.tile(prob, (K, 1))
+    reps = (K,) + (1,) * (demands.ndim - 1)
+    dem = np.tile(demands, reps)
+    pmf = np.tile(prob, reps)
     out = env.rollout_basestock(z, customer_demand=dem, pmf=pmf)
     return out["dfo"].reshape(K, D)
 

@@ -13,6 +13,9 @@
 #include "imx_reset.cuh"
 #include "imx_step_tma.cuh"
 #include "imx_rollout.cuh"
+#include "imx_step_pipe.cuh"
+#include "imx_kernels.cuh"
+#include "imx_stats.cuh"
 #include "imx_jit.cuh"
 #include "imx_cc.cuh"
 #include "imx_eval.cuh"
@@ -52,10 +55,7 @@ extern "C" int64_t imx_launch_count(void) { return g_launches.load(); }
 // --------------------------------------------------------------------------------------
 // handle
 // --------------------------------------------------------------------------------------
-typedef void (*step_fn_t)(const StepArgs);
-typedef void (*tma_fn_t)(const StepArgs, const TileLayout);
 typedef void (*reset_fn_t)(const StepArgs, const ResetArgs, int);
-typedef void (*rollout_fn_t)(const StepArgs, const RolloutArgs);
 
 struct imx_env {
     imx_config cfg;
@@ -82,6 +82,7 @@ struct imx_env {
     int cdf_len = 0;
     double* d_stats_partial = nullptr;   // [max(2 + 2m, 2(4 + m))][STATS_BLOCKS] scratch of imx_return_stats / imx_eval_stats
     double* d_returns = nullptr;         // [N][cols] scratch of imx_episode_stats
+    double* d_dfo_rewards = nullptr;     // [T][N] scratch of the dfo objective (allocated on first use / imx_prepare)
     double* d_tab = nullptr;             // [m][4][TL] rescale tables
     int TL = 0;
     // host-call staging (allocated on first use)
@@ -119,29 +120,34 @@ struct imx_env {
 };
 
 // --------------------------------------------------------------------------------------
-// kernel dispatch tables
+// kernel dispatch tables: the template instantiations live in imx_kernels_inst.cu, one object per
+// (tile width, network family), compiled in parallel by the build
 // --------------------------------------------------------------------------------------
-template <int M_PAD, bool DIV>
-static void pick_kernels(imx_env* e) {
+#define IMX_DECL_PICK(MP, DV) void imx_pick_kernels_##MP##_##DV(bool small, bool few, imx::KernelSet* ks);
+IMX_DECL_PICK(2, 0) IMX_DECL_PICK(4, 0) IMX_DECL_PICK(8, 0) IMX_DECL_PICK(16, 0) IMX_DECL_PICK(32, 0)
+IMX_DECL_PICK(4, 1) IMX_DECL_PICK(8, 1) IMX_DECL_PICK(16, 1) IMX_DECL_PICK(32, 1)
+#undef IMX_DECL_PICK
+
+static int m_pad_of(const imx_env* e);
+static void pick_kernels(imx_env* e, int m_pad, bool div) {
     const bool small = (e->D <= 4 && e->P <= 1);
-    if constexpr (DIV) {
-        const bool few = e->maxc <= 2;
-        if (small && few) { e->tma_fn = step_kernel_tma<M_PAD, 4, 1, 2, true>; e->tma_many_fn = step_kernel_tma_many<M_PAD, 4, 1, 2, true>; }
-        else if (small)   { e->tma_fn = step_kernel_tma<M_PAD, 4, 1, 8, true>; e->tma_many_fn = step_kernel_tma_many<M_PAD, 4, 1, 8, true>; }
-        else if (few)     { e->tma_fn = step_kernel_tma<M_PAD, 8, 8, 2, true>; e->tma_many_fn = step_kernel_tma_many<M_PAD, 8, 8, 2, true>; }
-        else              { e->tma_fn = step_kernel_tma<M_PAD, 8, 8, 8, true>; e->tma_many_fn = step_kernel_tma_many<M_PAD, 8, 8, 8, true>; }
-        if (small && few) { e->step_fn = step_kernel<M_PAD, 4, 1, 2, true>; e->rollout_fn = rollout_kernel<M_PAD, 4, 2, true>; }
-        else if (small)   { e->step_fn = step_kernel<M_PAD, 4, 1, 8, true>; e->rollout_fn = rollout_kernel<M_PAD, 4, 8, true>; }
-        else if (few)     { e->step_fn = step_kernel<M_PAD, 8, 8, 2, true>; e->rollout_fn = rollout_kernel<M_PAD, 8, 2, true>; }
-        else              { e->step_fn = step_kernel<M_PAD, 8, 8, 8, true>; e->rollout_fn = rollout_kernel<M_PAD, 8, 8, true>; }
+    const bool few = e->maxc <= 2;
+    KernelSet ks;
+    if (div) {
+        if (m_pad == 4) imx_pick_kernels_4_1(small, few, &ks);
+        else if (m_pad == 8) imx_pick_kernels_8_1(small, few, &ks);
+        else if (m_pad == 16) imx_pick_kernels_16_1(small, few, &ks);
+        else imx_pick_kernels_32_1(small, few, &ks);
     } else {
-        e->tma_fn = small ? step_kernel_tma<M_PAD, 4, 1, 1, false> : step_kernel_tma<M_PAD, 8, 8, 1, false>;
-        e->tma_many_fn = small ? step_kernel_tma_many<M_PAD, 4, 1, 1, false> : step_kernel_tma_many<M_PAD, 8, 8, 1, false>;
-        if (small) { e->step_fn = step_kernel<M_PAD, 4, 1, 1, false>; e->rollout_fn = rollout_kernel<M_PAD, 4, 1, false>; }
-        else       { e->step_fn = step_kernel<M_PAD, 8, 8, 1, false>; e->rollout_fn = rollout_kernel<M_PAD, 8, 1, false>; }
+        if (m_pad == 2) imx_pick_kernels_2_0(small, few, &ks);
+        else if (m_pad == 4) imx_pick_kernels_4_0(small, few, &ks);
+        else if (m_pad == 8) imx_pick_kernels_8_0(small, few, &ks);
+        else if (m_pad == 16) imx_pick_kernels_16_0(small, few, &ks);
+        else imx_pick_kernels_32_0(small, few, &ks);
     }
+    e->step_fn = ks.step_fn; e->tma_fn = ks.tma_fn; e->tma_many_fn = ks.tma_many_fn; e->rollout_fn = ks.rollout_fn;
     e->reset_fn = small ? reset_kernel<4, 1> : reset_kernel<8, 8>;
-    e->m_pad = M_PAD;
+    e->m_pad = m_pad;
 }
 
 // The dynamic-shared-memory limit is an attribute of the FUNCTION, shared by every handle that uses the same
@@ -152,6 +158,17 @@ static cudaError_t raise_dyn_smem_limit(const void* fn, size_t bytes) {
     if (rc != cudaSuccess) return rc;
     if ((size_t)fa.maxDynamicSharedSizeBytes >= bytes) return cudaSuccess;
     return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static int m_pad_of(const imx_env* e);
+// CTA size of the TMA kernel.  128-thread CTAs de-synchronise the load / compute / store phases of neighbouring tiles and
+// measured faster on every shipped config (profiles/r1_other_configs_1gpu.jsonl) except the 4-wide chain at
+// multi-million-env batches, where the 256-thread tile is 2.5% ahead; 512-thread CTAs lose 25%
+static int choose_tma_threads(const imx_env* e) {
+    const char* tt = getenv("IMX_TMA_THREADS");
+    const int dflt = (m_pad_of(e) <= 4 && e->N >= ((int64_t)1 << 20)) ? 256 : 128;
+    const int v = tt ? atoi(tt) : dflt;
+    return ((v == 64 || v == 128 || v == 256 || v == 512) && v >= 2 * m_pad_of(e)) ? v : 256;
 }
 
 static int m_pad_of(const imx_env* e) {
@@ -188,8 +205,8 @@ static void compute_tile(const imx_env* e, TileLayout& L, int tile_width) {
 }
 
 // -D options and template instantiations of the runtime-specialised build (imx_jit.cuh)
-static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, std::string& step_name, std::string& many_name,
-                     std::string& rollout_name, int has_obs = 1) {
+static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1) {
+    std::vector<std::string>& defs = sp.defines;
     const imx_config& c = e->cfg;
     const bool always_std = (c.kind == IMX_KIND_MAIM_DIV);
     const int std_state = always_std ? 1 : (c.standardise_state != 0);
@@ -231,62 +248,71 @@ static void jit_spec(const imx_env* e, int TL, std::vector<std::string>& defs, s
         if (maxnreg > 0) defs.push_back("IMX_MANY_MAXNREG=" + std::to_string(maxnreg));
     }
     defs.push_back("IMX_TMA_THREADS=" + std::to_string(e->tma_threads));
+    // the device translation unit checks its view of the argument blocks against this host build (imx_jit.cuh)
+    defs.push_back("IMX_HOST_SIZEOF_STEPARGS=" + std::to_string(sizeof(StepArgs)));
+    defs.push_back("IMX_HOST_SIZEOF_TILELAYOUT=" + std::to_string(sizeof(TileLayout)));
+    defs.push_back("IMX_HOST_SIZEOF_ROLLOUTARGS=" + std::to_string(sizeof(RolloutArgs)));
     const int mp = e->step_dense ? e->m : m_pad_of(e);     // step kernel: power-of-two tile width (see select_kernels)
     const int pmax = (e->need_hd || e->need_ho) ? e->P : 1;
     const int maxc = e->maxc > 1 ? e->maxc : 1;
     const std::string dv = e->div ? "true" : "false";
-    step_name = "imx::step_kernel_tma<" + std::to_string(mp) + ", " + std::to_string(e->D) + ", " + std::to_string(pmax) + ", " +
-                std::to_string(e->div ? maxc : 1) + ", " + dv + ">";
-    many_name = "imx::step_kernel_tma_many" + step_name.substr(strlen("imx::step_kernel_tma"));
-    rollout_name = "imx::rollout_kernel<" + std::to_string(e->m) + ", " + std::to_string(e->D) + ", " + std::to_string(e->div ? maxc : 1) +
-                   ", " + dv + ">";
+    const std::string targs = "<" + std::to_string(mp) + ", " + std::to_string(e->D) + ", " + std::to_string(pmax) + ", " +
+                              std::to_string(e->div ? maxc : 1) + ", " + dv + ">";
+    sp.name[0] = "imx::step_kernel_tma" + targs;
+    sp.name[1] = "imx::step_kernel_tma_many" + targs;
+    sp.name[2] = "imx::rollout_kernel<" + std::to_string(e->m) + ", " + std::to_string(e->D) + ", " + std::to_string(e->div ? maxc : 1) +
+                 ", " + dv + ">";
+    sp.name[3] = "";
 }
 
-// Loads the specialised kernels for this handle on first use (large batches, or IMX_JIT=1).
+static void jit_smem(const imx_env* e, int smem[imxjit::N_KERNELS]) {
+    smem[0] = e->tile_jit.total;
+    smem[1] = e->tile_jit.total2 <= 200 * 1024 ? e->tile_jit.total2 : e->tile_jit.total;
+    smem[2] = 0;
+    smem[3] = 0;
+}
+
+// Loads the specialised kernels for this handle (large batches, or IMX_JIT=1).  Called from imx_create() /
+// imx_prepare(); a later call only happens for handles whose policy changed, and never under stream capture.
 static void ensure_jit(imx_env* e) {
     if (e->jit_state != 0) return;
     e->jit_state = -1;
     if (e->jit_policy < 0 || !e->tma_fn) return;
     if (e->jit_policy == 0 && e->N < 1024) return;        // below ~1k envs a step is launch latency either way; the compile (1-2 s) is not worth it
-    std::vector<std::string> defs;
-    std::string sn, rn;
-    std::string mn;
-    jit_spec(e, e->TL, defs, sn, mn, rn);
     if (e->tile_jit.total > 200 * 1024) return;
-    e->jit = imxjit::get(defs, sn, mn, rn, e->tile_jit.total, e->tile_jit.total2 <= 200 * 1024 ? e->tile_jit.total2 : e->tile_jit.total,
-                         e->cfg.device);
+    imxjit::Spec sp;
+    jit_spec(e, e->TL, sp);
+    int smem[imxjit::N_KERNELS];
+    jit_smem(e, smem);
+    e->jit = imxjit::get(sp, smem, e->cfg.device);
     if (e->jit) e->jit_state = 1;
 }
 
 // The same kernels specialised WITHOUT an observation output (step / step_many with obs = NULL: scoring a stored plan
-// needs rewards only — the observation build and 60 % of the bytes fold away).  Compiled on first use.
+// needs rewards only — the observation build and 60 % of the bytes fold away).  Compiled by imx_prepare(IMX_PREPARE_NOOBS)
+// or on first use outside stream capture.
 static void ensure_jit_noobs(imx_env* e) {
     if (e->jit_noobs_state != 0) return;
     e->jit_noobs_state = -1;
     ensure_jit(e);
     if (e->jit_state != 1) return;
-    std::vector<std::string> defs;
-    std::string sn, rn, mn;
-    jit_spec(e, e->TL, defs, sn, mn, rn, 0);
-    e->jit_noobs = imxjit::get(defs, sn, mn, rn, e->tile_jit.total, e->tile_jit.total2 <= 200 * 1024 ? e->tile_jit.total2 : e->tile_jit.total,
-                               e->cfg.device);
+    imxjit::Spec sp;
+    jit_spec(e, e->TL, sp, 0);
+    int smem[imxjit::N_KERNELS];
+    jit_smem(e, smem);
+    e->jit_noobs = imxjit::get(sp, smem, e->cfg.device);
     if (e->jit_noobs) e->jit_noobs_state = 1;
+}
+
+static bool stream_is_capturing(cudaStream_t s) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+    return st != cudaStreamCaptureStatusNone;
 }
 
 static int select_kernels(imx_env* e) {
     const int m = e->m;
-    if (e->div) {
-        if (m <= 4) pick_kernels<4, true>(e);
-        else if (m <= 8) pick_kernels<8, true>(e);
-        else if (m <= 16) pick_kernels<16, true>(e);
-        else pick_kernels<32, true>(e);
-    } else {
-        if (m <= 2) pick_kernels<2, false>(e);
-        else if (m <= 4) pick_kernels<4, false>(e);
-        else if (m <= 8) pick_kernels<8, false>(e);
-        else if (m <= 16) pick_kernels<16, false>(e);
-        else pick_kernels<32, false>(e);
-    }
+    pick_kernels(e, m_pad_of(e), e->div);
     const int epw = 32 / e->m_pad;
     const int tile_bytes = (epw * m * e->O * (e->cfg.obs_f32 ? 4 : 8) + 15) & ~15;
     e->step_smem = (size_t)(STEP_THREADS / 32) * tile_bytes;
@@ -297,13 +323,7 @@ static int select_kernels(imx_env* e) {
     if (occ < 1) return fail(-4, "step kernel does not fit on an SM (smem %zu B)", e->step_smem);
     e->step_grid_cap = dev_sms * occ;
     {
-        const char* tt = getenv("IMX_TMA_THREADS");
-        // 128-thread CTAs de-synchronise the load / compute / store phases of neighbouring tiles and measured
-        // faster on every shipped config (profiles/r1_other_configs_1gpu.jsonl) except the 4-wide chain at
-        // multi-million-env batches, where the 256-thread tile is 2.5% ahead; 512-thread CTAs lose 25%
-        const int dflt = (m_pad_of(e) <= 4 && e->N >= ((int64_t)1 << 20)) ? 256 : 128;
-        const int v = tt ? atoi(tt) : dflt;
-        e->tma_threads = (v == 64 || v == 128 || v == 256 || v == 512) && v >= 2 * m_pad_of(e) ? v : 256;
+        e->tma_threads = choose_tma_threads(e);
         const char* dn = getenv("IMX_STEP_DENSE");
         e->step_dense = (dn && !strcmp(dn, "1")) ? 1 : 0;
     }
@@ -649,6 +669,7 @@ extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
         IMX_CREATE_CUDA(cudaDeviceSynchronize());
     }
 #undef IMX_CREATE_CUDA
+    ensure_jit(e);            // compile / load the specialised kernels now: no later call compiles on the step path
     *out = e;
     return 0;
 }
@@ -659,6 +680,7 @@ extern "C" int imx_destroy(imx_env* e) {
     if (e->hstream) { cudaStreamSynchronize(e->hstream); cudaStreamDestroy(e->hstream); }
     cudaFree(e->d_nodes); cudaFree(e->d_state); cudaFree(e->d_err);
     cudaFree(e->d_demand_T); cudaFree(e->d_mask_T); cudaFree(e->d_cdf); cudaFree(e->d_guide); cudaFree(e->d_tab); cudaFree(e->d_stats_partial); cudaFree(e->d_returns);
+    cudaFree(e->d_dfo_rewards);
     cudaFree(e->d_act_h); cudaFree(e->d_obs_h); cudaFree(e->d_rew_h); cudaFree(e->d_dem_h); cudaFree(e->d_mask_h);
     delete e;
     return 0;
@@ -733,7 +755,7 @@ static DemandGen make_gen(const imx_env* e, uint64_t episode) {
 }
 
 extern "C" int imx_reset(imx_env* e, const int32_t* demand_dev, const uint8_t* delay_mask_dev, int noisy,
-                         uint64_t episode, double* obs_dev, void* stream) {
+                         uint64_t episode, void* obs_dev, void* stream) {
     if (!e) return fail(-1, "null env");
     cudaStream_t s = (cudaStream_t)stream;
     IMX_CUDA(cudaSetDevice(e->cfg.device));
@@ -764,7 +786,7 @@ extern "C" int imx_reset(imx_env* e, const int32_t* demand_dev, const uint8_t* d
     }
     e->t = 0;
     e->episode = episode;
-    launch_reset_kernel(e, obs_dev, s);
+    launch_reset_kernel(e, (double*)obs_dev, s);
     IMX_CHECK_LAUNCH("reset_kernel");
     return 0;
 }
@@ -797,8 +819,14 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
     bool use_jit = false;
     const imxjit::Kernels* jk = nullptr;
     if (tma_legal && !A.has_info && !A.noisy) {
-        if (obs_dev) { ensure_jit(e); if (e->jit_state == 1) jk = e->jit; }
-        else { ensure_jit_noobs(e); if (e->jit_noobs_state == 1) jk = e->jit_noobs; }
+        // the specialised kernels were loaded by imx_create() / imx_prepare(); the obs-less variant may still be
+        // compiled here on first use, but never while the stream is being captured (module loads are not capturable)
+        if (obs_dev) { if (e->jit_state == 1) jk = e->jit; }
+        else {
+            if (e->jit_noobs_state == 0 && !stream_is_capturing(s)) ensure_jit_noobs(e);
+            if (e->jit_noobs_state == 1) jk = e->jit_noobs;
+            else if (e->jit_state == 1 && e->jit_noobs_state == 0) jk = nullptr;   // capture in progress: ahead-of-time kernel
+        }
         use_jit = jk != nullptr;
     }
     const TileLayout& TL_use = use_jit ? e->tile_jit : e->tile;
@@ -861,11 +889,26 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
     return 0;
 }
 
-extern "C" int imx_step(imx_env* e, const double* actions_dev, double* obs_dev, double* reward_dev,
+extern "C" int imx_step(imx_env* e, const double* actions_dev, void* obs_dev, double* reward_dev,
                         const imx_info_out* info, void* stream) {
     if (!e || !actions_dev || !reward_dev) return fail(-1, "null argument");
     IMX_CUDA(cudaSetDevice(e->cfg.device));
-    return launch_step(e, actions_dev, obs_dev, reward_dev, info, (cudaStream_t)stream);
+    return launch_step(e, actions_dev, (double*)obs_dev, reward_dev, info, (cudaStream_t)stream);
+}
+
+static int ensure_host_path(imx_env* e);
+
+extern "C" int imx_prepare(imx_env* e, int flags) {
+    if (!e) return fail(-1, "null env");
+    IMX_CUDA(cudaSetDevice(e->cfg.device));
+    if (flags == 0) flags = IMX_PREPARE_STEP | IMX_PREPARE_NOOBS | IMX_PREPARE_HOST | IMX_PREPARE_DFO;
+    if (flags & IMX_PREPARE_STEP) ensure_jit(e);
+    if (flags & IMX_PREPARE_NOOBS) ensure_jit_noobs(e);
+    if (flags & IMX_PREPARE_HOST) { const int rc = ensure_host_path(e); if (rc) return rc; }
+    if ((flags & IMX_PREPARE_DFO) && !e->multi && !e->d_dfo_rewards)
+        IMX_CUDA(cudaMalloc(&e->d_dfo_rewards, (size_t)e->T * e->N * sizeof(double)));
+    IMX_CUDA(cudaDeviceSynchronize());
+    return 0;
 }
 
 // K consecutive periods on pre-computed actions: one launch that keeps every tile's state in shared memory for all K
@@ -904,23 +947,31 @@ extern "C" int imx_step_many(imx_env* e, const double* actions_dev, int K, void*
 // fused base-stock rollout
 // --------------------------------------------------------------------------------------
 extern "C" int imx_rollout_basestock(imx_env* e, const double* z_dev, int z_stride, const int32_t* demand_dev,
-                                     uint64_t episode, const double* pmf_dev, double* return_dev,
-                                     double* step_reward_dev, double* dfo_dev, int write_state, void* stream) {
+                                     const uint8_t* delay_mask_dev, int noisy, uint64_t episode, const double* pmf_dev,
+                                     double* return_dev, double* step_reward_dev, double* dfo_dev, int write_state, void* stream) {
     if (!e || !z_dev || !return_dev) return fail(-1, "null argument");
     if (z_stride != 0 && z_stride != e->m) return fail(-1, "z_stride must be 0 or m");
     if (dfo_dev && (!pmf_dev || e->multi)) return fail(-1, "dfo output needs pmf_dev and a single-agent kind");
     if (!demand_dev && e->cfg.demand_dist == IMX_DIST_REPLAY_ONLY)
         return fail(-1, "rollout without a demand trace needs demand_dist poisson or uniform");
-    if (e->has_carry) return fail(-1, "the fused rollout does not model noisy delays; create the env with noisy_delay = 0");
+    if ((noisy || delay_mask_dev) && !e->has_carry) return fail(-1, "noisy delay requested but the env was created with noisy_delay = 0");
     cudaStream_t s = (cudaStream_t)stream;
     IMX_CUDA(cudaSetDevice(e->cfg.device));
+    if (dfo_dev && !step_reward_dev) {                       // the objective is a second kernel over the per-period rewards
+        if (!e->d_dfo_rewards) {
+            if (stream_is_capturing(s)) return fail(-1, "dfo_dev without step_reward_dev under stream capture: call imx_prepare(IMX_PREPARE_DFO) first");
+            IMX_CUDA(cudaMalloc(&e->d_dfo_rewards, (size_t)e->T * e->N * sizeof(double)));
+        }
+        step_reward_dev = e->d_dfo_rewards;
+    }
     StepArgs A;
     fill_args(e, A);
     A.t = 0;
     RolloutArgs Rg;
     memset(&Rg, 0, sizeof(Rg));
-    Rg.z = z_dev; Rg.z_stride = z_stride; Rg.demand = demand_dev; Rg.pmf = pmf_dev;
-    Rg.ret = return_dev; Rg.step_reward = step_reward_dev; Rg.dfo = dfo_dev; Rg.write_state = write_state;
+    Rg.z = z_dev; Rg.z_stride = z_stride; Rg.demand = demand_dev;
+    Rg.ret = return_dev; Rg.step_reward = step_reward_dev; Rg.write_state = write_state;
+    Rg.mask = delay_mask_dev; Rg.noisy = (noisy || delay_mask_dev) ? 1 : 0; Rg.delay_thr = e->cfg.noisy_delay_threshold;
     Rg.gen = make_gen(e, episode);
     const int epw = 32 / e->m_pad;
     // Philox demand is drawn cooperatively by the tile's lanes into shared memory when the episode fits
@@ -931,8 +982,7 @@ extern "C" int imx_rollout_basestock(imx_env* e, const double* z_dev, int z_stri
     const int64_t warp_tiles = (e->N + epw - 1) / epw;
     const int64_t blocks_needed = (warp_tiles + (ROLLOUT_THREADS / 32) - 1) / (ROLLOUT_THREADS / 32);
     const unsigned grid = (unsigned)(blocks_needed < e->rollout_grid_cap ? blocks_needed : e->rollout_grid_cap);
-    ensure_jit(e);
-    if (e->jit_state == 1) {
+    if (e->jit_state == 1 && e->jit->rollout) {
         void* params[] = {(void*)&A, (void*)&Rg};
         const int epw_j = 32 / e->m;                         // dense packing in the specialised build
         const int64_t wt_j = (e->N + epw_j - 1) / epw_j;
@@ -951,7 +1001,11 @@ extern "C" int imx_rollout_basestock(imx_env* e, const double* z_dev, int z_stri
         IMX_CHECK_LAUNCH("rollout_kernel");
         e->last_variant = 0;
     }
-    if (write_state) { e->t = e->T; e->episode = episode; }
+    if (dfo_dev) {
+        dfo_objective_kernel<<<(unsigned)((e->N + 127) / 128), 128, 0, s>>>(pmf_dev, step_reward_dev, dfo_dev, e->N, e->R, e->T);
+        IMX_CHECK_LAUNCH("dfo_objective_kernel");
+    }
+    if (write_state) { e->t = e->T; e->episode = episode; e->noisy_now = Rg.noisy; }
     return 0;
 }
 
@@ -1023,18 +1077,28 @@ extern "C" int imx_eval_stats(imx_env* e, const double* acc_dev, double* stats_d
 // --------------------------------------------------------------------------------------
 static int ensure_host_path(imx_env* e) {
     if (e->hstream) return 0;
-    IMX_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
     const size_t cells = (size_t)e->N * e->m;
-    IMX_CUDA(cudaMalloc(&e->d_act_h, cells * sizeof(double)));
-    IMX_CUDA(cudaMalloc(&e->d_obs_h, cells * e->O * (e->cfg.obs_f32 ? 4 : 8)));
-    IMX_CUDA(cudaMalloc(&e->d_rew_h, cells * sizeof(double)));
-    IMX_CUDA(cudaMalloc(&e->d_dem_h, (size_t)e->N * e->R * e->T * sizeof(int32_t)));
-    if (e->has_carry) IMX_CUDA(cudaMalloc(&e->d_mask_h, (size_t)e->N * e->T * e->m));
+    // the stream handle marks the path as ready, so it is published last: a failed allocation leaves nothing half-built
+    cudaError_t rc = cudaSuccess;
+    auto take = [&](void** p, size_t bytes) { if (rc == cudaSuccess && !*p) rc = cudaMalloc(p, bytes); };
+    take((void**)&e->d_act_h, cells * sizeof(double));
+    take((void**)&e->d_obs_h, cells * e->O * (e->cfg.obs_f32 ? 4 : 8));
+    take((void**)&e->d_rew_h, cells * sizeof(double));
+    take((void**)&e->d_dem_h, (size_t)e->N * e->R * e->T * sizeof(int32_t));
+    if (e->has_carry) take((void**)&e->d_mask_h, (size_t)e->N * e->T * e->m);
+    cudaStream_t hs = nullptr;
+    if (rc == cudaSuccess) rc = cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking);
+    if (rc != cudaSuccess) {
+        cudaFree(e->d_act_h); cudaFree(e->d_obs_h); cudaFree(e->d_rew_h); cudaFree(e->d_dem_h); cudaFree(e->d_mask_h);
+        e->d_act_h = e->d_obs_h = e->d_rew_h = nullptr; e->d_dem_h = nullptr; e->d_mask_h = nullptr;
+        return fail(-2, "host-path staging allocation failed: %s", cudaGetErrorString(rc));
+    }
+    e->hstream = hs;
     return 0;
 }
 
 extern "C" int imx_reset_host(imx_env* e, const int32_t* demand_host, const uint8_t* delay_mask_host, int noisy,
-                              uint64_t episode, double* obs_host) {
+                              uint64_t episode, void* obs_host) {
     if (!e) return fail(-1, "null env");
     IMX_CUDA(cudaSetDevice(e->cfg.device));
     int rc = ensure_host_path(e);
@@ -1064,7 +1128,7 @@ static void* pinned_alias(const void* host_ptr) {
     return at.devicePointer;
 }
 
-extern "C" int imx_step_host(imx_env* e, const double* actions_host, double* obs_host, double* reward_host) {
+extern "C" int imx_step_host(imx_env* e, const double* actions_host, void* obs_host, double* reward_host) {
     if (!e || !actions_host || !reward_host) return fail(-1, "null argument");
     IMX_CUDA(cudaSetDevice(e->cfg.device));
     int rc = ensure_host_path(e);
@@ -1119,16 +1183,16 @@ extern "C" int imx_jit_compile_check(const imx_config* cfg, char* log, int cap) 
     tmp.cfg = *cfg;
     const int rc = derive(&tmp);
     if (rc) return rc;
+    tmp.tma_threads = choose_tma_threads(&tmp);
     compute_tile(&tmp, tmp.tile, m_pad_of(&tmp));
     compute_tile(&tmp, tmp.tile_jit, m_pad_of(&tmp));
     int TL = 0;
     build_tables(&tmp, &TL);
-    std::vector<std::string> defs;
-    std::string sn, rn, lg;
-    std::string mn;
-    jit_spec(&tmp, TL, defs, sn, mn, rn);
+    imxjit::Spec sp;
+    jit_spec(&tmp, TL, sp);
+    std::string lg;
     std::vector<char> cubin;
-    const size_t n = imxjit::compile_only(defs, sn, mn, rn, lg, &cubin);
+    const size_t n = imxjit::compile_only(sp, lg, &cubin);
     if (n > 0 && getenv("IMX_JIT_DUMP")) {              // for cuobjdump -sass inspection
         FILE* f = fopen(getenv("IMX_JIT_DUMP"), "wb");
         if (f) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }

@@ -19,10 +19,12 @@ struct RolloutArgs {
     const int32_t* __restrict__ demand;    // replayed [N][R][T] or nullptr → Philox
     int32_t coop_demand;                   // Philox draws are produced cooperatively by the tile's lanes into shared memory
     int32_t pad_r;
-    const double* __restrict__ pmf;        // [N][T] or nullptr
     double* __restrict__ ret;              // [N] (IM kinds) / [N][m] (MAIM kinds)
-    double* __restrict__ step_reward;      // [T][N] / [T][N][m] or nullptr
-    double* __restrict__ dfo;              // [N] or nullptr
+    double* __restrict__ step_reward;      // [T][N] / [T][N][m] or nullptr (the dfo objective is a second kernel over this array)
+    const uint8_t* __restrict__ mask;      // replayed noisy-delay outcomes [N][T][m] or nullptr -> Philox (same draws as imx_reset)
+    int32_t noisy;                         // this episode runs with noisy delays (handles created with noisy_delay = 1 only)
+    int32_t pad_n;
+    double delay_thr;                      // Philox mask: P(delay) per eligible (stage, period)
     DemandGen gen;
 };
 
@@ -57,8 +59,6 @@ __global__ void IMX_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ StepAr
     const bool is_last = (i == m - 1);
     const int delay_m1 = np.delay - 1;
     const double om_d = (double)np.order_max;
-    const int full8 = T - (T % 8);
-    const double neg_inv_T = -1.0 / (double)T;        // "-1 / env.num_periods" (base_restock_policy.py:45)
 
     const int64_t warps_in_grid = (int64_t)gridDim.x * (ROLLOUT_THREADS / 32);
     const int64_t n_warp_tiles = (A.N + EPW - 1) / EPW;
@@ -68,7 +68,7 @@ __global__ void IMX_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ StepAr
         const int64_t cell = n * m + i;
 
         // reset state (MAIM_env.py:232-235): inv = init_inv, everything else 0
-        int inv = np.init_inv, backlog = 0, order_u = 0;
+        int inv = np.init_inv, backlog = 0, order_u = 0, carry = 0;
         int pipe[DMAX];
         int bt[MAXC];
 #pragma unroll
@@ -93,10 +93,6 @@ __global__ void IMX_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ StepAr
             __syncwarp();
         }
         double ret = 0.0;                 // "dfo_reward = 0; dfo_reward += r" (inv_management.py:223-231)
-        double acc8[8];                   // np.sum(prob * rewards) accumulators (numpy pairwise order)
-        double dfo_sum = 0.0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc8[j] = 0.0;
         int err_code = 0;
 
         for (int t = 0; t < T; ++t) {
@@ -130,7 +126,19 @@ __global__ void IMX_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ StepAr
                 demand = (i == 0) ? min(cust, np.inv_max) : down;
             }
 
-            const int acq = (t >= np.delay) ? pipe[0] : 0;
+            // update_acquisition (MAIM_env.py:438-476): head of the lead-time register, plus what a noisy delay held back
+            int acq = (t >= np.delay) ? pipe[0] : 0;
+            if (KF(has_carry)) {
+                if (Rg.noisy) {                              // sticky noisy_delay (MAIM_env.py:192-194): dfo_func after a noisy reset
+                    acq += carry;
+                    carry = 0;
+                    if (ok && t >= np.delay && t < T - 1) {
+                        const bool delayed = Rg.mask ? (Rg.mask[(n * T + t) * m + i] != 0)
+                                                     : draw_delay(Rg.gen.seed, Rg.gen.env_offset + n, i, t, Rg.gen.episode, Rg.delay_thr);
+                        if (delayed) { carry = acq; acq = 0; }
+                    }
+                }
+            }
             const int ship = min(backlog + demand, inv + acq);
             int incoming;
             if constexpr (DIV) {
@@ -186,30 +194,12 @@ __global__ void IMX_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ StepAr
                 if (KF(multi)) Rg.step_reward[(int64_t)t * A.N * m + cell] = r;
                 else if (i == 0) Rg.step_reward[(int64_t)t * A.N + n] = r;
             }
-            if (Rg.dfo && ok && i == 0) {
-                const double v = __dmul_rn(Rg.pmf[n * T + t], r);
-                if (T < 8) dfo_sum = __dadd_rn(dfo_sum, v);
-                else if (t < 8) acc8[t] = v;
-                else if (t < full8) acc8[t & 7] = __dadd_rn(acc8[t & 7], v);
-                else {
-                    if (t == full8)
-                        dfo_sum = __dadd_rn(__dadd_rn(__dadd_rn(acc8[0], acc8[1]), __dadd_rn(acc8[2], acc8[3])),
-                                            __dadd_rn(__dadd_rn(acc8[4], acc8[5]), __dadd_rn(acc8[6], acc8[7])));
-                    dfo_sum = __dadd_rn(dfo_sum, v);
-                }
-            }
         }
         __syncwarp();                                    // the next episode's period 0 reuses a profit buffer (odd T: the last one read)
 
         if (ok) {
             if (KF(multi)) Rg.ret[cell] = ret;
             else if (i == 0) Rg.ret[n] = ret;
-            if (Rg.dfo && i == 0) {
-                if (T >= 8 && full8 == T)
-                    dfo_sum = __dadd_rn(__dadd_rn(__dadd_rn(acc8[0], acc8[1]), __dadd_rn(acc8[2], acc8[3])),
-                                        __dadd_rn(__dadd_rn(acc8[4], acc8[5]), __dadd_rn(acc8[6], acc8[7])));
-                Rg.dfo[n] = __dmul_rn(neg_inv_T, dfo_sum);
-            }
             if (Rg.write_state) {
                 A.inv[cell] = inv;
                 A.backlog[cell] = backlog;
@@ -218,6 +208,7 @@ __global__ void IMX_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ StepAr
 #pragma unroll
                 for (int k = 0; k < DMAX; ++k)
                     if (k < np.delay) pp[k] = pipe[k];
+                if (KF(has_carry)) A.carry[cell] = carry;
                 if constexpr (DIV) {
                     if (np.bt_off >= 0) {
 #pragma unroll
@@ -231,72 +222,6 @@ __global__ void IMX_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ StepAr
             }
         }
     }
-}
-
-// Episode statistics [n, Σ total, Σ total², then per agent (Σ, Σ²)] in a fixed, deterministic
-// order (the payload of the single cross-GPU all-reduce).  Two stages: STATS_BLOCKS x nstat blocks
-// each reduce one statistic over a fixed slice of the envs (strided threads + shared-memory tree),
-// then one block per statistic adds the STATS_BLOCKS partials in index order.  The grid is a
-// constant, so the result depends only on N, never on the device.  The per-env total of a MAIM kind
-// is the sum over agents in agent order.
-constexpr int STATS_BLOCKS = 128;
-constexpr int STATS_THREADS = 256;
-
-__device__ __forceinline__ double stats_value(const double* __restrict__ ret, int64_t n, int cols, int q) {
-    double v;
-    if (q < 2) {
-        v = 0.0;
-        for (int c = 0; c < cols; ++c) v += ret[n * cols + c];
-    } else {
-        v = ret[n * cols + (q - 2) / 2];
-    }
-    return (q & 1) ? v * v : v;
-}
-
-__global__ void __launch_bounds__(STATS_THREADS) return_stats_partial_kernel(const double* __restrict__ ret, double* __restrict__ partial,
-                                                                             int64_t N, int cols) {
-    __shared__ double red[STATS_THREADS];
-    const int q = blockIdx.y;
-    const int64_t per_block = (N + STATS_BLOCKS - 1) / STATS_BLOCKS;
-    const int64_t lo = (int64_t)blockIdx.x * per_block;
-    const int64_t hi = lo + per_block < N ? lo + per_block : N;
-    double acc = 0.0;
-    for (int64_t n = lo + threadIdx.x; n < hi; n += STATS_THREADS) acc += stats_value(ret, n, cols, q);
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = STATS_THREADS / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) partial[q * STATS_BLOCKS + blockIdx.x] = red[0];
-}
-
-// One warp per statistic: fixed-shape tree over the STATS_BLOCKS partials (deterministic).
-// accumulate != 0: stats += result (statistics of an evaluation batch build up on the device).
-__global__ void __launch_bounds__(32) return_stats_final_kernel(const double* __restrict__ partial, double* __restrict__ stats, int64_t N,
-                                                                int nstat, int accumulate) {
-    const int q = blockIdx.x;
-    const int lane = threadIdx.x;
-    double acc = 0.0;
-    for (int b = lane; b < STATS_BLOCKS; b += 32) acc += partial[q * STATS_BLOCKS + b];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-    if (lane == 0) {
-        stats[1 + q] = accumulate ? stats[1 + q] + acc : acc;
-        if (q == 0) stats[0] = accumulate ? stats[0] + (double)N : (double)N;
-    }
-}
-
-// Episode return per (env, agent) = sum over periods of the step rewards, added in period order like
-// the host loops of the reference ("reward += r", inv_management.py:223-231).  One thread per cell;
-// each period is one coalesced row of step_reward [T][cells].
-__global__ void __launch_bounds__(256) episode_return_kernel(const double* __restrict__ step_reward, double* __restrict__ ret, int64_t cells,
-                                                             int T) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cells) return;
-    double acc = 0.0;
-    for (int t = 0; t < T; ++t) acc += step_reward[(int64_t)t * cells + c];
-    ret[c] = acc;
 }
 
 }  // namespace imx

@@ -358,20 +358,9 @@ class _ImxEnvBase:
         mask_dev = None
         if want_noisy:
             if delay_mask is None and not self.batched:
-                # drop-in mode: pre-draw the episode's uniforms on the host stream in the reference's order
-                # (factory first, eligible stages only — MAIM_env.py:447-468 / MAIM_div_env.py:666-687)
-                order = list(range(m)) if self.DIV else [m - 1] + list(range(m - 1))
-                delay_mask = np.zeros((T, m), dtype=bool)
-                for t in range(T):
-                    for i in order:
-                        if t - int(self.delay[i]) >= 0:
-                            delay_mask[t, i] = np.random.uniform(0, 1) <= self.noisy_delay_threshold
+                delay_mask = self._draw_host_delay_mask()
             if delay_mask is not None:
-                mk = torch.as_tensor(np.ascontiguousarray(np.asarray(delay_mask)).astype(np.uint8), device=self.device) \
-                    if not isinstance(delay_mask, torch.Tensor) else delay_mask.to(device=self.device, dtype=torch.uint8)
-                if mk.numel() == T * m:
-                    mk = mk.reshape(1, T, m).expand(N, T, m)
-                mask_dev = mk.reshape(N, T, m).contiguous()
+                mask_dev = self._mask_to_device(delay_mask)
 
         obs_buf = self._new_obs()
         self._episode += 1
@@ -386,6 +375,26 @@ class _ImxEnvBase:
         self.last_obs, self.last_reward = obs_buf, None       # packed [N, m, O] tensor behind the returned views
         self.state = self._shape_obs(obs_buf)
         return self.state
+
+    def _draw_host_delay_mask(self):
+        """Drop-in mode: pre-draw the episode's noisy-delay uniforms on the host stream in the reference's order
+        (factory first, eligible stages only — MAIM_env.py:447-468 / MAIM_div_env.py:666-687)."""
+        m, T = self.num_nodes, self.num_periods
+        order = list(range(m)) if self.DIV else [m - 1] + list(range(m - 1))
+        delay_mask = np.zeros((T, m), dtype=bool)
+        for t in range(T):
+            for i in order:
+                if t - int(self.delay[i]) >= 0:
+                    delay_mask[t, i] = np.random.uniform(0, 1) <= self.noisy_delay_threshold
+        return delay_mask
+
+    def _mask_to_device(self, delay_mask):
+        N, m, T = self.num_envs, self.num_nodes, self.num_periods
+        mk = torch.as_tensor(np.ascontiguousarray(np.asarray(delay_mask)).astype(np.uint8), device=self.device) \
+            if not isinstance(delay_mask, torch.Tensor) else delay_mask.to(device=self.device, dtype=torch.uint8)
+        if mk.numel() == T * m:
+            mk = mk.reshape(1, T, m).expand(N, T, m)
+        return mk.reshape(N, T, m).contiguous()
 
     def delay_mask_device(self):
         """[T, N, m] uint8 view of this episode's noisy-delay outcomes (None without noisy delays)."""
@@ -563,10 +572,6 @@ class _ImxEnvBase:
                                       C.c_void_p(rew_buf.data_ptr()),
                                       C.byref(info_struct) if info_struct is not None else None, self._stream()))
         done_flag = self.period >= self.num_periods
-        if not self.batched:
-            self._record_history(t, info_bufs)
-            if int(self.error_flags[0]) != 0:
-                raise Exception(f"Infinite Loop {int(self.error_flags[0])}")     # MAIM_div_env.py:503-505 etc.
         self.last_obs, self.last_reward = obs_buf, rew_buf    # packed [N, m, O] / [N, m] tensors behind the returned views
         self.state = self._shape_obs(obs_buf)
         return self.state, self._shape_reward(rew_buf), self._shape_done(done_flag), self._shape_info(t, info_bufs)
@@ -648,12 +653,17 @@ class _ImxEnvBase:
         raise NotImplementedError
 
     # ------------------------------------------------------------------ fused base-stock rollout
-    def rollout_basestock(self, z, customer_demand=None, pmf=None, step_rewards=False, write_state=False):
+    def rollout_basestock(self, z, customer_demand=None, pmf=None, step_rewards=False, write_state=False, delay_mask=None,
+                          noisy_delay=None):
         """Whole-episode order-up-to rollout in one kernel (dfo_func's loop, base_restock_policy.py:30-45).
 
         z: [m] or [N, m] base-stock levels.  customer_demand: [N, R, T] / [N, T] / one trace, or None
-        (Philox).  Returns dict(returns=[N] or [N, m], step_rewards=[T, N(, m)] or None, dfo=[N] or None)."""
-        N, m, T = self.num_envs, self.num_nodes, self.num_periods
+        (Philox).  pmf: probabilities of the trace, [N, R, T] / [R, T] / [N, T] / [T].  Noisy delays follow the
+        env's sticky ``noisy_delay`` flag (MAIM_env.py:192-194) unless ``noisy_delay`` is given; ``delay_mask``
+        replays their outcomes ([N, T, m] / [T, m]), otherwise the drop-in draws them from numpy's global stream in
+        the reference's order and a batched env from Philox.
+        Returns dict(returns=[N] or [N, m], step_rewards=[T, N(, m)] or None, dfo=[N] or None)."""
+        N, m, T, R = self.num_envs, self.num_nodes, self.num_periods, len(self._retailers)
         zt = torch.as_tensor(np.asarray(z, dtype=np.float64), device=self.device) if not isinstance(z, torch.Tensor) \
             else z.to(device=self.device, dtype=torch.float64)
         zt = zt.contiguous()
@@ -668,18 +678,28 @@ class _ImxEnvBase:
         if pmf is not None:
             pmf_dev = torch.as_tensor(np.asarray(pmf, dtype=np.float64), device=self.device) if not isinstance(pmf, torch.Tensor) \
                 else pmf.to(device=self.device, dtype=torch.float64)
-            if pmf_dev.numel() == T:
-                pmf_dev = pmf_dev.reshape(1, T).expand(N, T)
-            pmf_dev = pmf_dev.reshape(N, T).contiguous()
+            if pmf_dev.numel() == R * T:
+                pmf_dev = pmf_dev.reshape(1, R, T).expand(N, R, T)
+            pmf_dev = pmf_dev.reshape(N, R, T).contiguous()
+        want_noisy = (bool(self.noisy_delay) if noisy_delay is None else bool(noisy_delay)) or delay_mask is not None
+        mask_dev = None
+        if want_noisy:
+            if not self._has_carry:
+                self._create_handle(True)
+            if delay_mask is None and not self.batched:
+                delay_mask = self._draw_host_delay_mask()
+            if delay_mask is not None:
+                mask_dev = self._mask_to_device(delay_mask)
         ret = torch.empty((N, m) if self.MULTI else (N,), dtype=torch.float64, device=self.device)
-        sr = torch.empty((T, N, m) if self.MULTI else (T, N), dtype=torch.float64, device=self.device) if step_rewards else None
         dfo = torch.empty((N,), dtype=torch.float64, device=self.device) if (pmf_dev is not None and not self.MULTI) else None
+        want_sr = step_rewards or dfo is not None            # the objective kernel reads the per-period rewards
+        sr = torch.empty((T, N, m) if self.MULTI else (T, N), dtype=torch.float64, device=self.device) if want_sr else None
         self._episode += 1
         p = lambda x: C.c_void_p(x.data_ptr()) if x is not None else None   # noqa: E731
-        _lib.check(self._lib.imx_rollout_basestock(self._handle, p(zt), stride, p(demand_dev), self._episode, p(pmf_dev),
-                                                   p(ret), p(sr), p(dfo), int(write_state), self._stream()))
-        self._keepalive = (zt, demand_dev, pmf_dev)
-        return {"returns": ret, "step_rewards": sr, "dfo": dfo}
+        _lib.check(self._lib.imx_rollout_basestock(self._handle, p(zt), stride, p(demand_dev), p(mask_dev), int(want_noisy),
+                                                   self._episode, p(pmf_dev), p(ret), p(sr), p(dfo), int(write_state), self._stream()))
+        self._keepalive = (zt, demand_dev, pmf_dev, mask_dev)
+        return {"returns": ret, "step_rewards": sr if step_rewards else None, "dfo": dfo}
 
     def return_stats(self, returns):
         """[n, Σ, Σ², then per agent (Σ, Σ²)] float64 on the device — the payload of the cross-GPU all-reduce."""

@@ -119,20 +119,21 @@ class COracle:
         out["bad"] = int(bad)
         return out
 
-    def rollout(self, z, demand, pmf=None, step_rewards=False, threads=0):
+    def rollout(self, z, demand, pmf=None, step_rewards=False, threads=0, delay_mask=None):
         lib = load()
         N = demand.shape[0]
         demand = np.ascontiguousarray(demand.reshape(N, self.R, self.T), dtype=np.int32)
         z = np.ascontiguousarray(z, dtype=np.float64)
         stride = 0 if z.size == self.m else self.m
-        pmf = None if pmf is None else np.ascontiguousarray(np.broadcast_to(pmf, (N, self.T)), dtype=np.float64)
+        pmf = None if pmf is None else np.ascontiguousarray(np.broadcast_to(np.asarray(pmf, dtype=np.float64).reshape(-1, self.R, self.T), (N, self.R, self.T)))
+        mask = None if delay_mask is None else np.ascontiguousarray(np.broadcast_to(np.asarray(delay_mask).reshape(-1, self.T, self.m), (N, self.T, self.m)), dtype=np.uint8)
         out = {"returns": np.empty((N, self.cols)), "step_rewards": np.empty((self.T, N, self.cols)) if step_rewards else None,
                "dfo": np.empty(N) if pmf is not None else None,
                "inv": np.empty((N, self.m), dtype=np.int32), "backlog": np.empty((N, self.m), dtype=np.int32),
                "order_u": np.empty((N, self.m), dtype=np.int32), "pipe": np.empty((N, self.L), dtype=np.int32),
                "backlog_to": np.empty((N, max(self.NB, 1)), dtype=np.int32)}
         bad = lib.orc_rollout(C.byref(self.cfg), C.c_long(N), _p(z, C.c_double), C.c_int(stride), _p(demand, C.c_int32),
-                              _p(pmf, C.c_double), _p(out["returns"], C.c_double), _p(out["step_rewards"], C.c_double),
+                              _p(mask, C.c_ubyte), _p(pmf, C.c_double), _p(out["returns"], C.c_double), _p(out["step_rewards"], C.c_double),
                               _p(out["dfo"], C.c_double), _p(out["inv"], C.c_int32), _p(out["backlog"], C.c_int32),
                               _p(out["order_u"], C.c_int32), _p(out["pipe"], C.c_int32), _p(out["backlog_to"], C.c_int32), C.c_int(threads))
         out["bad"] = int(bad)

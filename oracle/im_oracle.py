@@ -46,16 +46,21 @@ class OracleWatchdog(Exception):
 # small helpers
 # --------------------------------------------------------------------------------------
 def np_sum_order(vals: Sequence[float]) -> float:
-    """Summation order of ``np.sum`` on a contiguous float64 vector (numpy's pairwise_sum:
-    sequential for n < 8, eight running accumulators otherwise; the recursive split only
-    starts above 128 elements, far beyond any network here).  Used for IM_env.py:372 and
-    IM_div_env.py:561.  Checked against numpy 2.3.5 for n = 2..33 in tests."""
+    """Summation order of ``np.sum`` on a contiguous float64 vector (numpy's pairwise_sum,
+    numpy/core/src/umath/loops_utils.h.src: sequential for n < 8, eight running accumulators up to
+    128 elements, above that a recursive split at n/2 rounded down to a multiple of 8).  Used for
+    IM_env.py:372, IM_div_env.py:561 and the dfo objective (base_restock_policy.py:45).  Checked
+    against numpy 2.3.5 for n = 2..33 and for n up to 70 000 in tests."""
     n = len(vals)
     if n < 8:
         res = 0.0
         for v in vals:
             res += v
         return res
+    if n > 128:
+        n2 = n // 2
+        n2 -= n2 % 8
+        return np_sum_order(vals[:n2]) + np_sum_order(vals[n2:])
     r = [vals[j] for j in range(8)]
     i = 8
     while i < n - (n % 8):
@@ -531,12 +536,17 @@ def poisson_pmf(k: int, mu: float) -> float:
     return math.exp((k * math.log(mu) if k > 0 else 0.0) - math.lgamma(k + 1) - mu)
 
 
-def dfo_value(env: OracleEnv, z: Sequence[float], customer_demand, pmf) -> float:
-    """dfo_func — base_restock_policy.py:24-45: -(1/T) * np.sum(pmf(demand_t) * reward_t).
-    ``pmf`` is the per-period probability vector (the caller evaluates the distribution)."""
-    rewards = base_stock_rollout(env, z, customer_demand)
+def dfo_value(env: OracleEnv, z: Sequence[float], customer_demand, pmf, delay_mask=None) -> float:
+    """dfo_func — base_restock_policy.py:24-45: -1 / T * np.sum(prob * rewards).
+    ``pmf`` is the probability array of the demand trace as the caller evaluates it: [T] for a serial env, [R, T]
+    for a divergent one (``env.dist.pmf(env.customer_demand)``, :42), where the product broadcasts over the retailer
+    rows and np.sum runs over the flattened [R, T] array (:45).  ``delay_mask`` replays noisy delays (the reference's
+    flag is sticky, so dfo_func after a noisy reset rolls out with them)."""
+    rewards = base_stock_rollout(env, z, customer_demand, delay_mask)
     prod = np.asarray(pmf, dtype=np.float64) * np.asarray(rewards, dtype=np.float64)
-    return -1 / env.T * np.sum(prod)
+    want = -1 / env.T * np.sum(prod)
+    assert want == -1 / env.T * np_sum_order(list(np.ascontiguousarray(prod).reshape(-1)))   # the restated order IS numpy's
+    return want
 
 
 # --------------------------------------------------------------------------------------

@@ -58,12 +58,17 @@ int orc_cfg_size(void) { return (int)sizeof(orc_cfg); }
 static double rescale(double v, double vmax, double a, double b) { return a + (((v - 0.0) * (b - a)) / (vmax - 0.0)); }
 static double rev_scale(double x, double vmax, double a, double b) { return (((x - a) * (vmax - 0.0)) / (b - a)) + 0.0; }
 
-/* numpy pairwise_sum order for n <= 128 */
+/* numpy pairwise_sum order (loops_utils.h.src): sequential below 8, eight accumulators up to 128, recursive split above */
 static double np_sum(const double* v, int n) {
     if (n < 8) {
         double r = 0.0;
         for (int i = 0; i < n; ++i) r += v[i];
         return r;
+    }
+    if (n > 128) {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return np_sum(v, n2) + np_sum(v + n2, n - n2);
     }
     double r[8];
     for (int j = 0; j < 8; ++j) r[j] = v[j];
@@ -325,11 +330,12 @@ long orc_run(const orc_cfg* c, long N, int periods, const int32_t* demand, const
     return bad;
 }
 
-/* Base-stock rollout (dfo_func's loop): z [m] (z_stride 0) or [N][m]; demand [N][R][T];
- * ret [N][cols]; step_reward [T][N][cols] or NULL; pmf [N][T] + dfo [N] or NULL. */
-long orc_rollout(const orc_cfg* c, long N, const double* z, int z_stride, const int32_t* demand, const double* pmf, double* ret,
-                 double* step_reward, double* dfo, int32_t* inv, int32_t* backlog, int32_t* order_u, int32_t* pipe, int32_t* bt,
-                 int nthreads) {
+/* Base-stock rollout (dfo_func's loop): z [m] (z_stride 0) or [N][m]; demand [N][R][T]; mask [N][T][m] or NULL;
+ * ret [N][cols]; step_reward [T][N][cols] or NULL; pmf [N][R][T] + dfo [N] or NULL (np.sum over the flattened
+ * [R][T] product of pmf and the per-period rewards, base_restock_policy.py:41-45). */
+long orc_rollout(const orc_cfg* c, long N, const double* z, int z_stride, const int32_t* demand, const unsigned char* mask,
+                 const double* pmf, double* ret, double* step_reward, double* dfo, int32_t* inv, int32_t* backlog, int32_t* order_u,
+                 int32_t* pipe, int32_t* bt, int nthreads) {
     const int m = c->m, T = c->T, R = c->R;
     const int cols = c->multi ? m : 1;
     int L = 0, NB = 0;
@@ -342,7 +348,8 @@ long orc_rollout(const orc_cfg* c, long N, const double* z, int z_stride, const 
     for (long n = 0; n < N; ++n) {
         orc_state s;
         reset_state(c, &s);
-        double act[ORC_MAX_NODES], rew[ORC_MAX_NODES], acc[ORC_MAX_NODES], prod[4096];
+        double act[ORC_MAX_NODES], rew[ORC_MAX_NODES], acc[ORC_MAX_NODES];
+        double* rew_t = dfo ? (double*)malloc(sizeof(double) * (size_t)T) : NULL;
         int cust[ORC_MAX_NODES];
         int e = 0;
         for (int k = 0; k < cols; ++k) acc[k] = 0.0;
@@ -355,14 +362,21 @@ long orc_rollout(const orc_cfg* c, long N, const double* z, int z_stride, const 
                 act[i] = (double)c->order_max[i] < u ? (double)c->order_max[i] : u;
             }
             for (int r = 0; r < R; ++r) cust[r] = demand[((size_t)n * R + r) * T + t];
-            const int code = step_env(c, &s, t, act, cust, NULL, rew, NULL, NULL);
+            const int code = step_env(c, &s, t, act, cust, mask ? mask + ((size_t)n * T + t) * m : NULL, rew, NULL, NULL);
             if (code && !e) e = code;
             for (int k = 0; k < cols; ++k) acc[k] += rew[k];
             if (step_reward) memcpy(step_reward + ((size_t)t * N + n) * cols, rew, sizeof(double) * cols);
-            if (dfo && t < 4096) prod[t] = pmf[(size_t)n * T + t] * rew[0];
+            if (dfo) rew_t[t] = rew[0];
         }
         memcpy(ret + (size_t)n * cols, acc, sizeof(double) * cols);
-        if (dfo) dfo[n] = (-1.0 / (double)T) * np_sum(prod, T);
+        if (dfo) {
+            double* prod = (double*)malloc(sizeof(double) * (size_t)R * T);
+            for (int r = 0; r < R; ++r)
+                for (int t = 0; t < T; ++t) prod[(size_t)r * T + t] = pmf[((size_t)n * R + r) * T + t] * rew_t[t];
+            dfo[n] = (-1.0 / (double)T) * np_sum(prod, R * T);
+            free(prod);
+            free(rew_t);
+        }
         store_state(c, &s, n, L, NB, inv, backlog, order_u, pipe, bt, NULL, NULL);
         if (e) bad += 1;
     }

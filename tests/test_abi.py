@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_mirror_and_version():
     lib = _lib.load()
     assert lib.imx_config_size() == ctypes.sizeof(_lib.ImxConfig)
-    assert lib.imx_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.imx_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_no_cpu_fallback():
@@ -143,4 +143,4 @@ def test_header_is_plain_c99_and_links_against_the_library(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
                     "-L", lib_dir, "-limx_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    assert out == ["2", "1"]                      # ABI version, and the C struct has the size the library was built with
+    assert out == ["3", "1"]                      # ABI version, and the C struct has the size the library was built with

@@ -182,3 +182,39 @@ def test_random_serial_chains(kind):
             actions = rng.uniform(-3, 50, size=(T, m))
         assert_same(run_reference(kind, cfg, demand, actions), run_oracle(kind, cfg, demand, actions), f"{kind} {cfg}")
         done += 1
+
+
+def test_dfo_func_divergent_and_noisy_live():
+    """The reference's own call (inv_management_div.py:228: dfo_func on InvManagementDiv with demand [R, T]) and dfo_func after a
+    noisy reset (the flag is sticky, MAIM_env.py:192-194), live against the oracle on random trees and chains."""
+    from scipy.stats import poisson
+    from harness import _uniform_replayer, copy_config, random_tree_config
+    from oracle import im_oracle
+    from oracle.ref_import import load_reference
+    import warnings
+    R = load_reference()
+    rng = np.random.default_rng(77)
+    for trial in range(10):
+        m = int(rng.integers(3, 9))
+        cfg = random_tree_config(rng, m, int(rng.integers(1, 4)), periods=int(rng.integers(5, 41)), time_dependency=False, prev_demand=False)
+        cfg.update(standardise_state=False, standardise_actions=False, demand_dist="poisson", mu=5, delay=np.asarray(cfg["delay"], dtype=np.int64))
+        noisy = bool(trial % 2)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            env = R.InvManagementDiv(copy_config(cfg))
+            nret, T = len(env.retailers), env.num_periods
+            orc = im_oracle.OracleEnv("IM_div", copy_config(cfg))
+            for _ in range(3):
+                z = rng.integers(5, 40, size=m).astype(float) + rng.choice([0.0, 0.25], size=m)
+                demand = rng.poisson(5, size=(nret, T))
+                mask = rng.uniform(size=(T, m)) <= 0.3 if noisy else None
+                saved = np.random.uniform
+                try:
+                    if noisy:
+                        env.reset(customer_demand=demand, noisy_delay=True, noisy_delay_threshold=0.5)
+                        seq = iter(_uniform_replayer("IM_div", [int(d) for d in env.delay], T, mask))
+                        np.random.uniform = lambda *a, **k: next(seq)
+                    want = R.dfo_func(z, env, demand)
+                finally:
+                    np.random.uniform = saved
+                assert im_oracle.dfo_value(orc, z, demand, poisson.pmf(demand, mu=5), mask) == want, (trial, cfg["connections"])
