@@ -36,10 +36,11 @@ T_PERIODS = 30
 M_STAGES = 4
 KERNEL_VARIANTS = {0: "imx::step_kernel (ahead-of-time, direct global accesses)",
                    1: "imx::step_kernel_tma (ahead-of-time, TMA-staged tiles)",
-                   2: "imx::step_kernel_tma<4,3,1,1,false> (NVRTC-specialised, TMA-staged tiles)"}
+                   2: "imx::step_kernel_tma (NVRTC-specialised, TMA-staged tiles, one tile per CTA)",
+                   3: "imx::step_kernel_pipe (NVRTC-specialised, persistent warp-specialised TMA pipeline)"}
 ENVS_PER_GPU = 65536
-NCU_TRAFFIC_BYTES_65536 = 8402176        # dram__bytes_read.sum + dram__bytes_write.sum, one launch (cold L2), profiles/r1_ncu_step_kernel_final.txt
-NCU_TRAFFIC_BYTES_4MI = 537099264 + 1402789000   # same counters at 4 Mi envs, profiles/r1_ncu_step_kernel_tma_specialised_4Mi_envs.txt
+NCU_TRAFFIC_JSON = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # written by benchmarks/ncu_summary.py --traffic-json from the ncu captures
+REFERENCE_TIMING_JSON = os.path.join(ROOT, "profiles", "r2_reference_cpu_timing.json")   # benchmarks/time_reference.py (build container)
 WORKLOAD = ("MAIM_env 4-stage serial, MA_6 obs mode (td=T,pd=T,pa=F,P=1, shared reward), step() on "
             "65536 envs per GPU, 30-period episodes, replayed Poisson(5) demand, uniform(-1,1) actions pre-staged")
 
@@ -62,6 +63,37 @@ def _cpu_worker(args):
         for t in range(T_PERIODS):
             env.step(actions[e, t])
     return time.perf_counter() - t0
+
+
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel `key`, from the committed ncu capture
+    (profiles/ncu_traffic.json: {key: {"bytes": ..., "source": profile file, "commit": ...}}); None when not captured."""
+    try:
+        rec = json.load(open(NCU_TRAFFIC_JSON)).get(key)
+        return (int(rec["bytes"]), f"{rec['source']} @ {rec.get('commit', '?')}") if rec else (None, None)
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
+def reference_timing(name):
+    """the UNMODIFIED reference timed on the build container (benchmarks/time_reference.py); the GPU box has no reference tree"""
+    try:
+        doc = json.load(open(REFERENCE_TIMING_JSON))
+        row = doc["configs"][name]
+        return {"value": row["reference"]["agent_steps_per_sec_all_cores"], "value_1core": row["reference"]["agent_steps_per_sec_1core"],
+                "unit": "agent-steps/s", "cores": row["reference"]["cores"], "kind": "reference",
+                "port_over_reference_1core_same_machine": row["port_over_reference_1core"],
+                "sample": f"{doc['episodes_per_measurement']} episodes x {doc['periods']} periods per core of the same workload through the "
+                          f"unmodified environments/*.py, measured on the build container ({doc['machine']['cores_available']} cores, {doc['when']}), "
+                          "not on this box: the reference tree cannot travel"}
+    except (OSError, ValueError, KeyError):
+        return None
+
+
+def bench_config(world, n_per_gpu):
+    """`config` of the JSON line — identical in both arms (workload description only)."""
+    return {"workload": WORKLOAD, "envs_per_gpu": n_per_gpu, "periods_per_step": T_PERIODS, "agents": M_STAGES,
+            "agent_steps_per_step": world * n_per_gpu * M_STAGES * T_PERIODS}
 
 
 def host_cores():
@@ -140,8 +172,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": bench_config(args.gpus, args.envs), "sample": sample,
         "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline_reference": reference_timing("config2_maim4_ma6"),
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -247,6 +280,181 @@ def timed_replays(graph, reps, torch):
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e-3
+
+
+# ----------------------------------------------------------------------------------------
+# the other BASELINE.json configs, measured at this run's world size (rows g2 of the coverage table)
+# ----------------------------------------------------------------------------------------
+def _timed_region(fn, reps, torch, dist, world, dev, post=None):
+    """barrier + sync, `reps` calls of fn, optional collective, CUDA events; returns the max over ranks in seconds"""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    if post is not None:
+        post()
+    e1.record()
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dt = float(tmax.item())
+    return dt
+
+
+def config4_episode_loop(name, total_envs, world, rank, dev, torch, dist, peak, reps, action_mode="near_eq"):
+    """BASELINE config 4: MAIM_div_env (div1 / div2), `total_envs` envs in total split over the ranks (STRONG scaling),
+    reset + 30 x imx_step + episode statistics per episode as one CUDA graph, one all-reduce per evaluation batch."""
+    from marl_for_im_b200 import _lib, presets
+    from marl_for_im_b200.envs import MultiAgentInvManagementDiv
+    cfg = presets.PRESETS[name]()
+    N = total_envs // world
+    env = MultiAgentInvManagementDiv(dict(cfg, num_envs=N, device=str(dev), env_offset=rank * N))
+    m, T, O, R = env.num_nodes, env.num_periods, env.obs_len, len(env._retailers)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+    demand = torch.poisson(torch.full((N, R, T), 5.0, device=dev), generator=g).to(torch.int32)
+    if action_mode == "uniform":
+        actions = torch.rand((T, N, m), dtype=torch.float64, device=dev, generator=g) * 2 - 1
+    else:                                                   # near-equilibrium: exercises every branch of the split (SURVEY config 4 (ii))
+        actions = (torch.randn((T, N, m), dtype=torch.float64, device=dev, generator=g) * 0.5 - 0.6).clamp(-1, 1)
+    nbuf = 4 if N * m * O * 8 > (64 << 20) else T          # > L2 either way: T distinct buffers, or 4 x (> 64 MB)
+    obs = [torch.empty((N, m, O), dtype=torch.float64, device=dev) for _ in range(nbuf)]
+    rew = torch.empty((T, N, m), dtype=torch.float64, device=dev)
+    stats = torch.zeros(3 + 2 * m, dtype=torch.float64, device=dev)
+    lib, h = env._lib, env._handle
+
+    def steps(stream):
+        for t in range(T):
+            _lib.check(lib.imx_step(h, C.c_void_p(actions[t].data_ptr()), C.c_void_p(obs[t % nbuf].data_ptr()), C.c_void_p(rew[t].data_ptr()),
+                                    None, C.c_void_p(stream)))
+
+    def episode(stream):
+        _lib.check(lib.imx_reset(h, C.c_void_p(demand.data_ptr()), None, 0, 1, C.c_void_p(obs[0].data_ptr()), C.c_void_p(stream)))
+        steps(stream)
+        _lib.check(lib.imx_episode_stats(h, C.c_void_p(rew.data_ptr()), T, None, C.c_void_p(stats.data_ptr()), 1, C.c_void_p(stream)))
+
+    def steps_only(stream):
+        lib.imx_set_period(h, 0)
+        steps(stream)
+
+    g_ep, g_st = capture(episode, torch), capture(steps_only, torch)
+    variant = lib.imx_kernel_variant(h)
+    for _ in range(3):
+        g_ep.replay()
+    stats.zero_()
+    dt = _timed_region(g_ep.replay, reps, torch, dist, world, dev, post=(lambda: dist.all_reduce(stats)) if world > 1 else None)
+    timed_replays(g_st, 3, torch)
+    dts = timed_replays(g_st, max(reps, 10), torch) / (max(reps, 10) * T)
+    B = algorithmic_bytes_per_env_step(env)
+    flags = int(env.error_flags.abs().sum())
+    out = {"workload": f"MAIM_div_env {name}, MA_6 obs mode, {total_envs} envs in total over {world} GPU(s) = {N} per GPU (strong scaling), "
+                       f"Poisson(5) demand [N,{R},30], clip(N(-0.6,0.5),-1,1) actions pre-staged, reset + 30 imx_step + statistics per episode",
+           "scaling": "strong", "envs_total": total_envs, "envs_per_gpu": N, "agent_steps_per_sec": world * N * m * T * reps / dt,
+           "ms_per_episode": dt / reps * 1e3,
+           "step_kernel": {"us_per_launch": dts * 1e6, "achieved": B * N / dts / 1e9, "peak": peak, "unit": "GB/s", "frac": B * N / dts / 1e9 / peak,
+                           "algorithmic_bytes_per_env_step": B, "kernel": KERNEL_VARIANTS[variant]},
+           "watchdog_flags": flags, "mean_return": float((stats[1] / stats[0]).item()) if float(stats[0].item()) > 0 else None,
+           "cpu_baseline_reference": reference_timing("config4_" + name)}
+    del env
+    return out
+
+
+def config3_fused_rollout(total_envs, world, rank, dev, torch, dist, reps):
+    """BASELINE config 3: MAIM_env 8-stage, `total_envs` envs over the ranks, fused 30-period base-stock rollout (z = 25),
+    Philox Poisson(5) demand drawn in the kernel, per-batch return statistics + one all-reduce."""
+    from marl_for_im_b200 import _lib, presets
+    from marl_for_im_b200.envs import MultiAgentInvManagement
+    cfg = presets.serial8(time_dependency=False, prev_demand=False)
+    cfg["standardise_actions"] = False
+    cfg.update(demand_dist="poisson", mu=5)
+    N = total_envs // world
+    env = MultiAgentInvManagement(dict(cfg, num_envs=N, device=str(dev), env_offset=rank * N))
+    m, T = env.num_nodes, env.num_periods
+    z = torch.full((m,), 25.0, dtype=torch.float64, device=dev)
+    ret = torch.empty((N, m), dtype=torch.float64, device=dev)
+    st_one = torch.zeros(3 + 2 * m, dtype=torch.float64, device=dev)
+    stats = torch.zeros(3 + 2 * m, dtype=torch.float64, device=dev)
+    lib, h = env._lib, env._handle
+    s = torch.cuda.current_stream().cuda_stream
+    ep = [0]
+
+    def batch():
+        ep[0] += 1                                          # a new episode id = new Philox draws
+        _lib.check(lib.imx_rollout_basestock(h, C.c_void_p(z.data_ptr()), 0, None, None, 0, ep[0], None, C.c_void_p(ret.data_ptr()), None, None, 0,
+                                             C.c_void_p(s)))
+        _lib.check(lib.imx_return_stats(h, C.c_void_p(ret.data_ptr()), C.c_void_p(st_one.data_ptr()), C.c_void_p(s)))
+        stats.add_(st_one)
+
+    for _ in range(3):
+        batch()
+    stats.zero_()
+    dt = _timed_region(batch, reps, torch, dist, world, dev, post=(lambda: dist.all_reduce(stats)) if world > 1 else None)
+    out = {"workload": f"MAIM_env 8-stage serial (MA_inv_management.py:40-61), {total_envs} envs in total over {world} GPU(s) = {N} per GPU, fused "
+                       "30-period base-stock rollout (z = 25), Philox Poisson(5) demand in-kernel, return statistics + 1 all-reduce per batch",
+           "scaling": "strong", "envs_total": total_envs, "envs_per_gpu": N, "agent_steps_per_sec": world * N * m * T * reps / dt,
+           "ms_per_batch": dt / reps * 1e3, "bound": "instruction issue (about 1 byte of HBM traffic per agent-step)",
+           "kernel": "imx::rollout_kernel (NVRTC-specialised)" if lib.imx_kernel_variant(h) >= 2 else "imx::rollout_kernel (ahead-of-time)",
+           "mean_return": float((stats[1] / stats[0]).item()), "cpu_baseline_reference": reference_timing("maim8_ma6")}
+    del env
+    return out
+
+
+def config5_env_plus_observer(n_per_gpu, world, rank, dev, torch, dist, peak, reps):
+    """BASELINE config 5, the part of it that is this path: 2-stage MAIM_env in CC_5 obs mode + the centralised-critic
+    observation (central_critic_observer + FillInActions, models/CC_Model.py:165-214) emitted by the step itself
+    (imx_step_cc: one kernel writes obs, reward, state and the [N][m][W] critic rows).  float32 observations (RLlib's cast).
+    The policy / value networks of config 5 are RLlib's and out of scope."""
+    from marl_for_im_b200 import _lib, presets
+    from marl_for_im_b200.envs import MultiAgentInvManagement
+    N = n_per_gpu
+    env = MultiAgentInvManagement(dict(presets.serial2(), num_envs=N, device=str(dev), env_offset=rank * N, obs_dtype="float32"))
+    m, T, O = env.num_nodes, env.num_periods, env.obs_len
+    W = (m - 1) * (1 + O) + O
+    g = torch.Generator(device=dev)
+    g.manual_seed(2000 + rank)
+    demand = torch.poisson(torch.full((N, 1, T), 5.0, device=dev), generator=g).to(torch.int32)
+    actions = torch.rand((T, N, m), dtype=torch.float64, device=dev, generator=g) * 2 - 1
+    obs = torch.empty((T, N, m, O), dtype=torch.float32, device=dev)
+    cc = torch.empty((T, N, m, W), dtype=torch.float32, device=dev)
+    rew = torch.empty((T, N, m), dtype=torch.float64, device=dev)
+    lib, h = env._lib, env._handle
+    fused = hasattr(lib, "imx_step_cc")
+
+    def steps_only(stream):
+        lib.imx_set_period(h, 0)
+        for t in range(T):
+            if fused:
+                _lib.check(lib.imx_step_cc(h, C.c_void_p(actions[t].data_ptr()), C.c_void_p(obs[t].data_ptr()), C.c_void_p(cc[t].data_ptr()), 1,
+                                           -1.0, 1.0, C.c_void_p(rew[t].data_ptr()), C.c_void_p(stream)))
+            else:
+                _lib.check(lib.imx_step(h, C.c_void_p(actions[t].data_ptr()), C.c_void_p(obs[t].data_ptr()), C.c_void_p(rew[t].data_ptr()), None,
+                                        C.c_void_p(stream)))
+                _lib.check(lib.imx_cc_observe(h, C.c_void_p(obs[t].data_ptr()), C.c_void_p(actions[t].data_ptr()), -1.0, 1.0,
+                                              C.c_void_p(cc[t].data_ptr()), 1, C.c_void_p(stream)))
+
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.imx_reset(h, C.c_void_p(demand.data_ptr()), None, 0, 1, None, C.c_void_p(s)))
+    gs = capture(steps_only, torch)
+    for _ in range(3):
+        gs.replay()
+    dt = _timed_region(gs.replay, reps, torch, dist, world, dev)
+    per_step = dt / (reps * T)
+    S_words = env.state_words
+    B = 2 * 4 * S_words + 4 + 8 * m * 2 + 4 * m * O + 4 * m * W        # state r+w, demand, actions + rewards (f64), obs + critic rows (f32)
+    out = {"workload": f"MAIM_env 2-stage (Oracle_2.py:26-37), CC_5 obs mode (O = {O}), {N} envs per GPU, step + centralised-critic observation "
+                       f"rows [N][{m}][{W}] float32 (models/CC_Model.py:165-214) per period",
+           "scaling": "weak", "envs_per_gpu": N, "samples_per_sec": world * N * m / per_step, "us_per_period": per_step * 1e6,
+           "fused_in_step_kernel": bool(fused), "algorithmic_bytes_per_env_step": B, "achieved": B * N / per_step / 1e9, "peak": peak, "unit": "GB/s",
+           "frac": B * N / per_step / 1e9 / peak, "cpu_baseline_reference": reference_timing("config5_maim2_cc5"),
+           "note": "samples = agent-steps of env + critic-observation build; the policy / value MLPs of config 5 are RLlib's (out of scope)"}
+    del env
+    return out
 
 
 def run_ours(args):
@@ -389,12 +597,15 @@ def run_ours(args):
                            "ahead, outputs streamed behind the compute; bit-identical to 30 imx_step calls (tests/test_gpu_step_many.py)"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8000_GBs": achieved / 8000.0,
-                "traffic": NCU_TRAFFIC_BYTES_65536 if N == ENVS_PER_GPU else None,
-                "traffic_source": "profiles/r1_ncu_step_kernel_final.txt (ncu --set full: dram__bytes_read+write per launch; "
-                                  "the 31 MB working set of one launch is L2-resident, hence traffic << algorithmic bytes)", "kernel": KERNEL_VARIANTS[env._lib.imx_kernel_variant(env._handle)], "us_per_launch": dt * 1e6,
+                "traffic": ncu_traffic("step_kernel_config2_65536")[0] if N == ENVS_PER_GPU else None,
+                "traffic_source": (ncu_traffic("step_kernel_config2_65536")[1] or "not captured for this kernel revision")
+                                  + " (ncu --set full: dram__bytes_read+write per launch, cold L2; the 31 MB working set of one launch is "
+                                    "L2-resident in the bench loop, hence traffic << algorithmic bytes)",
+                "kernel": KERNEL_VARIANTS[env._lib.imx_kernel_variant(env._handle)], "us_per_launch": dt * 1e6,
                 "algorithmic_bytes_per_env_step": B, "envs_per_launch": N, "peak_source": peak_src,
                 "note": "per-launch time = steps-only graph of 30 dependent launches / 30 (includes inter-kernel gaps)"}
 
+    state_mb = env.state_words * 4 * N / 1e6
     # ---- same kernel at large N (working set >> L2), rank 0 only -------------------------------------
     roof_large = None
     if rank == 0 and not args.skip_large:
@@ -412,18 +623,34 @@ def run_ours(args):
     e2e_f32["api"] += "; obs_f32 = 1"
     del env32
 
+    # ---- the other BASELINE configs at this world size (every rank takes part; rank 0 reports) --------------------------
+    other = {}
+    if not args.skip_configs:
+        del obs_all, obs, rew, ep
+        torch.cuda.empty_cache()
+        creps = max(5, min(args.steps, 20))
+        for key, fn in (("config3_maim8_fused_rollout_1Mi", lambda: config3_fused_rollout(1 << 20, world, rank, dev, torch, dist, creps)),
+                        ("config4_div1_262144", lambda: config4_episode_loop("div1", 262144, world, rank, dev, torch, dist, peak, creps)),
+                        ("config4_div2_262144", lambda: config4_episode_loop("div2", 262144, world, rank, dev, torch, dist, peak, creps)),
+                        ("config5_maim2_cc_observer", lambda: config5_env_plus_observer(ENVS_PER_GPU, world, rank, dev, torch, dist, peak, creps))):
+            try:
+                other[key] = fn()
+            except Exception as exc:                         # a side measurement must never cost the headline line
+                other[key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            torch.cuda.empty_cache()
+
     if rank == 0:
         line = {
             "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32 state / f64 obs+reward",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": N, "periods_per_step": T, "agents": m,
-                       "agent_steps_per_step": agent_steps_per_bench_step,
-                       "l2": (f"inputs larger than L2: each step streams {T} distinct action/obs/reward buffers "
-                              f"({(T * N * m * (2 + O) * 8) / 1e6:.0f} MB > 126 MB L2); the {env.state_words * 4 * N / 1e6:.1f} MB state stays cached by design"),
-                       "timing": "CUDA events around K CUDA-graph replays (reset + 30 step launches) + per-episode return statistics"
-                                 + (" + 1 NCCL all-reduce of the batch statistics" if world > 1 else "") + ", max over ranks"},
+            "config": bench_config(world, N),
+            "measurement": {"l2": (f"inputs larger than L2: each step streams {T} distinct action/obs/reward buffers "
+                                   f"({(T * N * m * (2 + O) * 8) / 1e6:.0f} MB > 126 MB L2); the {state_mb:.1f} MB state stays cached by design"),
+                            "timing": "CUDA events around K CUDA-graph replays (reset + 30 step launches) + per-episode return statistics"
+                                      + (" + 1 NCCL all-reduce of the batch statistics" if world > 1 else "") + ", max over ranks"},
+            "configs": other, "cpu_baseline_reference": reference_timing("config2_maim4_ma6"),
             "roofline": roofline, "roofline_large_n": roof_large, "replay_fused": replay_fused, "cpu_baseline": cpu, "cpu_baseline_1core": cpu_1, "cpu_baseline_c": cpu_c, "e2e": e2e, "e2e_f32_obs": e2e_f32,
             "gpu_launches": int(launches_per_episode * args.steps), "host_cores_bound_to_gpu_numa_node": numa_cores,
             "clocks": clocks,
@@ -461,12 +688,14 @@ def large_n_roofline(torch, dev, peak, N=4 * 1024 * 1024, periods=8):
     dt = e0.elapsed_time(e1) * 1e-3 / periods
     B = algorithmic_bytes_per_env_step(env)
     achieved = B * N / dt / 1e9
+    variant = env._lib.imx_kernel_variant(env._handle)
     del env
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "envs_per_launch": N, "us_per_launch": dt * 1e6, "working_set_mb": B * N / 1e6,
             "agent_steps_per_sec": N * m / dt, "algorithmic_bytes_per_launch": B * N,
-            "traffic": NCU_TRAFFIC_BYTES_4MI if N == 4 * 1024 * 1024 else None,
-            "traffic_source": "profiles/r1_ncu_step_kernel_tma_specialised_4Mi_envs.txt (dram read 537 MB + write 1403 MB per launch = 0.97 x algorithmic)"}
+            "traffic": ncu_traffic("step_kernel_config2_4Mi")[0] if N == 4 * 1024 * 1024 else None,
+            "traffic_source": ncu_traffic("step_kernel_config2_4Mi")[1] or "not captured for this kernel revision",
+            "kernel": KERNEL_VARIANTS[variant]}
 
 
 def e2e_measure(env, demand_h, actions_h, torch, dev, world, episodes):
@@ -515,6 +744,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-large", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="skip BASELINE configs 3 / 4 / 5 (the `configs` object of the line)")
     ap.add_argument("--large-only", action="store_true", help="only the 4 Mi-env roofline point (used for the ncu capture)")
     args = ap.parse_args()
     if args.large_only:

@@ -23,7 +23,7 @@ from marl_for_im_b200 import _lib, presets  # noqa: E402
 from marl_for_im_b200.envs import ENV_CLASSES  # noqa: E402
 
 PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-VARIANT = {0: "aot-direct", 1: "aot-tma", 2: "nvrtc-specialised-tma"}
+VARIANT = {0: "aot-direct", 1: "aot-tma", 2: "nvrtc-specialised-tma", 3: "nvrtc-specialised-tma-pipeline"}
 
 
 def bytes_per_env_step(env):

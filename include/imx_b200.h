@@ -140,8 +140,9 @@ int imx_destroy(imx_env* env);
  * does this for the variants its batch size selects; call imx_prepare() to force the rest.
  *   flags: IMX_PREPARE_STEP (observation-writing step / step_many / rollout kernels), IMX_PREPARE_NOOBS (the
  *          obs_dev = NULL specialisation), IMX_PREPARE_HOST (staging buffers + stream of the *_host calls),
- *          IMX_PREPARE_DFO (scratch of the dfo objective); 0 = all.  Synchronous; may take seconds (NVRTC). */
-enum imx_prepare_flags { IMX_PREPARE_STEP = 1, IMX_PREPARE_NOOBS = 2, IMX_PREPARE_HOST = 4, IMX_PREPARE_DFO = 8 };
+ *          IMX_PREPARE_DFO (scratch of the dfo objective), IMX_PREPARE_CC (imx_step_cc's specialisation and scratch);
+ *          0 = all.  Synchronous; may take seconds (NVRTC). */
+enum imx_prepare_flags { IMX_PREPARE_STEP = 1, IMX_PREPARE_NOOBS = 2, IMX_PREPARE_HOST = 4, IMX_PREPARE_DFO = 8, IMX_PREPARE_CC = 16 };
 int imx_prepare(imx_env* env, int flags);
 
 /* Derived sizes: O (observation length per agent), S (int32 state words per env), R, L, NB. */
@@ -249,6 +250,19 @@ int imx_cc_obs_len(const imx_env* env);
 int imx_cc_observe(imx_env* env, const void* obs_dev, const double* actions_dev, double clip_lo, double clip_hi,
                    void* out_dev, int out_is_f32, void* stream);
 
+/* step(action) + central_critic_observer in ONE kernel: the step kernel's epilogue assembles the critic rows of
+ * imx_cc_observe from the observation tile it has just built in shared memory and from this step's action tile, and
+ * writes them with one bulk store per tile next to obs / reward / state (no second pass over [N][m][O]).
+ *   obs_dev     [N][m][O] or NULL (the rows still contain every agent's observation)
+ *   cc_dev      [N][m][W], W = imx_cc_obs_len(), in the observation element type (float64, or float32 with cfg.obs_f32)
+ *   fill_actions non-zero: opponent-action slots = this step's actions clipped to [clip_lo, clip_hi] (FillInActions,
+ *               models/CC_Model.py:165-193; the evaluation loops' hand-built rows, CC_inv_management.py:516-528); zero: zeros, as
+ *               central_critic_observer leaves them at sampling time (:196-214)
+ * Fused wherever the runtime-specialised TMA kernels serve the whole batch (N a multiple of the tile size, 16-byte aligned
+ * buffers); otherwise imx_step followed by imx_cc_observe — same bytes either way.  Multi-agent kinds only. */
+int imx_step_cc(imx_env* env, const double* actions_dev, void* obs_dev, void* cc_dev, int fill_actions, double clip_lo,
+                double clip_hi, double* reward_dev, void* stream);
+
 /* End-to-end convenience calls on HOST buffers (pinned memory recommended): copy in, launch, copy
  * out, synchronise.  These are what a per-step Python caller pays for. */
 int imx_reset_host(imx_env* env, const int32_t* demand_host, const uint8_t* delay_mask_host, int noisy,
@@ -260,13 +274,16 @@ int imx_step_host(imx_env* env, const double* actions_host, void* obs_host, doub
 int imx_poisson_cdf(const imx_env* env, double* out, int cap);
 
 /* Which kernel served the last step()/rollout of this handle: 0 ahead-of-time direct kernel,
- * 1 ahead-of-time TMA-staged kernel, 2 runtime-specialised (NVRTC, same sources, flags as literals). */
+ * 1 ahead-of-time TMA-staged kernel, 2 runtime-specialised (NVRTC, same sources, flags as literals),
+ * 3 runtime-specialised persistent pipeline (imx_step_pipe.cuh). */
 int imx_kernel_variant(const imx_env* env);
 /* Last message of the runtime-specialisation layer (why it is unavailable, or a compile log). */
 const char* imx_jit_log(void);
-/* Compiles the specialised kernels for `cfg` with NVRTC for sm_100a WITHOUT a GPU (build check).
+/* Compiles the specialised kernels for `cfg` with NVRTC for sm_100a WITHOUT a GPU (build check; also warms the on-disk
+ * cubin cache).  variant: 0 = the step / step_many / rollout / pipelined kernels, 1 = the same without observations
+ * (obs_dev = NULL), 2 = with the centralised-critic rows (imx_step_cc).
  * Returns the cubin size in bytes, or a negative error; `log` receives the compiler log. */
-int imx_jit_compile_check(const imx_config* cfg, char* log, int cap);
+int imx_jit_compile_check(const imx_config* cfg, int variant, char* log, int cap);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 int64_t imx_launch_count(void);

@@ -64,6 +64,7 @@ SYMBOLS = {
     "imx_step_many": (C.c_int, [_P, _P, C.c_int, _P, _P, C.POINTER(ImxInfoOut), _P]),
     "imx_rollout_basestock": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_uint64, _P, _P, _P, _P, C.c_int, _P]),
     "imx_prepare": (C.c_int, [_P, C.c_int]),
+    "imx_step_cc": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_double, C.c_double, _P, _P]),
     "imx_return_stats": (C.c_int, [_P, _P, _P, _P]),
     "imx_reset_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint64, _P]),
     "imx_step_host": (C.c_int, [_P, _P, _P, _P]),
@@ -76,7 +77,7 @@ SYMBOLS = {
     "imx_cc_observe": (C.c_int, [_P, _P, _P, C.c_double, C.c_double, _P, C.c_int, _P]),
     "imx_kernel_variant": (C.c_int, [_P]),
     "imx_jit_log": (C.c_char_p, []),
-    "imx_jit_compile_check": (C.c_int, [C.POINTER(ImxConfig), C.c_char_p, C.c_int]),
+    "imx_jit_compile_check": (C.c_int, [C.POINTER(ImxConfig), C.c_int, C.c_char_p, C.c_int]),
     "imx_launch_count": (C.c_int64, []),
 }
 

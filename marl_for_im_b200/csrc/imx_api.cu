@@ -10,6 +10,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>       // header-only; a no-op unless a profiler injects itself (ranges around reset / step / rollout)
+
 #include "imx_reset.cuh"
 #include "imx_step_tma.cuh"
 #include "imx_rollout.cuh"
@@ -46,6 +48,26 @@ static int fail(int code, const char* fmt, ...) {
         if (e__ != cudaSuccess) return fail(-3, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
         g_launches.fetch_add(1, std::memory_order_relaxed);                                        \
     } while (0)
+
+// NVTX range of one entry point (domain "imx_b200"): shows up as reset / step / rollout spans on an nsys or ncu timeline.
+struct NvtxRange {
+    static nvtxDomainHandle_t domain() {
+        static nvtxDomainHandle_t d = nvtxDomainCreateA("imx_b200");
+        return d;
+    }
+    explicit NvtxRange(const char* name) { nvtxDomainRangePushEx(domain(), attr(name)); }
+    ~NvtxRange() { nvtxDomainRangePop(domain()); }
+    static const nvtxEventAttributes_t* attr(const char* name) {
+        static thread_local nvtxEventAttributes_t a;
+        memset(&a, 0, sizeof(a));
+        a.version = NVTX_VERSION;
+        a.size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
+        a.messageType = NVTX_MESSAGE_TYPE_ASCII;
+        a.message.ascii = name;
+        return &a;
+    }
+};
+#define IMX_NVTX(name) NvtxRange nvtx_range__(name)
 
 extern "C" const char* imx_last_error(void) { return g_err; }
 extern "C" int imx_abi_version(void) { return IMX_ABI_VERSION; }
@@ -106,11 +128,19 @@ struct imx_env {
     int tma_threads = 256;               // CTA size of the TMA kernel (IMX_TMA_THREADS: 64, 128 or 256)
     int use_pdl = 1;                     // chain step launches with programmatic dependent launch (IMX_PDL=0 disables)
     int fuse_periods = 1;                // imx_step_many advances all its periods in one launch (IMX_FUSE_PERIODS=0: K plain launches)
+    int pipe_mode = 0;                   // persistent pipelined step kernel: 0 auto, 1 always, -1 never (IMX_PIPE)
+    int pipe_stages = 4;                 // ring depth of the pipelined kernel (IMX_PIPE_STAGES)
+    int pipe_ctas = 0;                   // resident CTAs per SM of the pipelined kernel (IMX_PIPE_CTAS; 0 = derived)
+    int sm_count = 148;
     int jit_policy = 0;                  // 0 auto (large batches), 1 always, -1 never (IMX_JIT)
     int jit_state = 0;                   // 0 not tried, 1 specialised kernels loaded, -1 unavailable
     const imxjit::Kernels* jit = nullptr;
     const imxjit::Kernels* jit_noobs = nullptr;   // specialised without the observation output
     int jit_noobs_state = 0;
+    const imxjit::Kernels* jit_cc = nullptr;      // specialised with the centralised-critic rows emitted by the step (imx_step_cc)
+    int jit_cc_state = 0;
+    TileLayout tile_cc = {};             // tile_jit + the [E][m][W] critic-row region
+    void* d_obs_scratch = nullptr;       // [N][m][O] observations of the unfused imx_step_cc fallback when the caller passes none
     int last_variant = 0;                // 0 AOT direct, 1 AOT TMA, 2 runtime-specialised TMA
     reset_fn_t reset_fn = nullptr;
     rollout_fn_t rollout_fn = nullptr;
@@ -178,7 +208,7 @@ static int m_pad_of(const imx_env* e) {
 }
 
 // shared-memory tile layout of the TMA kernel (regions 128-byte aligned); pure host arithmetic
-static void compute_tile(const imx_env* e, TileLayout& L, int tile_width) {
+static void compute_tile(const imx_env* e, TileLayout& L, int tile_width, bool with_cc = false) {
     const int m = e->m;
     const int E = (e->tma_threads / 32) * (32 / tile_width);
     int off = 0;
@@ -196,6 +226,7 @@ static void compute_tile(const imx_env* e, TileLayout& L, int tile_width) {
     L.off_dem = take(e->R * E * 4);
     L.off_obs = take(E * m * e->O * (e->cfg.obs_f32 ? 4 : 8));
     L.off_rew = take(E * m * 8);
+    L.off_cc = with_cc ? take(E * m * ((m - 1) * (1 + e->O) + e->O) * (e->cfg.obs_f32 ? 4 : 8)) : 0;
     L.total = off;
     // multi-period launches double-buffer the per-period inputs; the extra regions sit behind the
     // single-period layout so that a plain step launches the same kernel with `total` bytes only
@@ -205,7 +236,7 @@ static void compute_tile(const imx_env* e, TileLayout& L, int tile_width) {
 }
 
 // -D options and template instantiations of the runtime-specialised build (imx_jit.cuh)
-static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1) {
+static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1, int has_cc = 0) {
     std::vector<std::string>& defs = sp.defines;
     const imx_config& c = e->cfg;
     const bool always_std = (c.kind == IMX_KIND_MAIM_DIV);
@@ -223,12 +254,13 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
     const double fr = std::frexp(c.b - c.a, &ex);
     add("bma_pow2", (fr == 0.5 && ex > -1000 && ex < 1000) ? 1 : 0);
     add("m_pow2", ((e->m & (e->m - 1)) == 0) ? 1 : 0);
-    const TileLayout& L = e->tile_jit;
+    const TileLayout& L = has_cc ? e->tile_cc : e->tile_jit;
+    add("has_cc", has_cc);
     auto addt = [&](const char* k, long long v) { defs.push_back(std::string("IMX_KT_") + k + "=" + std::to_string(v)); };
     addt("E", L.E); addt("off_act", L.off_act); addt("off_inv", L.off_inv); addt("off_bl", L.off_bl); addt("off_ou", L.off_ou);
     addt("off_pipe", L.off_pipe); addt("off_hd", L.off_hd); addt("off_ho", L.off_ho); addt("off_carry", L.off_carry);
     addt("off_bt", L.off_bt); addt("off_dem", L.off_dem); addt("off_obs", L.off_obs); addt("off_rew", L.off_rew); addt("total", L.total);
-    addt("off_act2", L.off_act2); addt("off_dem2", L.off_dem2); addt("total2", L.total2);
+    addt("off_act2", L.off_act2); addt("off_dem2", L.off_dem2); addt("total2", L.total2); addt("off_cc", L.off_cc);
     {   // register bound of the plain step kernel, measured per family: the divergent kernels (natural 47) gain occupancy at 40
         // (div1 +5 %, div2 +1.5 %), the 2-wide chain is faster unconstrained (+8 % at 64), the others are best at their natural 32
         const char* sr = getenv("IMX_STEP_MAXNREG");
@@ -263,13 +295,20 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
     sp.name[2] = "imx::rollout_kernel<" + std::to_string(e->m) + ", " + std::to_string(e->D) + ", " + std::to_string(e->div ? maxc : 1) +
                  ", " + dv + ">";
     sp.name[3] = "";
+    if (has_cc) { sp.name[1] = ""; sp.name[2] = ""; }      // the critic rows ride on the single-period kernels only
+    if (e->pipe_mode >= 0 && (int64_t)e->pipe_stages * L.total <= 200 * 1024) {
+        defs.push_back("IMX_PIPE_STAGES=" + std::to_string(e->pipe_stages));
+        const char* pr = getenv("IMX_PIPE_MAXNREG");
+        if (pr && atoi(pr) > 0) defs.push_back("IMX_PIPE_MAXNREG=" + std::to_string(atoi(pr)));
+        sp.name[3] = "imx::step_kernel_pipe" + targs;
+    }
 }
 
 static void jit_smem(const imx_env* e, int smem[imxjit::N_KERNELS]) {
     smem[0] = e->tile_jit.total;
     smem[1] = e->tile_jit.total2 <= 200 * 1024 ? e->tile_jit.total2 : e->tile_jit.total;
     smem[2] = 0;
-    smem[3] = 0;
+    smem[3] = e->pipe_stages * e->tile_jit.total;
 }
 
 // Loads the specialised kernels for this handle (large batches, or IMX_JIT=1).  Called from imx_create() /
@@ -304,6 +343,20 @@ static void ensure_jit_noobs(imx_env* e) {
     if (e->jit_noobs) e->jit_noobs_state = 1;
 }
 
+// ... and WITH the centralised-critic rows (imx_step_cc).  Compiled by imx_prepare(IMX_PREPARE_CC) or on first use outside capture.
+static void ensure_jit_cc(imx_env* e) {
+    if (e->jit_cc_state != 0) return;
+    e->jit_cc_state = -1;
+    ensure_jit(e);
+    if (e->jit_state != 1 || !e->multi || e->tile_cc.total > 200 * 1024) return;
+    imxjit::Spec sp;
+    jit_spec(e, e->TL, sp, 1, 1);
+    int smem[imxjit::N_KERNELS] = {e->tile_cc.total, 0, 0, e->pipe_stages * e->tile_cc.total};
+    if (smem[3] > 200 * 1024) smem[3] = 0;
+    e->jit_cc = imxjit::get(sp, smem, e->cfg.device);
+    if (e->jit_cc) e->jit_cc_state = 1;
+}
+
 static bool stream_is_capturing(cudaStream_t s) {
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -332,6 +385,7 @@ static int select_kernels(imx_env* e) {
     // ranges (e.g. 40 envs x 6 nodes x 4 B = 960 B) straddle 128-byte lines, measured slower at 262144 envs;
     // the issue-bound ROLLOUT kernel is specialised with tile width = m (dense lane packing, +21% on div2)
     compute_tile(e, e->tile_jit, e->step_dense ? e->m : m_pad_of(e));
+    compute_tile(e, e->tile_cc, e->step_dense ? e->m : m_pad_of(e), true);
     if (e->tile.total <= 200 * 1024) {
         IMX_CUDA(raise_dyn_smem_limit((const void*)e->tma_fn, (size_t)e->tile.total));
         if (e->tile.total2 <= 200 * 1024)
@@ -350,6 +404,15 @@ static int select_kernels(imx_env* e) {
         e->fuse_periods = (fu && !strcmp(fu, "0")) ? 0 : 1;
         const char* jp = getenv("IMX_JIT");
         e->jit_policy = (jp && !strcmp(jp, "1")) ? 1 : (jp && !strcmp(jp, "0")) ? -1 : 0;
+        const char* pm = getenv("IMX_PIPE");
+        e->pipe_mode = (pm && !strcmp(pm, "1")) ? 1 : (pm && !strcmp(pm, "0")) ? -1 : 0;
+        const char* ps = getenv("IMX_PIPE_STAGES");
+        e->pipe_stages = ps ? atoi(ps) : 4;
+        if (e->pipe_stages < 2 || e->pipe_stages > 8) e->pipe_stages = 4;
+        while (e->pipe_stages > 2 && (int64_t)e->pipe_stages * e->tile_jit.total > 200 * 1024) --e->pipe_stages;
+        const char* pc = getenv("IMX_PIPE_CTAS");
+        e->pipe_ctas = pc ? atoi(pc) : 0;
+        e->sm_count = dev_sms;
     }
     IMX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e->rollout_fn, ROLLOUT_THREADS, 0));
     if (occ < 1) return fail(-4, "rollout kernel does not fit on an SM");
@@ -404,7 +467,8 @@ static int derive(imx_env* e) {
             e->maxc = nc > e->maxc ? nc : e->maxc;
             for (int k = 0; k < nc; ++k) {
                 const int ch = c.children[p][k];
-                if (ch <= p || ch >= m)   // utils.py:87-92
+                if (ch == p) return fail(-1, "node %d lists itself as a child (utils.py:87-92 lets this through; the reference then never terminates its depth walk)", p);
+                if (ch < p || ch >= m)   // utils.py:87-92
                     return fail(-1, "Downstream node cannot have a smaller index number than upstream node (%d -> %d)", p, ch);
                 if (e->parent[ch] != -1) return fail(-1, "node %d has more than one upstream node", ch);
                 e->parent[ch] = p;
@@ -680,7 +744,7 @@ extern "C" int imx_destroy(imx_env* e) {
     if (e->hstream) { cudaStreamSynchronize(e->hstream); cudaStreamDestroy(e->hstream); }
     cudaFree(e->d_nodes); cudaFree(e->d_state); cudaFree(e->d_err);
     cudaFree(e->d_demand_T); cudaFree(e->d_mask_T); cudaFree(e->d_cdf); cudaFree(e->d_guide); cudaFree(e->d_tab); cudaFree(e->d_stats_partial); cudaFree(e->d_returns);
-    cudaFree(e->d_dfo_rewards);
+    cudaFree(e->d_dfo_rewards); cudaFree(e->d_obs_scratch);
     cudaFree(e->d_act_h); cudaFree(e->d_obs_h); cudaFree(e->d_rew_h); cudaFree(e->d_dem_h); cudaFree(e->d_mask_h);
     delete e;
     return 0;
@@ -756,6 +820,8 @@ static DemandGen make_gen(const imx_env* e, uint64_t episode) {
 
 extern "C" int imx_reset(imx_env* e, const int32_t* demand_dev, const uint8_t* delay_mask_dev, int noisy,
                          uint64_t episode, void* obs_dev, void* stream) {
+    IMX_NVTX("imx_reset");
+
     if (!e) return fail(-1, "null env");
     cudaStream_t s = (cudaStream_t)stream;
     IMX_CUDA(cudaSetDevice(e->cfg.device));
@@ -791,11 +857,37 @@ extern "C" int imx_reset(imx_env* e, const int32_t* demand_dev, const uint8_t* d
     return 0;
 }
 
+// Resident CTAs per SM of the pipelined kernel: bounded by shared memory (S stages per CTA), threads, and a cap that
+// keeps enough tiles per CTA for the ring to overlap anything.
+static int pipe_ctas_per_sm(const imx_env* e) {
+    if (e->pipe_ctas > 0) return e->pipe_ctas;
+    const int by_smem = (int)((227 * 1024) / ((int64_t)e->pipe_stages * e->tile_jit.total + 1024));
+    const int by_thr = 2048 / (e->tma_threads + 32);
+    int c = by_smem < by_thr ? by_smem : by_thr;
+    if (c > 4) c = 4;
+    return c < 1 ? 1 : c;
+}
+// auto policy: the pipeline needs more than one tile per resident CTA to overlap anything
+static bool pipe_pays(const imx_env* e, int n_tiles) {
+    return (int64_t)n_tiles > (int64_t)e->sm_count * pipe_ctas_per_sm(e);
+}
+static int pipe_ctas_for(const imx_env* e, const TileLayout& L) {
+    if (e->pipe_ctas > 0) return e->pipe_ctas;
+    const int by_smem = (int)((227 * 1024) / ((int64_t)e->pipe_stages * L.total + 1024));
+    const int by_thr = 2048 / (e->tma_threads + 32);
+    int c = by_smem < by_thr ? by_smem : by_thr;
+    if (c > 4) c = 4;
+    return c < 1 ? 1 : c;
+}
+
 // periods > 1 (imx_step_many): the TMA kernel advances that many periods in one launch with the tiles' state resident
 // in shared memory; *done receives how many periods the call really advanced (1 when the fused form is not applicable:
 // tail tiles, diagnostics, the direct path, a layout that does not fit).
+struct CcOut { void* dev; int fill; double lo, hi; };
+
 static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, double* reward_dev,
-                       const imx_info_out* info, cudaStream_t s, int periods = 1, int* done = nullptr) {
+                       const imx_info_out* info, cudaStream_t s, int periods = 1, int* done = nullptr, const CcOut* cc = nullptr,
+                       bool* cc_fused = nullptr) {
     if (e->t >= e->T) return fail(-6, "step() past the end of the episode (period %d of %d)", e->t, e->T);
     StepArgs A;
     fill_args(e, A);
@@ -818,7 +910,20 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
                            aligned16(reward_dev);
     bool use_jit = false;
     const imxjit::Kernels* jk = nullptr;
-    if (tma_legal && !A.has_info && !A.noisy) {
+    bool with_cc = false;
+    if (cc_fused) *cc_fused = false;
+    if (cc && tma_legal && !A.has_info && !A.noisy && obs_dev && aligned16(cc->dev)) {
+        if (e->jit_cc_state == 0 && !stream_is_capturing(s)) ensure_jit_cc(e);
+        const int64_t whole = (e->N / e->tile_cc.E) * e->tile_cc.E;
+        if (e->jit_cc_state == 1 && whole == e->N) {       // fused only when every env sits in a whole tile (else: unfused fallback)
+            jk = e->jit_cc;
+            use_jit = with_cc = true;
+            A.cc = cc->dev; A.cc_fill = cc->fill; A.cc_lo = cc->lo; A.cc_hi = cc->hi;
+            A.cc_W = (e->m - 1) * (1 + e->O) + e->O;
+            if (cc_fused) *cc_fused = true;
+        }
+    }
+    if (!with_cc && tma_legal && !A.has_info && !A.noisy) {
         // the specialised kernels were loaded by imx_create() / imx_prepare(); the obs-less variant may still be
         // compiled here on first use, but never while the stream is being captured (module loads are not capturable)
         if (obs_dev) { if (e->jit_state == 1) jk = e->jit; }
@@ -829,7 +934,7 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
         }
         use_jit = jk != nullptr;
     }
-    const TileLayout& TL_use = use_jit ? e->tile_jit : e->tile;
+    const TileLayout& TL_use = with_cc ? e->tile_cc : use_jit ? e->tile_jit : e->tile;
     const int epw_direct = 32 / e->m_pad;
     int64_t n_tma = 0;
     if (tma_legal) {
@@ -843,22 +948,33 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
     const unsigned tma_smem = (unsigned)(fused ? TL_use.total2 : TL_use.total);
     if (n_tma > 0) {
         if (use_jit) {
-            void* params[] = {(void*)&A, (void*)&e->tile_jit};
+            // persistent pipelined kernel (imx_step_pipe.cuh): a resident CTA walks over its tiles through a ring of stages
+            PipeArgs PA;
+            PA.n_tiles = (int32_t)(n_tma / TL_use.E);
+            PA.stages = e->pipe_stages;
+            const bool pipe = !fused && jk->step_pipe && e->pipe_mode >= 0 && (e->pipe_mode == 1 || pipe_pays(e, PA.n_tiles));
+            void* params[] = {(void*)&A, (void*)&TL_use, (void*)&PA};
             CUlaunchConfig lc;
             memset(&lc, 0, sizeof(lc));
             lc.gridDimX = (unsigned)(n_tma / TL_use.E); lc.gridDimY = 1; lc.gridDimZ = 1;
             lc.blockDimX = (unsigned)e->tma_threads; lc.blockDimY = 1; lc.blockDimZ = 1;
             lc.sharedMemBytes = tma_smem;
+            if (pipe) {
+                const int64_t resident = (int64_t)e->sm_count * pipe_ctas_for(e, TL_use);
+                lc.gridDimX = (unsigned)(PA.n_tiles < resident ? PA.n_tiles : resident);
+                lc.blockDimX = (unsigned)e->tma_threads + 32;
+                lc.sharedMemBytes = (unsigned)(e->pipe_stages * TL_use.total);
+            }
             lc.hStream = (CUstream)s;
             CUlaunchAttribute at[1];
             at[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
             at[0].value.programmaticStreamSerializationAllowed = 1;
             lc.attrs = at;
             lc.numAttrs = e->use_pdl ? 1 : 0;
-            const CUresult cr = imxjit::g_api.LaunchKernelEx(&lc, fused ? jk->step_many : jk->step, params, nullptr);
+            const CUresult cr = imxjit::g_api.LaunchKernelEx(&lc, pipe ? jk->step_pipe : fused ? jk->step_many : jk->step, params, nullptr);
             if (cr != CUDA_SUCCESS) return fail(-3, "launch of the specialised step kernel failed (CUresult %d)", (int)cr);
             g_launches.fetch_add(1, std::memory_order_relaxed);
-            e->last_variant = 2;
+            e->last_variant = pipe ? 3 : 2;
         } else {
             cudaLaunchConfig_t lc;
             memset(&lc, 0, sizeof(lc));
@@ -891,9 +1007,36 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
 
 extern "C" int imx_step(imx_env* e, const double* actions_dev, void* obs_dev, double* reward_dev,
                         const imx_info_out* info, void* stream) {
+    IMX_NVTX("imx_step");
+
     if (!e || !actions_dev || !reward_dev) return fail(-1, "null argument");
     IMX_CUDA(cudaSetDevice(e->cfg.device));
     return launch_step(e, actions_dev, (double*)obs_dev, reward_dev, info, (cudaStream_t)stream);
+}
+
+// step() that also emits the centralised-critic observation rows.  Fused into the step kernel's epilogue wherever the
+// runtime-specialised TMA kernels serve the whole batch; otherwise the plain step followed by the gather kernel.
+extern "C" int imx_step_cc(imx_env* e, const double* actions_dev, void* obs_dev, void* cc_dev, int fill_actions, double clip_lo,
+                           double clip_hi, double* reward_dev, void* stream) {
+    IMX_NVTX("imx_step_cc");
+
+    if (!e || !actions_dev || !reward_dev || !cc_dev) return fail(-1, "null argument");
+    if (!e->multi) return fail(-1, "the centralised-critic observation is defined for the multi-agent kinds");
+    IMX_CUDA(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    void* obs = obs_dev;
+    if (!obs) {                                              // the rows are built from the observation tile either way
+        if (!e->d_obs_scratch) {
+            if (stream_is_capturing(s)) return fail(-1, "imx_step_cc without obs_dev under stream capture: call imx_prepare(IMX_PREPARE_CC) first");
+            IMX_CUDA(cudaMalloc(&e->d_obs_scratch, (size_t)e->N * e->m * e->O * (e->cfg.obs_f32 ? 4 : 8)));
+        }
+        obs = e->d_obs_scratch;
+    }
+    const CcOut cc = {cc_dev, fill_actions ? 1 : 0, clip_lo, clip_hi};
+    bool fused = false;
+    const int rc = launch_step(e, actions_dev, (double*)obs, reward_dev, nullptr, s, 1, nullptr, &cc, &fused);
+    if (rc || fused) return rc;
+    return imx_cc_observe(e, obs, fill_actions ? actions_dev : nullptr, clip_lo, clip_hi, cc_dev, e->cfg.obs_f32 ? 1 : 0, stream);
 }
 
 static int ensure_host_path(imx_env* e);
@@ -901,10 +1044,14 @@ static int ensure_host_path(imx_env* e);
 extern "C" int imx_prepare(imx_env* e, int flags) {
     if (!e) return fail(-1, "null env");
     IMX_CUDA(cudaSetDevice(e->cfg.device));
-    if (flags == 0) flags = IMX_PREPARE_STEP | IMX_PREPARE_NOOBS | IMX_PREPARE_HOST | IMX_PREPARE_DFO;
+    if (flags == 0) flags = IMX_PREPARE_STEP | IMX_PREPARE_NOOBS | IMX_PREPARE_HOST | IMX_PREPARE_DFO | IMX_PREPARE_CC;
     if (flags & IMX_PREPARE_STEP) ensure_jit(e);
     if (flags & IMX_PREPARE_NOOBS) ensure_jit_noobs(e);
     if (flags & IMX_PREPARE_HOST) { const int rc = ensure_host_path(e); if (rc) return rc; }
+    if ((flags & IMX_PREPARE_CC) && e->multi) {
+        ensure_jit_cc(e);
+        if (!e->d_obs_scratch) IMX_CUDA(cudaMalloc(&e->d_obs_scratch, (size_t)e->N * e->m * e->O * (e->cfg.obs_f32 ? 4 : 8)));
+    }
     if ((flags & IMX_PREPARE_DFO) && !e->multi && !e->d_dfo_rewards)
         IMX_CUDA(cudaMalloc(&e->d_dfo_rewards, (size_t)e->T * e->N * sizeof(double)));
     IMX_CUDA(cudaDeviceSynchronize());
@@ -916,6 +1063,8 @@ extern "C" int imx_prepare(imx_env* e, int flags) {
 // wherever the whole batch goes through the TMA kernel; otherwise K plain launches.  Same results either way.
 extern "C" int imx_step_many(imx_env* e, const double* actions_dev, int K, void* obs_dev, double* reward_dev,
                              const imx_info_out* info, void* stream) {
+    IMX_NVTX("imx_step_many");
+
     if (!e || !actions_dev || !reward_dev) return fail(-1, "null argument");
     if (K < 1) return fail(-1, "K must be >= 1");
     if (e->t + K > e->T) return fail(-6, "imx_step_many: %d periods from period %d run past the end of the episode (%d)", K, e->t, e->T);
@@ -949,6 +1098,8 @@ extern "C" int imx_step_many(imx_env* e, const double* actions_dev, int K, void*
 extern "C" int imx_rollout_basestock(imx_env* e, const double* z_dev, int z_stride, const int32_t* demand_dev,
                                      const uint8_t* delay_mask_dev, int noisy, uint64_t episode, const double* pmf_dev,
                                      double* return_dev, double* step_reward_dev, double* dfo_dev, int write_state, void* stream) {
+    IMX_NVTX("imx_rollout_basestock");
+
     if (!e || !z_dev || !return_dev) return fail(-1, "null argument");
     if (z_stride != 0 && z_stride != e->m) return fail(-1, "z_stride must be 0 or m");
     if (dfo_dev && (!pmf_dev || e->multi)) return fail(-1, "dfo output needs pmf_dev and a single-agent kind");
@@ -1023,6 +1174,8 @@ extern "C" int imx_return_stats(imx_env* e, const double* return_dev, double* st
 
 extern "C" int imx_episode_stats(imx_env* e, const double* step_reward_dev, int periods, double* return_dev, double* stats_dev,
                                  int accumulate, void* stream) {
+    IMX_NVTX("imx_episode_stats");
+
     if (!e || !step_reward_dev || !stats_dev) return fail(-1, "null argument");
     if (periods < 1) return fail(-1, "periods must be >= 1");
     IMX_CUDA(cudaSetDevice(e->cfg.device));
@@ -1099,6 +1252,8 @@ static int ensure_host_path(imx_env* e) {
 
 extern "C" int imx_reset_host(imx_env* e, const int32_t* demand_host, const uint8_t* delay_mask_host, int noisy,
                               uint64_t episode, void* obs_host) {
+    IMX_NVTX("imx_reset_host");
+
     if (!e) return fail(-1, "null env");
     IMX_CUDA(cudaSetDevice(e->cfg.device));
     int rc = ensure_host_path(e);
@@ -1129,6 +1284,8 @@ static void* pinned_alias(const void* host_ptr) {
 }
 
 extern "C" int imx_step_host(imx_env* e, const double* actions_host, void* obs_host, double* reward_host) {
+    IMX_NVTX("imx_step_host");
+
     if (!e || !actions_host || !reward_host) return fail(-1, "null argument");
     IMX_CUDA(cudaSetDevice(e->cfg.device));
     int rc = ensure_host_path(e);
@@ -1177,8 +1334,9 @@ extern "C" int imx_poisson_cdf(const imx_env* e, double* out, int cap) {
 extern "C" int imx_kernel_variant(const imx_env* e) { return e ? e->last_variant : fail(-1, "null env"); }
 extern "C" const char* imx_jit_log(void) { return imxjit::g_last_log.c_str(); }
 
-extern "C" int imx_jit_compile_check(const imx_config* cfg, char* log, int cap) {
+extern "C" int imx_jit_compile_check(const imx_config* cfg, int variant, char* log, int cap) {
     if (!cfg) return fail(-1, "null argument");
+    if (variant < 0 || variant > 2) return fail(-1, "variant must be 0 (step), 1 (no observations) or 2 (critic rows)");
     imx_env tmp;
     tmp.cfg = *cfg;
     const int rc = derive(&tmp);
@@ -1186,10 +1344,12 @@ extern "C" int imx_jit_compile_check(const imx_config* cfg, char* log, int cap) 
     tmp.tma_threads = choose_tma_threads(&tmp);
     compute_tile(&tmp, tmp.tile, m_pad_of(&tmp));
     compute_tile(&tmp, tmp.tile_jit, m_pad_of(&tmp));
+    compute_tile(&tmp, tmp.tile_cc, m_pad_of(&tmp), true);
     int TL = 0;
     build_tables(&tmp, &TL);
     imxjit::Spec sp;
-    jit_spec(&tmp, TL, sp);
+    if (variant == 2 && !tmp.multi) return fail(-1, "the critic rows exist for the multi-agent kinds only");
+    jit_spec(&tmp, TL, sp, variant == 1 ? 0 : 1, variant == 2 ? 1 : 0);
     std::string lg;
     std::vector<char> cubin;
     const size_t n = imxjit::compile_only(sp, lg, &cubin);

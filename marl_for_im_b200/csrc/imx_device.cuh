@@ -28,6 +28,10 @@ typedef unsigned long uintptr_t;
 #define KBMA_POW2 (IMX_K_bma_pow2)
 #define KM_POW2 (IMX_K_m_pow2)
 #define KNOISY_DEMAND(g) (IMX_K_noisy_demand)
+#ifndef IMX_K_has_cc
+#define IMX_K_has_cc 0
+#define IMX_KT_off_cc 0
+#endif
 #else
 #define KF(name) (A.name)
 #define KT(name) (TLY.name)
@@ -140,6 +144,12 @@ struct StepArgs {
     int64_t act_stride;                     // doubles between consecutive periods' action blocks
     int64_t obs_stride_bytes;               // bytes between consecutive periods' observation blocks
     int64_t rew_stride;                     // doubles between consecutive periods' reward blocks
+    // centralised-critic observation emitted by the step itself (imx_step_cc; models/CC_Model.py:165-214): for every agent the
+    // row [opponent actions (m-1) | opponent observations (m-1)*O | own observation O], in the observation element type
+    void* __restrict__ cc;                  // [N][m][W] or nullptr
+    int32_t cc_fill;                        // 1: opponent-action slots = clip(this step's actions, cc_lo, cc_hi); 0: zeros
+    int32_t cc_W;                           // (m-1)*(1+O) + O
+    double cc_lo, cc_hi;
 };
 
 // ------------------------------------------------------------------------------------
@@ -173,10 +183,23 @@ __device__ __forceinline__ int decode_order(double x, double om, bool std_action
 // unfulfilled orders by inv_max, capped backlog and demand by demand_max, pipeline entries by
 // 2*max(demand_max) + children), so the host precomputes a + (v*(b-a))/max for every v with the same
 // IEEE operations and the kernel replaces an FP64 division by one cached 8-byte load.
+// CHECKED (reset kernel: init_inv is an arbitrary config value and the reference does not clip it before the first
+// observation): a value outside the table is computed with the three IEEE operations instead.  Unchecked (step / rollout
+// kernels: every value is bounded by construction): the index is clamped for memory safety only;
+// -DIMX_DEBUG_BOUNDS turns an out-of-table value into a trap.
 enum : int { TAB_INV = 0, TAB_ORD = 1, TAB_DEM = 2, TAB_PIPE2 = 3 };
+template <bool CHECKED = false>
 __device__ __forceinline__ double scaled(bool has_tab, const double* __restrict__ tabrow, int TL, int which, int v,
                                          double vmax, double a, double bma) {
-    if (has_tab) return __ldg(tabrow + which * TL + (int)min((unsigned)v, (unsigned)(TL - 1)));
+    if (has_tab) {
+        if (CHECKED) {
+            if ((unsigned)v >= (unsigned)TL) return rescale((double)v, vmax, a, bma);
+        }
+#ifdef IMX_DEBUG_BOUNDS
+        if ((unsigned)v >= (unsigned)TL) __trap();
+#endif
+        return __ldg(tabrow + which * TL + (int)min((unsigned)v, (unsigned)(TL - 1)));
+    }
     return rescale((double)v, vmax, a, bma);
 }
 // mean of the shared reward: reward_sum / num_stages (MAIM_env.py:434)

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
             for (int k = 0; k < DMAX; ++k) pipe[k] = 0;
 #pragma unroll
             for (int j = 0; j < PMAX; ++j) { hd[j] = 0; ho[j] = 0; }
-            write_obs_row<DMAX, PMAX>(reinterpret_cast<unsigned char*>(s_tmpl) + (size_t)i * O * es, A, np, i, A.tab ? A.tab + (size_t)i * 4 * A.TL : nullptr, np.init_inv, 0, 0, pipe, hd,
+            write_obs_row<DMAX, PMAX, true>(reinterpret_cast<unsigned char*>(s_tmpl) + (size_t)i * O * es, A, np, i, A.tab ? A.tab + (size_t)i * 4 * A.TL : nullptr, np.init_inv, 0, 0, pipe, hd,
                                       ho, div != 0);
         }
     }

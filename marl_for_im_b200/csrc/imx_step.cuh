@@ -211,7 +211,7 @@ __device__ __forceinline__ int split_ship(int nchild, int ship, int demand, int 
 
 // Writes one agent's observation vector (O doubles) — the field order and per-field maxima of
 // SURVEY.md table A.5.  `row` points into the warp's shared-memory staging tile.
-template <int DMAX, int PMAX>
+template <int DMAX, int PMAX, bool CHECKED = false>
 __device__ __forceinline__ void write_obs_row(void* row, const StepArgs& A, const NodeParams& np, int node_idx,
                                               const double* __restrict__ tabrow, int inv, int backlog, int order_u,
                                               const int (&pipe)[DMAX], const int (&hd)[PMAX], const int (&ho)[PMAX], bool div) {
@@ -221,9 +221,9 @@ __device__ __forceinline__ void write_obs_row(void* row, const StepArgs& A, cons
     const double dem_max = (double)np.demand_max;
     const double ou_max = KF(multi) ? order_max : inv_max;   // MAIM_env.py:300 vs IM_env.py:265
     if (KF(std_state)) {
-        OBS_PUT(row, 0, scaled(KHAS(tab), tabrow, TL, TAB_INV, inv, inv_max, a, bma));
-        OBS_PUT(row, 1, scaled(KHAS(tab), tabrow, TL, TAB_DEM, backlog, dem_max, a, bma));
-        OBS_PUT(row, 2, scaled(KHAS(tab), tabrow, TL, KF(multi) ? TAB_ORD : TAB_INV, order_u, ou_max, a, bma));
+        OBS_PUT(row, 0, scaled<CHECKED>(KHAS(tab), tabrow, TL, TAB_INV, inv, inv_max, a, bma));
+        OBS_PUT(row, 1, scaled<CHECKED>(KHAS(tab), tabrow, TL, TAB_DEM, backlog, dem_max, a, bma));
+        OBS_PUT(row, 2, scaled<CHECKED>(KHAS(tab), tabrow, TL, KF(multi) ? TAB_ORD : TAB_INV, order_u, ou_max, a, bma));
     } else {
         OBS_PUT(row, 0, (double)inv);
         OBS_PUT(row, 1, (double)backlog);
@@ -243,13 +243,13 @@ __device__ __forceinline__ void write_obs_row(void* row, const StepArgs& A, cons
     if (KF(pd)) {
 #pragma unroll
         for (int j = 0; j < PMAX; ++j)
-            if (j < KF(P)) OBS_PUT(row, k0 + j, KF(write_hd) ? scaled(KHAS(tab), tabrow, TL, TAB_DEM, hd[j], dem_max, a, bma) : 0.0);   // quirk 2
+            if (j < KF(P)) OBS_PUT(row, k0 + j, KF(write_hd) ? scaled<CHECKED>(KHAS(tab), tabrow, TL, TAB_DEM, hd[j], dem_max, a, bma) : 0.0);   // quirk 2
         k0 += KF(P);
     }
     if (KF(pa)) {
 #pragma unroll
         for (int j = 0; j < PMAX; ++j)
-            if (j < KF(P)) OBS_PUT(row, k0 + j, scaled(KHAS(tab), tabrow, TL, TAB_ORD, ho[j], order_max, a, bma));
+            if (j < KF(P)) OBS_PUT(row, k0 + j, scaled<CHECKED>(KHAS(tab), tabrow, TL, TAB_ORD, ho[j], order_max, a, bma));
         k0 += KF(P);
     }
     if (KF(td)) {
@@ -258,8 +258,8 @@ __device__ __forceinline__ void write_obs_row(void* row, const StepArgs& A, cons
             if (k < KF(D)) {
                 double v;
                 if (!KF(std_state)) v = (double)pipe[k];                                    // IM kinds, raw
-                else if (div && KF(multi)) v = scaled(KHAS(tab), tabrow, TL, TAB_PIPE2, min(pipe[k], 2 * np.inv_max), 2.0 * inv_max, a, bma);   // MAIM_div_env.py:408-411
-                else v = scaled(KHAS(tab), tabrow, TL, TAB_INV, pipe[k], inv_max, a, bma);
+                else if (div && KF(multi)) v = scaled<CHECKED>(KHAS(tab), tabrow, TL, TAB_PIPE2, min(pipe[k], 2 * np.inv_max), 2.0 * inv_max, a, bma);   // MAIM_div_env.py:408-411
+                else v = scaled<CHECKED>(KHAS(tab), tabrow, TL, TAB_INV, pipe[k], inv_max, a, bma);
                 OBS_PUT(row, k0 + k, v);
             }
         }

@@ -36,6 +36,7 @@ struct TileLayout {
     // second buffers of the per-period inputs (actions, demand), used by multi-period launches
     int32_t off_act2, off_dem2;
     int32_t total2;            // dynamic shared memory bytes of a multi-period launch (second buffers sit behind `total`)
+    int32_t off_cc;            // centralised-critic rows [E][m][W] (layouts built for imx_step_cc only; inside `total`)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -119,109 +120,69 @@ __device__ __forceinline__ void store_row_rotated(unsigned char* dst, const unsi
 }
 #endif
 
-// MANY = false: one period per launch (the loop below folds away); MANY = true: A.periods periods per launch with the
-// tile's state resident in shared memory (imx_step_many) — separate kernels because the loop costs registers.
-template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV, bool MANY>
-__device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& TLY) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar[2];         // bar[b]: inputs of the periods with parity b (bar[0] also the state)
+// Shared-memory views of ONE tile for ONE period (all regions laid out like the global arrays: [E][m] etc.).
+struct TileSmem {
+    const double* act;          // [E][m] actions of this period (consumed first; afterwards scratch for the shared reward)
+    const int32_t* dem;         // [R][E] customer demand of this period
+    int32_t *inv, *bl, *ou, *pipe, *hd, *ho, *carry, *bt;   // state, updated in place
+    unsigned char* obs;         // [E][m][O] observation tile (float64 or float32)
+    double* rew;                // [E][m] / [E] reward tile
+};
 
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    // M_PAD is the tile width: a power of two >= m in the ahead-of-time build, exactly m in the
-    // runtime-specialised build (dense packing: 32 / m envs per warp, e.g. 5 instead of 4 for m = 6)
-    constexpr int EPW = 32 / M_PAD;
-    const int i = lane % M_PAD;                      // stage / node of this lane
-    const int sub = lane / M_PAD;                    // env slot inside the warp
-    const int tbase = lane - i;                      // first lane of this env's tile
-    const int e_loc = (tid >> 5) * EPW + sub;        // env inside the CTA tile
-    const int m = KF(m), O = KF(O), E = KT(E);
-    const bool ok = i < m && sub < EPW;               // full tiles only: every env slot is live
-    const int cell = e_loc * m + i;                  // index inside a [E][m] tile
-    const int64_t n0 = (int64_t)blockIdx.x * E;      // first env of the tile
-    const int K = MANY ? A.periods : 1;              // periods this launch advances
-
-    int32_t* s_inv = reinterpret_cast<int32_t*>(smem + KT(off_inv));
-    int32_t* s_bl = reinterpret_cast<int32_t*>(smem + KT(off_bl));
-    int32_t* s_ou = reinterpret_cast<int32_t*>(smem + KT(off_ou));
-    int32_t* s_pipe = reinterpret_cast<int32_t*>(smem + KT(off_pipe));
-    int32_t* s_hd = reinterpret_cast<int32_t*>(smem + KT(off_hd));
-    int32_t* s_ho = reinterpret_cast<int32_t*>(smem + KT(off_ho));
-    int32_t* s_carry = reinterpret_cast<int32_t*>(smem + KT(off_carry));
-    int32_t* s_bt = reinterpret_cast<int32_t*>(smem + KT(off_bt));
-    const int es = KF(obs_f32) ? 4 : 8;              // observation element size
-
-    const uint32_t b_cell4 = (uint32_t)E * m * 4u, b_cell8 = (uint32_t)E * m * 8u;
-    const uint32_t b_pipe = (uint32_t)E * KF(L) * 4u, b_hist = b_cell4 * (uint32_t)KF(P);
-    const uint32_t b_bt = (uint32_t)E * KF(NB) * 4u, b_dem = (uint32_t)E * 4u;
-    const uint32_t b_in = b_cell8 + (uint32_t)KF(R) * b_dem;       // per-period inputs: actions + demand rows
-
-    // per-period inputs of period j (actions block j, demand rows of period t0 + j) into input buffer j & 1
-    auto load_inputs = [&](int j) {
-        double* sa = reinterpret_cast<double*>(smem + ((j & 1) ? KT(off_act2) : KT(off_act)));
-        int32_t* sd = reinterpret_cast<int32_t*>(smem + ((j & 1) ? KT(off_dem2) : KT(off_dem)));
-        bulk_load_g2s(sa, A.actions + (int64_t)j * A.act_stride + n0 * m, b_cell8, &bar[j & 1]);
-        for (int r = 0; r < KF(R); ++r)
-            bulk_load_g2s(sd + r * E, A.demand_T + ((int64_t)(A.t + j) * KF(R) + r) * A.N + n0, b_dem, &bar[j & 1]);
-    };
-
-    pdl_launch_dependents();
-    if (tid == 0) {                                  // on the critical path of the tile: one barrier for a plain step
-        mbar_init(&bar[0], 1);
-        if (MANY) mbar_init(&bar[1], 1);
-        mbar_init_fence();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        pdl_wait();                                  // state written by the previous step must be complete and visible
-        uint32_t bytes = b_in + 3u * b_cell4 + b_pipe;
-        if (KF(need_hd)) bytes += b_hist;
-        if (KF(need_ho)) bytes += b_hist;
-        if (KF(has_carry)) bytes += b_cell4;
-        if (DIV && KF(NB) > 0) bytes += b_bt;
-        mbar_expect_tx(&bar[0], bytes);
-        load_inputs(0);
-        bulk_load_g2s(s_inv, A.inv + n0 * m, b_cell4, &bar[0]);
-        bulk_load_g2s(s_bl, A.backlog + n0 * m, b_cell4, &bar[0]);
-        bulk_load_g2s(s_ou, A.order_u + n0 * m, b_cell4, &bar[0]);
-        bulk_load_g2s(s_pipe, A.pipe + n0 * KF(L), b_pipe, &bar[0]);
-        if (KF(need_hd)) bulk_load_g2s(s_hd, A.hist_d + n0 * m * KF(P), b_hist, &bar[0]);
-        if (KF(need_ho)) bulk_load_g2s(s_ho, A.hist_o + n0 * m * KF(P), b_hist, &bar[0]);
-        if (KF(has_carry)) bulk_load_g2s(s_carry, A.carry + n0 * m, b_cell4, &bar[0]);
-        if (DIV && KF(NB) > 0) bulk_load_g2s(s_bt, A.bt + n0 * KF(NB), b_bt, &bar[0]);
-        if (K > 1) {                                 // period 1's inputs land while period 0 computes
-            mbar_expect_tx(&bar[1], b_in);
-            load_inputs(1);
-        }
-    }
-
-    // per-lane constants (overlaps the bulk loads)
-    const NodeParams np = load_node(A.nodes + (ok ? i : 0));
+// Per-thread constants of the lanes = stages mapping.
+template <int MAXC>
+struct LaneCtx {
+    NodeParams np;
     int child_lane[MAXC];
+    const double* tabrow;
+    int lane, i, tbase, e_loc, cell;
+    bool ok, is_last;
+};
+
+template <int M_PAD, int MAXC, bool DIV>
+__device__ __forceinline__ LaneCtx<MAXC> make_lane_ctx(const StepArgs& A, int tid) {
+    constexpr int EPW = 32 / M_PAD;
+    LaneCtx<MAXC> L;
+    L.lane = tid & 31;
+    L.i = L.lane % M_PAD;                             // stage / node of this lane
+    const int sub = L.lane / M_PAD;                   // env slot inside the warp
+    L.tbase = L.lane - L.i;                           // first lane of this env's tile
+    L.e_loc = (tid >> 5) * EPW + sub;                 // env inside the CTA tile
+    const int m = KF(m);
+    L.ok = L.i < m && sub < EPW;                      // full tiles only: every env slot is live
+    L.cell = L.e_loc * m + L.i;                       // index inside a [E][m] tile
+    L.np = load_node(A.nodes + (L.ok ? L.i : 0));
     if constexpr (DIV) {
 #pragma unroll
-        for (int k = 0; k < MAXC; ++k)
-            child_lane[k] = ok ? child_lane_of(np, k) : -1;
+        for (int k = 0; k < MAXC; ++k) L.child_lane[k] = L.ok ? child_lane_of(L.np, k) : -1;
+    } else {
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) L.child_lane[k] = -1;
     }
-    const bool is_last = (i == m - 1);
+    L.is_last = (L.i == m - 1);
+    L.tabrow = KHAS(tab) ? A.tab + (size_t)(L.ok ? L.i : 0) * 4 * KF(TL) : nullptr;
+    return L;
+}
+
+// ONE period of ONE tile out of shared memory: read the lane's cell, the period's arithmetic (identical to step_kernel),
+// write the new state in place and the observation / reward tiles.  `before_store` runs between the arithmetic and the
+// writes (a multi-period launch waits there for the previous period's bulk stores).  No barriers or fences in here:
+// the caller orders the tile's loads before and its stores after.
+//   j = period index inside the launch (diagnostics block, MANY only), t = period being simulated, n0 = first env of the tile
+template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV, bool MANY, typename BeforeStore>
+__device__ __forceinline__ void tile_period(const StepArgs& A, const TileLayout& TLY, const TileSmem& S, const LaneCtx<MAXC>& L,
+                                            int t, int j, int64_t n0, bool delayed, BeforeStore&& before_store) {
+    const NodeParams& np = L.np;
+    const int lane = L.lane, i = L.i, tbase = L.tbase, e_loc = L.e_loc, cell = L.cell;
+    const bool ok = L.ok, is_last = L.is_last;
+    const int m = KF(m), O = KF(O), E = KT(E);
+    const int es = KF(obs_f32) ? 4 : 8;              // observation element size
     const int delay_m1 = np.delay - 1;
     const double om_d = (double)np.order_max;
-    const double* __restrict__ tabrow = KHAS(tab) ? A.tab + (size_t)(ok ? i : 0) * 4 * KF(TL) : nullptr;
-    int32_t* my_pipe = s_pipe + e_loc * KF(L) + np.pipe_off;
-    pdl_wait();
-
-    for (int j = 0; j < K; ++j) {
-    const int t = A.t + j;                           // period being simulated
-    const int b = j & 1;
-    const double* s_act = reinterpret_cast<const double*>(smem + (b ? KT(off_act2) : KT(off_act)));
-    const int32_t* s_dem = reinterpret_cast<const int32_t*>(smem + (b ? KT(off_dem2) : KT(off_dem)));
-    unsigned char* s_obs = smem + KT(off_obs);       // ONE output buffer: period j - 1's bulk stores have long finished
-    double* s_rew = reinterpret_cast<double*>(smem + KT(off_rew));   // reading it when period j's dynamics are done (waited below)
-    bool delayed = false;
-    if (KF(noisy) && ok) delayed = A.mask_T[((int64_t)t * A.N + n0 + e_loc) * m + i] != 0;
-
-    mbar_wait(&bar[b], (uint32_t)((j >> 1) & 1));
-
+    const double* __restrict__ tabrow = L.tabrow;
+    int32_t* my_pipe = S.pipe + e_loc * KF(L) + np.pipe_off;
+    const double* s_act = S.act;
+    (void)lane; (void)E; (void)O; (void)es; (void)s_act;
     // ---- read the tile ----------------------------------------------------------------------
     double act = 0.0;
     int inv = 0, backlog = 0, order_u = 0, carry = 0, cust = 0;
@@ -233,30 +194,30 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
 #pragma unroll
     for (int k = 0; k < MAXC; ++k) bt[k] = 0;
     if (ok) {
-        act = s_act[cell];
-        inv = s_inv[cell];
-        backlog = s_bl[cell];
-        order_u = s_ou[cell];
+        act = S.act[cell];
+        inv = S.inv[cell];
+        backlog = S.bl[cell];
+        order_u = S.ou[cell];
 #pragma unroll
         for (int k = 0; k < DMAX; ++k)
             if (k < np.delay) pipe[k] = my_pipe[k];
         if (KF(need_hd)) {
 #pragma unroll
             for (int jj = 0; jj < PMAX; ++jj)
-                if (jj < KF(P)) hd[jj] = s_hd[cell * KF(P) + jj];
+                if (jj < KF(P)) hd[jj] = S.hd[cell * KF(P) + jj];
         }
         if (KF(need_ho)) {
 #pragma unroll
             for (int jj = 0; jj < PMAX; ++jj)
-                if (jj < KF(P)) ho[jj] = s_ho[cell * KF(P) + jj];
+                if (jj < KF(P)) ho[jj] = S.ho[cell * KF(P) + jj];
         }
-        if (np.retailer_idx >= 0) cust = s_dem[np.retailer_idx * E + e_loc];
-        if (KF(has_carry)) carry = s_carry[cell];
+        if (np.retailer_idx >= 0) cust = S.dem[np.retailer_idx * E + e_loc];
+        if (KF(has_carry)) carry = S.carry[cell];
         if constexpr (DIV) {
             if (np.bt_off >= 0) {
 #pragma unroll
                 for (int k = 0; k < MAXC; ++k)
-                    if (k < np.nchild) bt[k] = s_bt[e_loc * KF(NB) + np.bt_off + k];
+                    if (k < np.nchild) bt[k] = S.bt[e_loc * KF(NB) + np.bt_off + k];
             }
         }
     }
@@ -271,8 +232,8 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
         for (int k = 0; k < MAXC; ++k) {
             od[k] = 0;
             if (k < KF(maxc)) {
-                const int v = __shfl_sync(0xffffffffu, order, tbase + (child_lane[k] < 0 ? 0 : child_lane[k]));
-                od[k] = child_lane[k] < 0 ? 0 : v;
+                const int v = __shfl_sync(0xffffffffu, order, tbase + (L.child_lane[k] < 0 ? 0 : L.child_lane[k]));
+                od[k] = L.child_lane[k] < 0 ? 0 : v;
                 sum += od[k];
             }
         }
@@ -336,7 +297,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
             // shared reward: the env's m profits meet in ITS row of this period's ACTION tile — already consumed, same
             // [E][m] float64 shape, refilled only after the CTA barrier below — one 8-byte store per lane, then 16-byte
             // broadcast loads, instead of 2 m shuffles
-            double* scratch = const_cast<double*>(s_act);
+            double* scratch = const_cast<double*>(S.act);
             if (ok) scratch[cell] = profit;
             __syncwarp();
             const double* row = scratch + e_loc * m;
@@ -356,38 +317,35 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
     }
 
     // ---- write the tile back (in place) ----------------------------------------------------------
-    if (MANY && j > 0) {                             // the previous period's stores must be done reading the output buffer
-        if (tid == 0) bulk_wait_read_all();
-        __syncthreads();
-    }
+    before_store();                                  // e.g. the previous period's bulk stores must be done reading the output buffer
     if (ok) {
-        s_inv[cell] = inv_new;
-        s_bl[cell] = backlog_new;
-        s_ou[cell] = order_u_new;
+        S.inv[cell] = inv_new;
+        S.bl[cell] = backlog_new;
+        S.ou[cell] = order_u_new;
 #pragma unroll
         for (int k = 0; k < DMAX; ++k)
             if (k < np.delay) my_pipe[k] = pipe[k];
         if (KF(need_hd)) {
 #pragma unroll
             for (int jj = 0; jj < PMAX; ++jj)
-                if (jj < KF(P)) s_hd[cell * KF(P) + jj] = hd[jj];
+                if (jj < KF(P)) S.hd[cell * KF(P) + jj] = hd[jj];
         }
         if (KF(need_ho)) {
 #pragma unroll
             for (int jj = 0; jj < PMAX; ++jj)
-                if (jj < KF(P)) s_ho[cell * KF(P) + jj] = ho[jj];
+                if (jj < KF(P)) S.ho[cell * KF(P) + jj] = ho[jj];
         }
-        if (KF(has_carry)) s_carry[cell] = carry_new;
+        if (KF(has_carry)) S.carry[cell] = carry_new;
         if constexpr (DIV) {
             if (np.bt_off >= 0) {
 #pragma unroll
                 for (int k = 0; k < MAXC; ++k)
-                    if (k < np.nchild) s_bt[e_loc * KF(NB) + np.bt_off + k] = bt[k];
+                    if (k < np.nchild) S.bt[e_loc * KF(NB) + np.bt_off + k] = bt[k];
             }
             if (err_code != 0) A.err[n0 + e_loc] = err_code;
         }
-        if (KF(multi)) s_rew[cell] = reward_out;
-        else if (i == 0) s_rew[e_loc] = reward_out;
+        if (KF(multi)) S.rew[cell] = reward_out;
+        else if (i == 0) S.rew[e_loc] = reward_out;
 #ifdef IMX_OBS_ROTATE
         {
             if (KHAS(obs)) {
@@ -405,11 +363,11 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
 #pragma unroll
                     for (int k = 0; k < OBS_ROW_BYTES / 8; ++k) w[k] = (unsigned long long)__double_as_longlong(rowd[k]);
                 }
-                store_row_rotated(s_obs + (size_t)cell * OBS_ROW_BYTES, w, lane);
+                store_row_rotated(S.obs + (size_t)cell * OBS_ROW_BYTES, w, lane);
             }
         }
 #else
-        if (KHAS(obs)) write_obs_row<DMAX, PMAX>(s_obs + (size_t)cell * O * es, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
+        if (KHAS(obs)) write_obs_row<DMAX, PMAX>(S.obs + (size_t)cell * O * es, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
 #endif
         // optional diagnostics go straight to global memory (off the fast path)
         if (KF(has_info)) {
@@ -421,9 +379,143 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
         if (A.info.profit_dev) A.info.profit_dev[gcell] = profit;
         }
     }
+}
+
+// Centralised-critic rows of one tile (imx_step_cc): lane (env e, agent i) assembles
+//     [ opponent actions (m-1) | opponent observations (m-1)*O | own observation O ]        models/CC_Model.py:196-214
+// from the observation tile the step has just written (all m rows of an env are written by lanes of ONE warp: the caller
+// separates the two phases with __syncwarp) and from the action tile of this period (FillInActions :165-193 /
+// CC_inv_management.py:516-528: opponent actions clipped to [lo, hi]; zeros at sampling time).  Opponents in agent order.
+template <typename ObsT, int MAXC>
+__device__ __forceinline__ void cc_build_row(const StepArgs& A, const TileSmem& S, unsigned char* cc_tile, const LaneCtx<MAXC>& L) {
+    if (!L.ok) return;
+    const int m = KF(m), O = KF(O);
+    const int W = (m - 1) * (1 + O) + O;
+    const int e0 = L.e_loc * m;
+    ObsT* row = reinterpret_cast<ObsT*>(cc_tile) + (size_t)L.cell * W;
+    const ObsT* ob = reinterpret_cast<const ObsT*>(S.obs);
+    int k = 0;
+    for (int j = 0; j < m; ++j) {
+        if (j == L.i) continue;
+        row[k++] = A.cc_fill ? (ObsT)fmin(fmax(S.act[e0 + j], A.cc_lo), A.cc_hi) : (ObsT)0;
+    }
+    for (int j = 0; j < m; ++j) {
+        if (j == L.i) continue;
+        const ObsT* src = ob + (size_t)(e0 + j) * O;
+        for (int q = 0; q < O; ++q) row[k++] = src[q];
+    }
+    const ObsT* own = ob + (size_t)L.cell * O;
+    for (int q = 0; q < O; ++q) row[k++] = own[q];
+}
+template <int MAXC>
+__device__ __forceinline__ void cc_build(const StepArgs& A, const TileLayout& TLY, const TileSmem& S, unsigned char* tile_base, const LaneCtx<MAXC>& L) {
+    __syncwarp();                                    // the env's m observation rows are complete
+    if (KF(obs_f32)) cc_build_row<float, MAXC>(A, S, tile_base + KT(off_cc), L);
+    else cc_build_row<double, MAXC>(A, S, tile_base + KT(off_cc), L);
+}
+
+// MANY = false: one period per launch (the loop below folds away); MANY = true: A.periods periods per launch with the
+// tile's state resident in shared memory (imx_step_many) — separate kernels because the loop costs registers.
+template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV, bool MANY>
+__device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& TLY) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar[2];         // bar[b]: inputs of the periods with parity b (bar[0] also the state)
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    // M_PAD is the tile width: a power of two >= m in the ahead-of-time build, exactly m in the
+    // runtime-specialised build (dense packing: 32 / m envs per warp, e.g. 5 instead of 4 for m = 6)
+    constexpr int EPW = 32 / M_PAD;
+    const int i = lane % M_PAD;                      // stage / node of this lane
+    const int sub = lane / M_PAD;                    // env slot inside the warp
+    const int e_loc = (tid >> 5) * EPW + sub;        // env inside the CTA tile
+    const int m = KF(m), O = KF(O), E = KT(E);
+    const bool ok = i < m && sub < EPW;               // full tiles only: every env slot is live
+    const int64_t n0 = (int64_t)blockIdx.x * E;      // first env of the tile
+    const int K = MANY ? A.periods : 1;              // periods this launch advances
+
+    int32_t* s_inv = reinterpret_cast<int32_t*>(smem + KT(off_inv));
+    int32_t* s_bl = reinterpret_cast<int32_t*>(smem + KT(off_bl));
+    int32_t* s_ou = reinterpret_cast<int32_t*>(smem + KT(off_ou));
+    int32_t* s_pipe = reinterpret_cast<int32_t*>(smem + KT(off_pipe));
+    int32_t* s_hd = reinterpret_cast<int32_t*>(smem + KT(off_hd));
+    int32_t* s_ho = reinterpret_cast<int32_t*>(smem + KT(off_ho));
+    int32_t* s_carry = reinterpret_cast<int32_t*>(smem + KT(off_carry));
+    int32_t* s_bt = reinterpret_cast<int32_t*>(smem + KT(off_bt));
+    const int es = KF(obs_f32) ? 4 : 8;              // observation element size
+
+    const uint32_t b_cell4 = (uint32_t)E * m * 4u, b_cell8 = (uint32_t)E * m * 8u;
+    const uint32_t b_pipe = (uint32_t)E * KF(L) * 4u, b_hist = b_cell4 * (uint32_t)KF(P);
+    const uint32_t b_bt = (uint32_t)E * KF(NB) * 4u, b_dem = (uint32_t)E * 4u;
+    const uint32_t b_in = b_cell8 + (uint32_t)KF(R) * b_dem;       // per-period inputs: actions + demand rows
+
+    // per-period inputs of period j (actions block j, demand rows of period t0 + j) into input buffer j & 1
+    auto load_inputs = [&](int j) {
+        double* sa = reinterpret_cast<double*>(smem + ((j & 1) ? KT(off_act2) : KT(off_act)));
+        int32_t* sd = reinterpret_cast<int32_t*>(smem + ((j & 1) ? KT(off_dem2) : KT(off_dem)));
+        bulk_load_g2s(sa, A.actions + (int64_t)j * A.act_stride + n0 * m, b_cell8, &bar[j & 1]);
+        for (int r = 0; r < KF(R); ++r)
+            bulk_load_g2s(sd + r * E, A.demand_T + ((int64_t)(A.t + j) * KF(R) + r) * A.N + n0, b_dem, &bar[j & 1]);
+    };
+
+    pdl_launch_dependents();
+    if (tid == 0) {                                  // on the critical path of the tile: one barrier for a plain step
+        mbar_init(&bar[0], 1);
+        if (MANY) mbar_init(&bar[1], 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        pdl_wait();                                  // state written by the previous step must be complete and visible
+        uint32_t bytes = b_in + 3u * b_cell4 + b_pipe;
+        if (KF(need_hd)) bytes += b_hist;
+        if (KF(need_ho)) bytes += b_hist;
+        if (KF(has_carry)) bytes += b_cell4;
+        if (DIV && KF(NB) > 0) bytes += b_bt;
+        mbar_expect_tx(&bar[0], bytes);
+        load_inputs(0);
+        bulk_load_g2s(s_inv, A.inv + n0 * m, b_cell4, &bar[0]);
+        bulk_load_g2s(s_bl, A.backlog + n0 * m, b_cell4, &bar[0]);
+        bulk_load_g2s(s_ou, A.order_u + n0 * m, b_cell4, &bar[0]);
+        bulk_load_g2s(s_pipe, A.pipe + n0 * KF(L), b_pipe, &bar[0]);
+        if (KF(need_hd)) bulk_load_g2s(s_hd, A.hist_d + n0 * m * KF(P), b_hist, &bar[0]);
+        if (KF(need_ho)) bulk_load_g2s(s_ho, A.hist_o + n0 * m * KF(P), b_hist, &bar[0]);
+        if (KF(has_carry)) bulk_load_g2s(s_carry, A.carry + n0 * m, b_cell4, &bar[0]);
+        if (DIV && KF(NB) > 0) bulk_load_g2s(s_bt, A.bt + n0 * KF(NB), b_bt, &bar[0]);
+        if (K > 1) {                                 // period 1's inputs land while period 0 computes
+            mbar_expect_tx(&bar[1], b_in);
+            load_inputs(1);
+        }
+    }
+
+    // per-lane constants (overlaps the bulk loads)
+    const LaneCtx<MAXC> L = make_lane_ctx<M_PAD, MAXC, DIV>(A, tid);
+    pdl_wait();
+
+    for (int j = 0; j < K; ++j) {
+    const int t = A.t + j;                           // period being simulated
+    const int b = j & 1;
+    const double* s_act = reinterpret_cast<const double*>(smem + (b ? KT(off_act2) : KT(off_act)));
+    const int32_t* s_dem = reinterpret_cast<const int32_t*>(smem + (b ? KT(off_dem2) : KT(off_dem)));
+    unsigned char* s_obs = smem + KT(off_obs);       // ONE output buffer: period j - 1's bulk stores have long finished
+    double* s_rew = reinterpret_cast<double*>(smem + KT(off_rew));   // reading it when period j's dynamics are done (waited below)
+    bool delayed = false;
+    if (KF(noisy) && ok) delayed = A.mask_T[((int64_t)t * A.N + n0 + e_loc) * m + i] != 0;
+
+    mbar_wait(&bar[b], (uint32_t)((j >> 1) & 1));
+
+    const TileSmem S = {s_act, s_dem, s_inv, s_bl, s_ou, s_pipe, s_hd, s_ho, s_carry, s_bt, s_obs, s_rew};
+    tile_period<M_PAD, DMAX, PMAX, MAXC, DIV, MANY>(A, TLY, S, L, t, j, n0, delayed, [&]() {
+        if (MANY && j > 0) {                         // the previous period's stores must be done reading the output buffer
+            if (tid == 0) bulk_wait_read_all();
+            __syncthreads();
+        }
+    });
+    if (!MANY && KHAS(cc)) cc_build<MAXC>(A, TLY, S, smem, L);
     fence_proxy_async_smem();          // every writer orders its generic-proxy stores before the bulk copies
     __syncthreads();                   // ... and everybody is done reading input buffer b
     if (tid == 0) {
+        if (!MANY && KHAS(cc)) bulk_store_only(reinterpret_cast<unsigned char*>(A.cc) + n0 * m * A.cc_W * es, smem + KT(off_cc), (uint32_t)E * m * A.cc_W * es);
         if (KHAS(obs)) bulk_store_only(reinterpret_cast<unsigned char*>(A.obs) + (int64_t)j * A.obs_stride_bytes + n0 * m * O * es, s_obs, (uint32_t)E * m * O * es);
         bulk_store_only(A.reward + (int64_t)j * A.rew_stride + (KF(multi) ? n0 * m : n0), s_rew, KF(multi) ? b_cell8 : (uint32_t)E * 8u);
         if (j == K - 1) {              // the tile's state leaves the SM once per launch

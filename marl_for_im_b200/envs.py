@@ -456,6 +456,28 @@ class _ImxEnvBase:
         self.last_obs, self.last_reward = obs_buf, rew_buf
         return obs_buf, rew_buf, self.period >= self.num_periods
 
+    def step_cc(self, action, fill_actions=True, clip=(-1.0, 1.0), want_obs=True):
+        """``step_packed`` that also returns the centralised-critic observation rows ``[N, m, W]`` (``W = (m-1)(1+O) + O``:
+        opponent actions | opponent observations | own observation — central_critic_observer + FillInActions,
+        models/CC_Model.py:165-214), emitted by the step kernel's epilogue from the observation tile it has just built.
+        ``fill_actions=False`` leaves the opponent-action slots zero, as the observer does at sampling time.
+        Returns ``(obs or None, cc_obs, reward, done)``; cc_obs has the env's observation dtype."""
+        if not self.MULTI:
+            raise _lib.ImxError("the centralised-critic observation is defined for the multi-agent envs")
+        act = self._actions_to_device(action)
+        N, m, O = self.num_envs, self.num_nodes, self.obs_len
+        obs_buf = self._new_obs() if want_obs else None
+        rew_buf = self._new_reward()
+        W = (m - 1) * (1 + O) + O
+        cc_buf = torch.empty((N, m, W), dtype=self.obs_dtype, device=self.device)
+        _lib.check(self._lib.imx_step_cc(self._handle, C.c_void_p(act.data_ptr()), C.c_void_p(obs_buf.data_ptr()) if want_obs else None,
+                                         C.c_void_p(cc_buf.data_ptr()), int(bool(fill_actions)), float(clip[0]), float(clip[1]),
+                                         C.c_void_p(rew_buf.data_ptr()), self._stream()))
+        if want_obs:
+            self.last_obs, self.last_reward = obs_buf, rew_buf
+            self.state = self._shape_obs(obs_buf)
+        return obs_buf, cc_buf, rew_buf, self.period >= self.num_periods
+
     def _cached_views(self, obs_buf, rew_buf):
         """Per-agent dict views of the packed outputs; built once per buffer pair (reuse_buffers keeps the pair alive)."""
         key = (obs_buf.data_ptr(), rew_buf.data_ptr())

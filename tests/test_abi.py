@@ -116,9 +116,10 @@ def test_runtime_specialisation_compiles_for_sm100a_without_gpu():
     for kind, cfg in (("MAIM", presets.serial4()), ("MAIM", presets.serial8()), ("IM", presets.serial4_dfo()),
                       ("MAIM_div", presets.div1()), ("IM_div", presets.div2(prev_actions=True, prev_length=2))):
         c = _raw_config(kind, cfg)
-        buf = ctypes.create_string_buffer(8192)
-        n = lib.imx_jit_compile_check(ctypes.byref(c), buf, 8192)
-        assert n > 10000, (kind, n, buf.value.decode()[:500], lib.imx_last_error())
+        for variant in ((0, 1, 2) if kind.startswith("MAIM") else (0, 1)):      # step, no observations, critic rows
+            buf = ctypes.create_string_buffer(8192)
+            n = lib.imx_jit_compile_check(ctypes.byref(c), variant, buf, 8192)
+            assert n > 10000, (kind, variant, n, buf.value.decode()[:500], lib.imx_last_error())
 
 
 def test_header_is_plain_c99_and_links_against_the_library(tmp_path):

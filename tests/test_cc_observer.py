@@ -69,3 +69,44 @@ def test_cuda_cc_observer_matches_oracle():
     np.testing.assert_array_equal(d["stage_0"]["own_obs"], o["stage_0"])
     np.testing.assert_array_equal(d["stage_0"]["opponent_obs"], o["stage_1"])
     np.testing.assert_array_equal(d["stage_0"]["opponent_action"], np.zeros(1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset,N,obs_dtype,pipe", [("serial2", 65536, "float32", "0"), ("serial2", 65536, "float32", "1"), ("serial4", 4096, "float64", "0"),
+                                                     ("serial8", 8192, "float64", "1"), ("serial4", 4100, "float64", "0"), ("serial2", 96, "float32", "0")])
+def test_fused_cc_rows_from_the_step_kernel(preset, N, obs_dtype, pipe, monkeypatch):
+    """imx_step_cc: the critic rows the step kernel emits == oracle.central_critic_flat of the oracle's observations, and
+    == the separate gather kernel; fused variants (one tile per CTA, pipelined) and the unfused fallbacks (tail, N < 1024)."""
+    import torch
+    from marl_for_im_b200 import presets
+    from marl_for_im_b200.cc import cc_observe
+    from marl_for_im_b200.envs import MultiAgentInvManagement
+    from oracle import c_oracle
+    monkeypatch.setenv("IMX_PIPE", pipe)
+    if pipe == "1":
+        monkeypatch.setenv("IMX_PIPE_CTAS", "1")
+    cfg = presets.PRESETS[preset]()
+    rng = np.random.default_rng(3)
+    env = MultiAgentInvManagement(dict(cfg, num_envs=N, obs_dtype=obs_dtype))
+    m, O, T = env.num_nodes, env.obs_len, 6
+    demand = rng.poisson(5, size=(N, 1, 30)).astype(np.int32)
+    actions = rng.uniform(-1.3, 1.3, size=(T, N, m))
+    env.reset(customer_demand=demand)
+    a_dev = torch.as_tensor(actions, device="cuda:0")
+    np_dt = np.float32 if obs_dtype == "float32" else np.float64
+    want = c_oracle.COracle("MAIM", cfg).run(demand, actions, periods=T, all_obs=True)
+    for t in range(T):
+        fill = bool(t % 2 == 0)
+        obs, cc, rew, done = env.step_cc(a_dev[t], fill_actions=fill, want_obs=(t != 3))
+        cc_h = cc.cpu().numpy()
+        assert cc_h.dtype == np_dt
+        if obs is not None:
+            np.testing.assert_array_equal(obs.cpu().numpy(), want["obs_all"][t + 1].astype(np_dt))
+            sep = cc_observe(env, obs, actions=a_dev[t] if fill else None, dtype=env.obs_dtype).cpu().numpy()
+            np.testing.assert_array_equal(cc_h, sep)
+        np.testing.assert_array_equal(rew.cpu().numpy(), want["reward"][t])
+        for n in (0, 1, N // 2, N - 1):
+            flat = im_oracle.central_critic_flat(want["obs_all"][t + 1, n], actions[t, n] if fill else None)
+            np.testing.assert_array_equal(cc_h[n], flat.astype(np_dt), err_msg=f"t={t} n={n}")
+    if N >= 1024 and N % 64 == 0:
+        assert env._lib.imx_kernel_variant(env._handle) == (3 if pipe == "1" else 2)

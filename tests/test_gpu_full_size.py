@@ -32,7 +32,7 @@ def test_config2_maim4_65536_envs_bit_exact():
     demand = np.random.default_rng(420).poisson(5, size=(N, T)).astype(np.int32)
     actions = np.random.default_rng(0).uniform(-1, 1, size=(T, N, m))
     obs, rew, st, env = _run_gpu(MultiAgentInvManagement, cfg, demand, actions)
-    assert env._lib.imx_kernel_variant(env._handle) == 2          # the runtime-specialised TMA kernel served it
+    assert env._lib.imx_kernel_variant(env._handle) in (2, 3)    # a runtime-specialised TMA kernel served it
     want = c_oracle.COracle("MAIM", cfg).run(demand, actions)
     np.testing.assert_array_equal(obs, want["obs_last"])
     np.testing.assert_array_equal(rew, want["reward"])

@@ -61,7 +61,7 @@ def test_f32_obs_is_the_cast_of_f64_obs(kind, preset, kw, n, monkeypatch):
     for k in s64:
         np.testing.assert_array_equal(s32[k], s64[k], err_msg=k)
     if n >= 4096 and n % 4 == 0:
-        assert variant == 2
+        assert variant in (2, 3)
 
 
 def test_f32_obs_host_buffer_path(monkeypatch):

@@ -158,7 +158,7 @@ def test_rotated_observation_rows_wide(obs_dtype, monkeypatch):
     env.reset(customer_demand=d)
     for t in range(12):
         env.step(a[t])
-        assert env._lib.imx_kernel_variant(env._handle) == 2
+        assert env._lib.imx_kernel_variant(env._handle) in (2, 3)
         got = env.last_obs.cpu().numpy()
         for k in (0, 3, 8, 255):
             np.testing.assert_array_equal(got[k], cast(want["obs"][t + 1]), err_msg=f"t={t} env={k}")

@@ -151,7 +151,7 @@ def test_runtime_specialised_kernels_match(monkeypatch):
         for t in range(env.num_periods):
             a = torch.as_tensor(np.broadcast_to(actions[t][None], (128, env.num_nodes)).copy(), device="cuda:0")
             o, r, done, _ = env.step(a)
-            assert env._lib.imx_kernel_variant(env._handle) == 2, env._lib.imx_jit_log()
+            assert env._lib.imx_kernel_variant(env._handle) in (2, 3), env._lib.imx_jit_log()
             got_o = (torch.stack([o[n] for n in env.agent_names], dim=1) if multi else o).cpu().numpy()
             got_r = (torch.stack([r[n] for n in env.agent_names], dim=1) if multi else r[:, None]).cpu().numpy()
             for n in (0, 63, 64, 127):
@@ -322,7 +322,7 @@ def test_cuda_random_serial_chains(kind, monkeypatch):
         env.reset(customer_demand=np.broadcast_to(demand[None], (64, T)))
         for t in range(T):
             env.step(torch.as_tensor(np.broadcast_to(actions[t][None], (64, m)).copy(), device="cuda:0"))
-            assert env._lib.imx_kernel_variant(env._handle) == 2, env._lib.imx_jit_log()
+            assert env._lib.imx_kernel_variant(env._handle) in (2, 3), env._lib.imx_jit_log()
             np.testing.assert_array_equal(env.last_obs[37].cpu().numpy(), want["obs"][t + 1], err_msg=f"jit obs t={t} {cfg}")
             r = env.last_reward[37].cpu().numpy()
             np.testing.assert_array_equal(r if env.MULTI else np.array([r]), want["reward"][t][:m if env.MULTI else 1], err_msg=f"jit reward t={t}")

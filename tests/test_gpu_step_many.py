@@ -76,7 +76,7 @@ def test_step_many_repeated_and_graph_replayed_at_bench_size():
         obs.zero_()
         env.step_many(actions, obs_out=obs, reward_out=rew)
         assert torch.equal(obs, want_obs) and torch.equal(rew, want_rew), rep
-    assert env._lib.imx_kernel_variant(env._handle) == 2
+    assert env._lib.imx_kernel_variant(env._handle) in (2, 3)
     # one CUDA graph: reset + the chained 30-period replay; replayed with fresh output buffers each time
     lib, h = env._lib, env._handle
     side = torch.cuda.Stream()
