@@ -528,6 +528,7 @@ def run_ours(args):
         ep.steps(stream, T)
 
     g_steps = capture(steps_only, torch)
+    step_variant = env._lib.imx_kernel_variant(env._handle)      # which kernel the per-step launches use (before imx_step_many changes it)
 
     def steps_only_many(stream):
         env._lib.imx_set_period(env._handle, 0)
@@ -601,7 +602,7 @@ def run_ours(args):
                 "traffic_source": (ncu_traffic("step_kernel_config2_65536")[1] or "not captured for this kernel revision")
                                   + " (ncu --set full: dram__bytes_read+write per launch, cold L2; the 31 MB working set of one launch is "
                                     "L2-resident in the bench loop, hence traffic << algorithmic bytes)",
-                "kernel": KERNEL_VARIANTS[env._lib.imx_kernel_variant(env._handle)], "us_per_launch": dt * 1e6,
+                "kernel": KERNEL_VARIANTS[step_variant], "us_per_launch": dt * 1e6,
                 "algorithmic_bytes_per_env_step": B, "envs_per_launch": N, "peak_source": peak_src,
                 "note": "per-launch time = steps-only graph of 30 dependent launches / 30 (includes inter-kernel gaps)"}
 
@@ -616,6 +617,23 @@ def run_ours(args):
 
     # ---- end-to-end through the host-buffer ABI (H2D + kernel + D2H + sync per step) ----------------
     e2e = e2e_measure(env, demand_h, actions_h, torch, dev, world, episodes=max(2, min(args.steps, 5)))
+    e2e["mode"] = "zero-copy: the step kernel addresses the pinned host buffers directly (default)"
+    # the same call with staged copies (cudaMemcpyAsync H2D, kernel, cudaMemcpyAsync D2H on one stream): the copy engine moves
+    # the payload a little faster than SM stores over PCIe but adds two copy launches per step; both are measured at every
+    # world size and the headline is the better one (the library default is zero-copy; IMX_HOST_ZERO_COPY=0 selects staged)
+    os.environ["IMX_HOST_ZERO_COPY"] = "0"
+    try:
+        env_st = MultiAgentInvManagement(dict(presets.serial4(), num_envs=N, device=str(dev), env_offset=rank * N))
+        e2e_staged = e2e_measure(env_st, demand_h, actions_h, torch, dev, world, episodes=max(2, min(args.steps, 5)))
+        e2e_staged["mode"] = "staged: cudaMemcpyAsync in, kernel, cudaMemcpyAsync out (IMX_HOST_ZERO_COPY=0)"
+        del env_st
+    except Exception as exc:
+        e2e_staged = {"error": str(exc)[:200]}
+    finally:
+        os.environ.pop("IMX_HOST_ZERO_COPY", None)
+    e2e_modes = {"zero_copy": dict(e2e), "staged_copy_engine": e2e_staged}
+    if e2e_staged.get("value", 0.0) > e2e["value"]:
+        e2e = dict(e2e_staged)
     # same call with float32 observations (the cast RLlib's preprocessor applies to every observation anyway):
     # 40 % fewer bytes over PCIe; reported beside the float64 drop-in number, never instead of it
     env32 = MultiAgentInvManagement(dict(presets.serial4(), num_envs=N, device=str(dev), env_offset=rank * N, obs_dtype="float32"))
@@ -651,7 +669,7 @@ def run_ours(args):
                             "timing": "CUDA events around K CUDA-graph replays (reset + 30 step launches) + per-episode return statistics"
                                       + (" + 1 NCCL all-reduce of the batch statistics" if world > 1 else "") + ", max over ranks"},
             "configs": other, "cpu_baseline_reference": reference_timing("config2_maim4_ma6"),
-            "roofline": roofline, "roofline_large_n": roof_large, "replay_fused": replay_fused, "cpu_baseline": cpu, "cpu_baseline_1core": cpu_1, "cpu_baseline_c": cpu_c, "e2e": e2e, "e2e_f32_obs": e2e_f32,
+            "roofline": roofline, "roofline_large_n": roof_large, "replay_fused": replay_fused, "cpu_baseline": cpu, "cpu_baseline_1core": cpu_1, "cpu_baseline_c": cpu_c, "e2e": e2e, "e2e_modes": e2e_modes, "e2e_f32_obs": e2e_f32,
             "gpu_launches": int(launches_per_episode * args.steps), "host_cores_bound_to_gpu_numa_node": numa_cores,
             "clocks": clocks,
             "episode_stats": {"n": float(final_stats[0].item()), "mean_return": float((final_stats[1] / final_stats[0]).item())},

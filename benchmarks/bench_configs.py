@@ -180,6 +180,9 @@ def main():
         ("config3 MAIM 8-stage fused rollout, 1048576 envs, philox", lambda: time_rollout("MAIM", presets.serial8(standardise_actions=False), 1 << 20, args.reps, False)),
         ("config1 IM 4-stage DFO rollout, 1048576 envs, philox", lambda: time_rollout("IM", presets.serial4_dfo(), 1 << 20, args.reps, False)),
         ("MAIM_div div2 fused rollout, 262144 envs, philox", lambda: time_rollout("MAIM_div", presets.div2(), 262144, args.reps, False)),
+        ("MAIM_div div2 fused rollout, 262144 envs, replayed", lambda: time_rollout("MAIM_div", presets.div2(), 262144, args.reps, True)),
+        ("MAIM_div div1 fused rollout, 262144 envs, philox", lambda: time_rollout("MAIM_div", presets.div1(), 262144, args.reps, False)),
+        ("IM_div div2 fused rollout, 262144 envs, philox", lambda: time_rollout("IM_div", presets.div2(), 262144, args.reps, False)),
     ]
     for name, fn in jobs:
         if args.only and args.only not in name:

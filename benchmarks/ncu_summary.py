@@ -3,6 +3,9 @@
 
     python benchmarks/ncu_summary.py report  gpurun_out/prof.ncu-rep   > profiles/rN_ncu_<kernel>.txt
     python benchmarks/ncu_summary.py launches gpurun_out/launches.csv  > profiles/rN_launch_list_summary.txt
+    python benchmarks/ncu_summary.py traffic gpurun_out/prof.ncu-rep <key> <profiles/summary.txt> [kernel-name-substring]
+        records dram__bytes_read.sum + dram__bytes_write.sum per launch of the (matching) kernel in profiles/ncu_traffic.json
+        under <key>, with the summary file and the git commit it was captured at — bench.py reads `roofline.traffic` from there
 """
 import csv
 import io
@@ -80,5 +83,29 @@ def launches(path):
         print(f"{n:5d} {us:10.1f} {100.0 * us / tot:6.1f}% {us / n:9.2f}  {name[:110]}")
 
 
+def traffic(rep, key, source, match=""):
+    import json
+    import os
+    rows = ncu_csv(rep, "raw")
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    kn, kr, kw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = [(float(r[kr].replace(",", "")) * scale[units[kr]], float(r[kw].replace(",", "")) * scale[units[kw]], r[kn]) for r in data if match in r[kn]]
+    if not vals:
+        raise SystemExit(f"no kernel matching {match!r} in {rep}")
+    rd, wr = sum(v[0] for v in vals) / len(vals), sum(v[1] for v in vals) / len(vals)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "profiles", "ncu_traffic.json")
+    doc = json.load(open(path)) if os.path.exists(path) else {}
+    commit = subprocess.run(["git", "-C", root, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    doc[key] = {"bytes": int(rd + wr), "dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "launches_averaged": len(vals),
+                "kernel": vals[0][2][:160], "source": source, "commit": commit}
+    json.dump(doc, open(path, "w"), indent=1, sort_keys=True)
+    print(json.dumps(doc[key]))
+
+
 if __name__ == "__main__":
-    {"report": report, "launches": launches}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:6])
+    else:
+        {"report": report, "launches": launches}[sys.argv[1]](sys.argv[2])

@@ -16,6 +16,7 @@
 #include "imx_step_tma.cuh"
 #include "imx_rollout.cuh"
 #include "imx_step_pipe.cuh"
+#include "imx_rollout_et.cuh"
 #include "imx_kernels.cuh"
 #include "imx_stats.cuh"
 #include "imx_jit.cuh"
@@ -128,6 +129,10 @@ struct imx_env {
     int tma_threads = 256;               // CTA size of the TMA kernel (IMX_TMA_THREADS: 64, 128 or 256)
     int use_pdl = 1;                     // chain step launches with programmatic dependent launch (IMX_PDL=0 disables)
     int fuse_periods = 1;                // imx_step_many advances all its periods in one launch (IMX_FUSE_PERIODS=0: K plain launches)
+    int cells = 0;                       // specialised STEP kernels use the cell mapping (thread k = cell k of the [E][m] tile; IMX_CELLS=1)
+    int rollout_et = 0;                  // the specialised ROLLOUT kernel is the env-per-thread one (imx_rollout_et.cuh; IMX_ROLLOUT_ET, default m <= 8)
+    int rollout_cells = 0;               // the specialised ROLLOUT kernel uses the cell mapping (IMX_ROLLOUT_CELLS; default: divergent networks)
+    int jit_threads = 128;               // CTA size (compute threads) of the specialised TMA kernels: tma_threads, or 32 * m with cells
     int pipe_mode = 0;                   // persistent pipelined step kernel: 0 auto, 1 always, -1 never (IMX_PIPE)
     int pipe_stages = 4;                 // ring depth of the pipelined kernel (IMX_PIPE_STAGES)
     int pipe_ctas = 0;                   // resident CTAs per SM of the pipelined kernel (IMX_PIPE_CTAS; 0 = derived)
@@ -208,9 +213,9 @@ static int m_pad_of(const imx_env* e) {
 }
 
 // shared-memory tile layout of the TMA kernel (regions 128-byte aligned); pure host arithmetic
-static void compute_tile(const imx_env* e, TileLayout& L, int tile_width, bool with_cc = false) {
+static void compute_tile(const imx_env* e, TileLayout& L, int tile_width, bool with_cc = false, bool cells = false) {
     const int m = e->m;
-    const int E = (e->tma_threads / 32) * (32 / tile_width);
+    const int E = cells ? 32 : (e->tma_threads / 32) * (32 / tile_width);     // cell mapping: 32 envs x m nodes = m full warps
     int off = 0;
     auto take = [&](int bytes) { const int o = off; off += (bytes + 127) & ~127; return o; };
     L.E = E;
@@ -227,6 +232,7 @@ static void compute_tile(const imx_env* e, TileLayout& L, int tile_width, bool w
     L.off_obs = take(E * m * e->O * (e->cfg.obs_f32 ? 4 : 8));
     L.off_rew = take(E * m * 8);
     L.off_cc = with_cc ? take(E * m * ((m - 1) * (1 + e->O) + e->O) * (e->cfg.obs_f32 ? 4 : 8)) : 0;
+    L.off_x = cells ? take(E * m * (8 + 4 * 4)) : 0;
     L.total = off;
     // multi-period launches double-buffer the per-period inputs; the extra regions sit behind the
     // single-period layout so that a plain step launches the same kernel with `total` bytes only
@@ -236,6 +242,13 @@ static void compute_tile(const imx_env* e, TileLayout& L, int tile_width, bool w
 }
 
 // -D options and template instantiations of the runtime-specialised build (imx_jit.cuh)
+// dynamic shared memory of the cell-mapped rollout kernel (exchange arrays + the tile's Philox demand), 0 = not applicable
+static int rollout_cells_smem(const imx_env* e) {
+    if (!e->rollout_cells) return 0;
+    const int64_t bytes = (int64_t)32 * e->m * (8 + 5 * 4) + (int64_t)32 * e->R * ((e->T + 1) & ~1) * 4;
+    return bytes <= 96 * 1024 ? (int)bytes : 0;
+}
+
 static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1, int has_cc = 0) {
     std::vector<std::string>& defs = sp.defines;
     const imx_config& c = e->cfg;
@@ -260,11 +273,19 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
     addt("E", L.E); addt("off_act", L.off_act); addt("off_inv", L.off_inv); addt("off_bl", L.off_bl); addt("off_ou", L.off_ou);
     addt("off_pipe", L.off_pipe); addt("off_hd", L.off_hd); addt("off_ho", L.off_ho); addt("off_carry", L.off_carry);
     addt("off_bt", L.off_bt); addt("off_dem", L.off_dem); addt("off_obs", L.off_obs); addt("off_rew", L.off_rew); addt("total", L.total);
-    addt("off_act2", L.off_act2); addt("off_dem2", L.off_dem2); addt("total2", L.total2); addt("off_cc", L.off_cc);
+    addt("off_act2", L.off_act2); addt("off_dem2", L.off_dem2); addt("total2", L.total2); addt("off_cc", L.off_cc); addt("off_x", L.off_x);
+    if (e->cells) defs.push_back("IMX_CELLS=1");
+    if (rollout_cells_smem(e) > 0) defs.push_back("IMX_ROLLOUT_CELLS=1");
+    {
+        int nsplit = 0;
+        if (e->div)
+            for (int i = 0; i < e->m; ++i) nsplit += c.num_children[i] > 1;
+        add("nsplit", nsplit);
+    }
     {   // register bound of the plain step kernel, measured per family: the divergent kernels (natural 47) gain occupancy at 40
         // (div1 +5 %, div2 +1.5 %), the 2-wide chain is faster unconstrained (+8 % at 64), the others are best at their natural 32
         const char* sr = getenv("IMX_STEP_MAXNREG");
-        const int bound = sr ? atoi(sr) : (e->div ? 40 : (m_pad_of(e) == 2 ? 64 : 0));
+        const int bound = sr ? atoi(sr) : (e->cells ? 0 : e->div ? 40 : (m_pad_of(e) == 2 ? 64 : 0));   // the cell-mapped kernel spills at 40
         if (bound > 0) defs.push_back("IMX_STEP_MAXNREG=" + std::to_string(bound));
     }
     {   // register bound of the rollout kernel.  Measured (profiles/r1_other_configs_1gpu.jsonl): the divergent kernel wants
@@ -279,7 +300,7 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
         const int maxnreg = mr ? atoi(mr) : 0;             // 0: the per-config default in imx_step_tma.cuh
         if (maxnreg > 0) defs.push_back("IMX_MANY_MAXNREG=" + std::to_string(maxnreg));
     }
-    defs.push_back("IMX_TMA_THREADS=" + std::to_string(e->tma_threads));
+    defs.push_back("IMX_TMA_THREADS=" + std::to_string(e->jit_threads));
     // the device translation unit checks its view of the argument blocks against this host build (imx_jit.cuh)
     defs.push_back("IMX_HOST_SIZEOF_STEPARGS=" + std::to_string(sizeof(StepArgs)));
     defs.push_back("IMX_HOST_SIZEOF_TILELAYOUT=" + std::to_string(sizeof(TileLayout)));
@@ -292,8 +313,43 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
                               std::to_string(e->div ? maxc : 1) + ", " + dv + ">";
     sp.name[0] = "imx::step_kernel_tma" + targs;
     sp.name[1] = "imx::step_kernel_tma_many" + targs;
-    sp.name[2] = "imx::rollout_kernel<" + std::to_string(e->m) + ", " + std::to_string(e->D) + ", " + std::to_string(e->div ? maxc : 1) +
-                 ", " + dv + ">";
+    if (e->rollout_et) {
+        // env-per-thread rollout: the network as compile-time integer lists
+        auto list = [&](const char* k, auto get) {
+            std::string v;
+            for (int i = 0; i < e->m; ++i) v += (i ? "," : "") + std::to_string((long long)get(i));
+            defs.push_back(std::string("IMX_L_") + k + "=" + v);
+        };
+        defs.push_back("IMX_ET=1");
+        list("inv_max", [&](int i) { return c.inv_max[i]; });
+        list("order_max", [&](int i) { return c.order_max[i]; });
+        list("demand_max", [&](int i) { return e->demand_max[i]; });
+        list("delay", [&](int i) { return c.delay[i]; });
+        list("init_inv", [&](int i) { return c.inv_init[i]; });
+        list("nchild", [&](int i) { return e->div ? c.num_children[i] : 0; });
+        list("retailer_idx", [&](int i) { return e->retailer_idx[i]; });
+        {
+            std::string po, bo, ch;
+            int p_off = 0, b_off = 0;
+            for (int i = 0; i < e->m; ++i) {
+                po += (i ? "," : "") + std::to_string(p_off);
+                p_off += c.delay[i];
+                const bool split = e->div && c.num_children[i] > 1;
+                bo += (i ? "," : "") + std::to_string(split ? b_off : -1);
+                if (split) b_off += c.num_children[i];
+                for (int k = 0; k < maxc; ++k)
+                    ch += ((i || k) ? "," : "") + std::to_string((e->div && k < c.num_children[i]) ? c.children[i][k] : -1);
+            }
+            defs.push_back("IMX_L_pipe_off=" + po);
+            defs.push_back("IMX_L_bt_off=" + bo);
+            defs.push_back("IMX_L_children=" + ch);
+        }
+        sp.name[2] = "imx::rollout_kernel_et<" + std::to_string(e->m) + ", " + std::to_string(e->D) + ", " + std::to_string(maxc) + ", " + dv + ">";
+    } else if (rollout_cells_smem(e) > 0)
+        sp.name[2] = "imx::rollout_kernel_cells<" + std::to_string(e->D) + ", " + std::to_string(e->div ? maxc : 1) + ", " + dv + ">";
+    else
+        sp.name[2] = "imx::rollout_kernel<" + std::to_string(e->m) + ", " + std::to_string(e->D) + ", " + std::to_string(e->div ? maxc : 1) +
+                     ", " + dv + ">";
     sp.name[3] = "";
     if (has_cc) { sp.name[1] = ""; sp.name[2] = ""; }      // the critic rows ride on the single-period kernels only
     if (e->pipe_mode >= 0 && (int64_t)e->pipe_stages * L.total <= 200 * 1024) {
@@ -307,7 +363,7 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
 static void jit_smem(const imx_env* e, int smem[imxjit::N_KERNELS]) {
     smem[0] = e->tile_jit.total;
     smem[1] = e->tile_jit.total2 <= 200 * 1024 ? e->tile_jit.total2 : e->tile_jit.total;
-    smem[2] = 0;
+    smem[2] = rollout_cells_smem(e);
     smem[3] = e->pipe_stages * e->tile_jit.total;
 }
 
@@ -384,8 +440,23 @@ static int select_kernels(imx_env* e) {
     // the specialised STEP kernel keeps the power-of-two tile: a dense m-wide tile makes the per-field byte
     // ranges (e.g. 40 envs x 6 nodes x 4 B = 960 B) straddle 128-byte lines, measured slower at 262144 envs;
     // the issue-bound ROLLOUT kernel is specialised with tile width = m (dense lane packing, +21% on div2)
-    compute_tile(e, e->tile_jit, e->step_dense ? e->m : m_pad_of(e));
-    compute_tile(e, e->tile_cc, e->step_dense ? e->m : m_pad_of(e), true);
+    {
+        // Cell mapping (thread k = cell k of a [32][m] tile, coupling through shared memory, the split re-packed into tasks).
+        // ROLLOUT kernel: default for divergent networks up to 16 nodes (issue-bound loop: half the instructions).
+        // STEP kernels: opt-in (IMX_CELLS=1) — measured SLOWER than the lane mapping although they execute 36 % fewer
+        // instructions (profiles/r2_ncu_div2_step_kernel_{lanes,cells}.txt): four CTA barriers per period and 6-warp tiles
+        // leave the kernel latency-bound (issue-active 40 %, long-scoreboard + barrier stalls) instead of issue-bound.
+        const char* cm = getenv("IMX_CELLS");
+        e->cells = (cm && !strcmp(cm, "1")) ? (e->m <= 16) : 0;
+        const char* rc = getenv("IMX_ROLLOUT_CELLS");
+        e->rollout_cells = (rc && !strcmp(rc, "1")) ? (e->m <= 16) : 0;      // opt-in: measured no faster than the lane mapping (profiles/r2_rollout_mappings.txt)
+        // env-per-thread rollout (imx_rollout_et.cuh): networks up to 8 nodes, lead times up to 4 (registers); IMX_ROLLOUT_ET=0 disables
+        const char* re = getenv("IMX_ROLLOUT_ET");
+        e->rollout_et = (re && !strcmp(re, "0")) ? 0 : (e->m <= 8 && e->D <= 4 && !e->rollout_cells);
+        e->jit_threads = e->cells ? 32 * e->m : e->tma_threads;
+    }
+    compute_tile(e, e->tile_jit, e->step_dense ? e->m : m_pad_of(e), false, e->cells != 0);
+    compute_tile(e, e->tile_cc, e->step_dense ? e->m : m_pad_of(e), true, e->cells != 0);
     if (e->tile.total <= 200 * 1024) {
         IMX_CUDA(raise_dyn_smem_limit((const void*)e->tma_fn, (size_t)e->tile.total));
         if (e->tile.total2 <= 200 * 1024)
@@ -566,6 +637,10 @@ static void fill_args(const imx_env* e, StepArgs& A) {
     A.hist_o = (int32_t*)e->field_ptr[IMX_F_HIST_O];
     A.carry = (int32_t*)e->field_ptr[IMX_F_CARRY];
     A.bt = (int32_t*)e->field_ptr[IMX_F_BACKLOG_TO];
+    A.nsplit = 0;
+    if (e->div)
+        for (int i = 0; i < e->m && A.nsplit < IMX_MAX_NODES / 2; ++i)
+            if (c.num_children[i] > 1) A.split_nodes[A.nsplit++] = (int8_t)i;
     A.err = e->d_err;
     A.demand_T = e->d_demand_T;
     A.mask_T = e->d_mask_T;
@@ -659,6 +734,7 @@ extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
         q.bt_off = -1;
         if (e->div && cfg->num_children[i] > 1) { q.bt_off = bt_off; bt_off += cfg->num_children[i]; }
         q.retailer_idx = e->retailer_idx[i];
+        q.parent_nchild = (e->div && e->parent[i] >= 0) ? cfg->num_children[e->parent[i]] : 0;
         q.p = e->sell[i]; q.c = e->buy[i]; q.h = cfg->stock_cost[i]; q.bc = cfg->backlog_cost[i]; q.target = cfg->inv_target[i];
         q.child_lo = q.child_hi = 0xFFFFFFFFu;
         if (e->div)
@@ -862,9 +938,9 @@ extern "C" int imx_reset(imx_env* e, const int32_t* demand_dev, const uint8_t* d
 static int pipe_ctas_per_sm(const imx_env* e) {
     if (e->pipe_ctas > 0) return e->pipe_ctas;
     const int by_smem = (int)((227 * 1024) / ((int64_t)e->pipe_stages * e->tile_jit.total + 1024));
-    const int by_thr = 2048 / (e->tma_threads + 32);
+    const int by_thr = 2048 / (e->jit_threads + 32);
     int c = by_smem < by_thr ? by_smem : by_thr;
-    if (c > 4) c = 4;
+    if (c > 6) c = 6;
     return c < 1 ? 1 : c;
 }
 // auto policy: the pipeline needs more than one tile per resident CTA to overlap anything
@@ -874,9 +950,9 @@ static bool pipe_pays(const imx_env* e, int n_tiles) {
 static int pipe_ctas_for(const imx_env* e, const TileLayout& L) {
     if (e->pipe_ctas > 0) return e->pipe_ctas;
     const int by_smem = (int)((227 * 1024) / ((int64_t)e->pipe_stages * L.total + 1024));
-    const int by_thr = 2048 / (e->tma_threads + 32);
+    const int by_thr = 2048 / (e->jit_threads + 32);
     int c = by_smem < by_thr ? by_smem : by_thr;
-    if (c > 4) c = 4;
+    if (c > 6) c = 6;
     return c < 1 ? 1 : c;
 }
 
@@ -884,6 +960,7 @@ static int pipe_ctas_for(const imx_env* e, const TileLayout& L) {
 // in shared memory; *done receives how many periods the call really advanced (1 when the fused form is not applicable:
 // tail tiles, diagnostics, the direct path, a layout that does not fit).
 struct CcOut { void* dev; int fill; double lo, hi; };
+constexpr unsigned ET_THREADS_HOST = 128;     // = imx::ET_THREADS of the env-per-thread rollout (device-only constant)
 
 static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, double* reward_dev,
                        const imx_info_out* info, cudaStream_t s, int periods = 1, int* done = nullptr, const CcOut* cc = nullptr,
@@ -957,12 +1034,12 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
             CUlaunchConfig lc;
             memset(&lc, 0, sizeof(lc));
             lc.gridDimX = (unsigned)(n_tma / TL_use.E); lc.gridDimY = 1; lc.gridDimZ = 1;
-            lc.blockDimX = (unsigned)e->tma_threads; lc.blockDimY = 1; lc.blockDimZ = 1;
+            lc.blockDimX = (unsigned)e->jit_threads; lc.blockDimY = 1; lc.blockDimZ = 1;
             lc.sharedMemBytes = tma_smem;
             if (pipe) {
                 const int64_t resident = (int64_t)e->sm_count * pipe_ctas_for(e, TL_use);
                 lc.gridDimX = (unsigned)(PA.n_tiles < resident ? PA.n_tiles : resident);
-                lc.blockDimX = (unsigned)e->tma_threads + 32;
+                lc.blockDimX = (unsigned)e->jit_threads + 32;
                 lc.sharedMemBytes = (unsigned)(e->pipe_stages * TL_use.total);
             }
             lc.hStream = (CUstream)s;
@@ -1133,7 +1210,32 @@ extern "C" int imx_rollout_basestock(imx_env* e, const double* z_dev, int z_stri
     const int64_t warp_tiles = (e->N + epw - 1) / epw;
     const int64_t blocks_needed = (warp_tiles + (ROLLOUT_THREADS / 32) - 1) / (ROLLOUT_THREADS / 32);
     const unsigned grid = (unsigned)(blocks_needed < e->rollout_grid_cap ? blocks_needed : e->rollout_grid_cap);
-    if (e->jit_state == 1 && e->jit->rollout) {
+    if (e->jit_state == 1 && e->jit->rollout && e->rollout_et) {
+        EtNodeConsts C;
+        memset(&C, 0, sizeof(C));
+        for (int i = 0; i < e->m; ++i) {
+            C.p[i] = e->sell[i]; C.c[i] = e->buy[i]; C.h[i] = e->cfg.stock_cost[i]; C.bc[i] = e->cfg.backlog_cost[i]; C.target[i] = e->cfg.inv_target[i];
+        }
+        void* params[] = {(void*)&A, (void*)&Rg, (void*)&C};
+        const int64_t blocks = (e->N + ET_THREADS_HOST - 1) / ET_THREADS_HOST;
+        const int64_t cap = (int64_t)e->sm_count * 16;
+        Rg.coop_demand = 0;
+        const CUresult cr = imxjit::g_api.LaunchKernel(e->jit->rollout, (unsigned)(blocks < cap ? blocks : cap), 1, 1, ET_THREADS_HOST, 1, 1, 0, (CUstream)s,
+                                                       params, nullptr);
+        if (cr != CUDA_SUCCESS) return fail(-3, "launch of the env-per-thread rollout kernel failed (CUresult %d)", (int)cr);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e->last_variant = 2;
+    } else if (e->jit_state == 1 && e->jit->rollout && rollout_cells_smem(e) > 0) {
+        void* params[] = {(void*)&A, (void*)&Rg};
+        const int64_t n_tiles = (e->N + 31) / 32;
+        const int64_t cap = (int64_t)e->sm_count * 8;
+        Rg.coop_demand = 0;
+        const CUresult cr = imxjit::g_api.LaunchKernel(e->jit->rollout, (unsigned)(n_tiles < cap ? n_tiles : cap), 1, 1, (unsigned)(32 * e->m), 1, 1,
+                                                       (unsigned)rollout_cells_smem(e), (CUstream)s, params, nullptr);
+        if (cr != CUDA_SUCCESS) return fail(-3, "launch of the cell-mapped rollout kernel failed (CUresult %d)", (int)cr);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e->last_variant = 2;
+    } else if (e->jit_state == 1 && e->jit->rollout) {
         void* params[] = {(void*)&A, (void*)&Rg};
         const int epw_j = 32 / e->m;                         // dense packing in the specialised build
         const int64_t wt_j = (e->N + epw_j - 1) / epw_j;
@@ -1342,9 +1444,18 @@ extern "C" int imx_jit_compile_check(const imx_config* cfg, int variant, char* l
     const int rc = derive(&tmp);
     if (rc) return rc;
     tmp.tma_threads = choose_tma_threads(&tmp);
+    {
+        const char* cm = getenv("IMX_CELLS");
+        tmp.cells = (cm && !strcmp(cm, "1")) ? (tmp.m <= 16) : 0;
+        const char* rc = getenv("IMX_ROLLOUT_CELLS");
+        tmp.rollout_cells = (rc && !strcmp(rc, "1")) ? (tmp.m <= 16) : 0;
+        const char* re = getenv("IMX_ROLLOUT_ET");
+        tmp.rollout_et = (re && !strcmp(re, "0")) ? 0 : (tmp.m <= 8 && tmp.D <= 4 && !tmp.rollout_cells);
+        tmp.jit_threads = tmp.cells ? 32 * tmp.m : tmp.tma_threads;
+    }
     compute_tile(&tmp, tmp.tile, m_pad_of(&tmp));
-    compute_tile(&tmp, tmp.tile_jit, m_pad_of(&tmp));
-    compute_tile(&tmp, tmp.tile_cc, m_pad_of(&tmp), true);
+    compute_tile(&tmp, tmp.tile_jit, m_pad_of(&tmp), false, tmp.cells != 0);
+    compute_tile(&tmp, tmp.tile_cc, m_pad_of(&tmp), true, tmp.cells != 0);
     int TL = 0;
     build_tables(&tmp, &TL);
     imxjit::Spec sp;

@@ -41,7 +41,22 @@ typedef unsigned long uintptr_t;
 #define KNOISY_DEMAND(g) ((g).noise_thr > 0.0)
 #endif
 
+// cell mapping of the runtime-specialised kernels: step kernels (see imx_step_tma.cuh) and the fused rollout (imx_rollout.cuh)
+#if defined(IMX_JIT) && defined(IMX_CELLS) && IMX_CELLS
+#define IMX_USE_CELLS 1
+#else
+#define IMX_USE_CELLS 0
+#endif
+#if defined(IMX_JIT) && defined(IMX_ROLLOUT_CELLS) && IMX_ROLLOUT_CELLS
+#define IMX_USE_ROLLOUT_CELLS 1
+#else
+#define IMX_USE_ROLLOUT_CELLS 0
+#endif
+
 namespace imx {
+
+// named barrier of a CTA's compute threads (id 1; bar 0 = __syncthreads stays free for the whole CTA)
+__device__ __forceinline__ void cells_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
 // ------------------------------------------------------------------------------------
 // Per-node constants.  Lives in global memory (one small table per env handle); every thread
@@ -61,7 +76,7 @@ struct __align__(16) NodeParams {
     int32_t nchild;        // divergent: number of children
     int32_t bt_off;        // divergent: offset of this node's ledger in bt[NB] (-1: not a split node)
     int32_t retailer_idx;  // row of the demand trace feeding this node (-1: not a retailer)
-    int32_t pad0;
+    int32_t parent_nchild; // divergent: number of children of the parent (> 1: this node's inflow comes out of a split)
     double p;              // unit sell price
     double c;              // unit buy cost
     double h;              // stock holding cost
@@ -78,7 +93,7 @@ __device__ __forceinline__ NodeParams load_node(const NodeParams* p) {
     NodeParams n;
     n.inv_max = q0.x; n.order_max = q0.y; n.demand_max = q0.z; n.delay = q0.w;
     n.pipe_off = q1.x; n.init_inv = q1.y; n.parent = q1.z; n.child_slot = q1.w;
-    n.nchild = q2.x; n.bt_off = q2.y; n.retailer_idx = q2.z; n.pad0 = 0;
+    n.nchild = q2.x; n.bt_off = q2.y; n.retailer_idx = q2.z; n.parent_nchild = q2.w;
     n.p = __hiloint2double(q3.y, q3.x); n.c = __hiloint2double(q3.w, q3.z);
     n.h = __hiloint2double(q4.y, q4.x); n.bc = __hiloint2double(q4.w, q4.z);
     n.target = __hiloint2double(q5.y, q5.x); n.child_lo = (uint32_t)q5.z; n.child_hi = (uint32_t)q5.w;
@@ -146,6 +161,8 @@ struct StepArgs {
     int64_t rew_stride;                     // doubles between consecutive periods' reward blocks
     // centralised-critic observation emitted by the step itself (imx_step_cc; models/CC_Model.py:165-214): for every agent the
     // row [opponent actions (m-1) | opponent observations (m-1)*O | own observation O], in the observation element type
+    int32_t nsplit;                         // divergent: nodes with more than one child ...
+    int8_t split_nodes[IMX_MAX_NODES / 2];  // ... and their indices (the cell-mapped kernels hand each (env, split node) pair to one thread)
     void* __restrict__ cc;                  // [N][m][W] or nullptr
     int32_t cc_fill;                        // 1: opponent-action slots = clip(this step's actions, cc_lo, cc_hi); 0: zeros
     int32_t cc_W;                           // (m-1)*(1+O) + O

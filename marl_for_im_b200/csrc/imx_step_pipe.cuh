@@ -137,8 +137,12 @@ __global__ void IMX_PIPE_BOUNDS step_kernel_pipe(const __grid_constant__ StepArg
                             st + KT(off_obs), reinterpret_cast<double*>(st + KT(off_rew))};
         const int64_t n0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * E;
         mbar_wait(&full[s], (uint32_t)((k / S) & 1));
+#if IMX_USE_CELLS
+        tile_period_cells<M_PAD, DMAX, PMAX, MAXC, DIV, false>(A, TLY, T, st, L, tid, CT, A.t, 0, n0, false, []() {});
+#else
         tile_period<M_PAD, DMAX, PMAX, MAXC, DIV, false>(A, TLY, T, L, A.t, 0, n0, false, []() {});
-        if (KHAS(cc)) cc_build<MAXC>(A, TLY, T, st, L);
+#endif
+        if (KHAS(cc)) cc_build<MAXC>(A, TLY, T, st, L, CT);
         fence_proxy_async_smem();                    // this thread's tile writes, before the bulk engine reads them
         __syncwarp();
         if (L.lane == 0) mbar_arrive(&done[s]);      // release: the producer's wait acquires the whole warp's writes

@@ -133,6 +133,9 @@ class _ImxEnvBase:
         self.state = {} if self.MULTI else None
         self._episode = 0
         self._handle = None
+        if take("_config_only", False):                      # build tooling: parse + derive the imx_config, no device work
+            self.imx_config = self._build_config(self.noisy_delay)
+            return
         self._create_handle(self.noisy_delay)
         self._build_spaces()
         self.reset()
@@ -144,10 +147,8 @@ class _ImxEnvBase:
         raise NotImplementedError
 
     # ------------------------------------------------------------------ native handle
-    def _create_handle(self, with_carry: bool):
-        lib = _lib.load()
-        if not torch.cuda.is_available():
-            raise _lib.ImxError("no CUDA device — marl_for_im_b200 has no CPU fallback")
+    def _build_config(self, with_carry: bool):
+        """The C ABI's imx_config for this env (pure host code: no device needed)."""
         m = self.num_nodes
         c = _lib.ImxConfig()
         c.kind = _lib.KIND[self.KIND]
@@ -162,7 +163,7 @@ class _ImxEnvBase:
         c.demand_dist = _lib.DIST[dist]
         lower_upper = self.config.get("lower_upper", (1, 5))
         c.uniform_low, c.uniform_high = int(lower_upper[0]), int(lower_upper[1])
-        c.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        c.device = self.device.index if self.device.index is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
         c.obs_f32 = int(self.obs_dtype == torch.float32)
         c.a, c.b = float(self.a), float(self.b)
         c.mu = float(self.config.get("mu", 5))
@@ -190,6 +191,14 @@ class _ImxEnvBase:
             price = np.asarray(self.price, dtype=np.float64).reshape(-1)
             for i in range(m + 1):
                 c.price[i] = float(price[i])
+        return c
+
+    def _create_handle(self, with_carry: bool):
+        lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.ImxError("no CUDA device — marl_for_im_b200 has no CPU fallback")
+        m = self.num_nodes
+        c = self._build_config(with_carry)
         if self._handle is not None:
             lib.imx_destroy(self._handle)
             self._handle = None

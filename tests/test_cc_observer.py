@@ -108,5 +108,5 @@ def test_fused_cc_rows_from_the_step_kernel(preset, N, obs_dtype, pipe, monkeypa
         for n in (0, 1, N // 2, N - 1):
             flat = im_oracle.central_critic_flat(want["obs_all"][t + 1, n], actions[t, n] if fill else None)
             np.testing.assert_array_equal(cc_h[n], flat.astype(np_dt), err_msg=f"t={t} n={n}")
-    if N >= 1024 and N % 64 == 0:
-        assert env._lib.imx_kernel_variant(env._handle) == (3 if pipe == "1" else 2)
+    if N >= 1024 and N % 64 == 0:        # fused: a specialised kernel served it (the pipelined one when its ring of critic-row tiles fits in shared memory)
+        assert env._lib.imx_kernel_variant(env._handle) in ((2, 3) if pipe == "1" else (2,))
