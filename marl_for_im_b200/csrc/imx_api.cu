@@ -130,11 +130,12 @@ struct imx_env {
     int use_pdl = 1;                     // chain step launches with programmatic dependent launch (IMX_PDL=0 disables)
     int fuse_periods = 1;                // imx_step_many advances all its periods in one launch (IMX_FUSE_PERIODS=0: K plain launches)
     int cells = 0;                       // specialised STEP kernels use the cell mapping (thread k = cell k of the [E][m] tile; IMX_CELLS=1)
+    int step_et = 0;                     // the specialised STEP kernels use the env-per-thread period (IMX_STEP_ET; default: divergent networks, m <= 8)
     int rollout_et = 0;                  // the specialised ROLLOUT kernel is the env-per-thread one (imx_rollout_et.cuh; IMX_ROLLOUT_ET, default m <= 8)
     int rollout_cells = 0;               // the specialised ROLLOUT kernel uses the cell mapping (IMX_ROLLOUT_CELLS; default: divergent networks)
     int jit_threads = 128;               // CTA size (compute threads) of the specialised TMA kernels: tma_threads, or 32 * m with cells
     int pipe_mode = 0;                   // persistent pipelined step kernel: 0 auto, 1 always, -1 never (IMX_PIPE)
-    int pipe_stages = 4;                 // ring depth of the pipelined kernel (IMX_PIPE_STAGES)
+    int pipe_stages = 0;                 // ring depth of the pipelined kernel (IMX_PIPE_STAGES; 0 = measured default)
     int pipe_ctas = 0;                   // resident CTAs per SM of the pipelined kernel (IMX_PIPE_CTAS; 0 = derived)
     int sm_count = 148;
     int jit_policy = 0;                  // 0 auto (large batches), 1 always, -1 never (IMX_JIT)
@@ -201,7 +202,11 @@ static int m_pad_of(const imx_env* e);
 // multi-million-env batches, where the 256-thread tile is 2.5% ahead; 512-thread CTAs lose 25%
 static int choose_tma_threads(const imx_env* e) {
     const char* tt = getenv("IMX_TMA_THREADS");
-    const int dflt = (m_pad_of(e) <= 4 && e->N >= ((int64_t)1 << 20)) ? 256 : 128;
+    // 4-wide serial chains in the pipelined regime (working set within ~1.5 x L2, see pipe_pays): 64-thread tiles of 16 envs with
+    // 8 resident CTAs per SM measured 3 % ahead of 128-thread tiles (profiles/r2_pipe_sweep.txt); 256-thread tiles from 1 Mi envs
+    const int64_t bytes_per_env = 8 * (int64_t)e->S + 4 * e->R + (int64_t)e->m * (16 + e->O * (e->cfg.obs_f32 ? 4 : 8));
+    const bool small4 = !e->div && m_pad_of(e) == 4 && e->N >= 1024 && bytes_per_env * e->N <= ((int64_t)192 << 20);
+    const int dflt = (m_pad_of(e) <= 4 && e->N >= ((int64_t)1 << 20)) ? 256 : small4 ? 64 : 128;
     const int v = tt ? atoi(tt) : dflt;
     return ((v == 64 || v == 128 || v == 256 || v == 512) && v >= 2 * m_pad_of(e)) ? v : 256;
 }
@@ -213,9 +218,10 @@ static int m_pad_of(const imx_env* e) {
 }
 
 // shared-memory tile layout of the TMA kernel (regions 128-byte aligned); pure host arithmetic
-static void compute_tile(const imx_env* e, TileLayout& L, int tile_width, bool with_cc = false, bool cells = false) {
+static void compute_tile(const imx_env* e, TileLayout& L, int tile_width, bool with_cc = false, bool cells = false, int E_fixed = 0) {
     const int m = e->m;
-    const int E = cells ? 32 : (e->tma_threads / 32) * (32 / tile_width);     // cell mapping: 32 envs x m nodes = m full warps
+    // cell mapping: 32 envs x m nodes = m full warps; env-per-thread: one env per compute thread (E_fixed)
+    const int E = E_fixed > 0 ? E_fixed : cells ? 32 : (e->tma_threads / 32) * (32 / tile_width);
     int off = 0;
     auto take = [&](int bytes) { const int o = off; off += (bytes + 127) & ~127; return o; };
     L.E = E;
@@ -242,6 +248,16 @@ static void compute_tile(const imx_env* e, TileLayout& L, int tile_width, bool w
 }
 
 // -D options and template instantiations of the runtime-specialised build (imx_jit.cuh)
+// Ring depth of the pipelined kernel for a given tile layout.  Measured shapes (profiles/r2_pipe_sweep.txt, r2_step_et_sweep.txt):
+// four stages for the lane-mapped tiles, two for the env-per-thread tiles (their 32-env tiles are 2-3 x larger: a deeper ring
+// costs resident CTAs); the critic-row variant shortens its ring until four CTAs fit on an SM.
+static int pipe_stages_for(const imx_env* e, const TileLayout& L) {
+    const bool is_cc = (&L == &e->tile_cc);
+    int s = e->pipe_stages > 0 ? e->pipe_stages : ((e->step_et && !is_cc) ? 2 : 4);
+    while (s > 2 && ((int64_t)s * L.total > 200 * 1024 || (is_cc && (227 * 1024) / ((int64_t)s * L.total + 1024) < 4))) --s;
+    return s;
+}
+
 // dynamic shared memory of the cell-mapped rollout kernel (exchange arrays + the tile's Philox demand), 0 = not applicable
 static int rollout_cells_smem(const imx_env* e) {
     if (!e->rollout_cells) return 0;
@@ -285,7 +301,7 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
     {   // register bound of the plain step kernel, measured per family: the divergent kernels (natural 47) gain occupancy at 40
         // (div1 +5 %, div2 +1.5 %), the 2-wide chain is faster unconstrained (+8 % at 64), the others are best at their natural 32
         const char* sr = getenv("IMX_STEP_MAXNREG");
-        const int bound = sr ? atoi(sr) : (e->cells ? 0 : e->div ? 40 : (m_pad_of(e) == 2 ? 64 : 0));   // the cell-mapped kernel spills at 40
+        const int bound = sr ? atoi(sr) : ((e->cells || e->step_et) ? 0 : e->div ? 40 : (m_pad_of(e) == 2 ? 64 : 0));   // cell-mapped / env-per-thread kernels spill at 40
         if (bound > 0) defs.push_back("IMX_STEP_MAXNREG=" + std::to_string(bound));
     }
     {   // register bound of the rollout kernel.  Measured (profiles/r1_other_configs_1gpu.jsonl): the divergent kernel wants
@@ -300,7 +316,7 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
         const int maxnreg = mr ? atoi(mr) : 0;             // 0: the per-config default in imx_step_tma.cuh
         if (maxnreg > 0) defs.push_back("IMX_MANY_MAXNREG=" + std::to_string(maxnreg));
     }
-    defs.push_back("IMX_TMA_THREADS=" + std::to_string(e->jit_threads));
+    defs.push_back("IMX_TMA_THREADS=" + std::to_string((has_cc && e->step_et) ? e->tma_threads : e->jit_threads));
     // the device translation unit checks its view of the argument blocks against this host build (imx_jit.cuh)
     defs.push_back("IMX_HOST_SIZEOF_STEPARGS=" + std::to_string(sizeof(StepArgs)));
     defs.push_back("IMX_HOST_SIZEOF_TILELAYOUT=" + std::to_string(sizeof(TileLayout)));
@@ -313,14 +329,35 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
                               std::to_string(e->div ? maxc : 1) + ", " + dv + ">";
     sp.name[0] = "imx::step_kernel_tma" + targs;
     sp.name[1] = "imx::step_kernel_tma_many" + targs;
-    if (e->rollout_et) {
-        // env-per-thread rollout: the network as compile-time integer lists
+    const bool step_et = e->step_et && !has_cc;            // (the critic-row variant keeps the lane mapping and its tile geometry)
+    if (e->rollout_et || step_et) {
+        // env-per-thread kernels: the network as compile-time integer lists
         auto list = [&](const char* k, auto get) {
             std::string v;
             for (int i = 0; i < e->m; ++i) v += (i ? "," : "") + std::to_string((long long)get(i));
             defs.push_back(std::string("IMX_L_") + k + "=" + v);
         };
-        defs.push_back("IMX_ET=1");
+        if (e->rollout_et) defs.push_back("IMX_ET=1");
+        if (step_et) {
+            defs.push_back("IMX_STEP_ET=1");
+            auto bits = [&](const char* k, auto get) {
+                std::string v;
+                for (int i = 0; i < e->m; ++i) {
+                    const double d = get(i);
+                    unsigned long long u;
+                    memcpy(&u, &d, 8);
+                    char buf[32];
+                    snprintf(buf, sizeof(buf), "0x%016llxull", u);
+                    v += (i ? "," : "") + std::string(buf);
+                }
+                defs.push_back(std::string("IMX_L_") + k + "=" + v);
+            };
+            bits("p_bits", [&](int i) { return e->sell[i]; });
+            bits("c_bits", [&](int i) { return e->buy[i]; });
+            bits("h_bits", [&](int i) { return c.stock_cost[i]; });
+            bits("bc_bits", [&](int i) { return c.backlog_cost[i]; });
+            bits("target_bits", [&](int i) { return c.inv_target[i]; });
+        }
         list("inv_max", [&](int i) { return c.inv_max[i]; });
         list("order_max", [&](int i) { return c.order_max[i]; });
         list("demand_max", [&](int i) { return e->demand_max[i]; });
@@ -344,6 +381,8 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
             defs.push_back("IMX_L_bt_off=" + bo);
             defs.push_back("IMX_L_children=" + ch);
         }
+    }
+    if (e->rollout_et) {
         sp.name[2] = "imx::rollout_kernel_et<" + std::to_string(e->m) + ", " + std::to_string(e->D) + ", " + std::to_string(maxc) + ", " + dv + ">";
     } else if (rollout_cells_smem(e) > 0)
         sp.name[2] = "imx::rollout_kernel_cells<" + std::to_string(e->D) + ", " + std::to_string(e->div ? maxc : 1) + ", " + dv + ">";
@@ -352,8 +391,8 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
                      ", " + dv + ">";
     sp.name[3] = "";
     if (has_cc) { sp.name[1] = ""; sp.name[2] = ""; }      // the critic rows ride on the single-period kernels only
-    if (e->pipe_mode >= 0 && (int64_t)e->pipe_stages * L.total <= 200 * 1024) {
-        defs.push_back("IMX_PIPE_STAGES=" + std::to_string(e->pipe_stages));
+    if (e->pipe_mode >= 0 && (int64_t)pipe_stages_for(e, L) * L.total <= 200 * 1024) {
+        defs.push_back("IMX_PIPE_STAGES=" + std::to_string(pipe_stages_for(e, L)));
         const char* pr = getenv("IMX_PIPE_MAXNREG");
         if (pr && atoi(pr) > 0) defs.push_back("IMX_PIPE_MAXNREG=" + std::to_string(atoi(pr)));
         sp.name[3] = "imx::step_kernel_pipe" + targs;
@@ -364,7 +403,7 @@ static void jit_smem(const imx_env* e, int smem[imxjit::N_KERNELS]) {
     smem[0] = e->tile_jit.total;
     smem[1] = e->tile_jit.total2 <= 200 * 1024 ? e->tile_jit.total2 : e->tile_jit.total;
     smem[2] = rollout_cells_smem(e);
-    smem[3] = e->pipe_stages * e->tile_jit.total;
+    smem[3] = pipe_stages_for(e, e->tile_jit) * e->tile_jit.total;
 }
 
 // Loads the specialised kernels for this handle (large batches, or IMX_JIT=1).  Called from imx_create() /
@@ -407,7 +446,7 @@ static void ensure_jit_cc(imx_env* e) {
     if (e->jit_state != 1 || !e->multi || e->tile_cc.total > 200 * 1024) return;
     imxjit::Spec sp;
     jit_spec(e, e->TL, sp, 1, 1);
-    int smem[imxjit::N_KERNELS] = {e->tile_cc.total, 0, 0, e->pipe_stages * e->tile_cc.total};
+    int smem[imxjit::N_KERNELS] = {e->tile_cc.total, 0, 0, pipe_stages_for(e, e->tile_cc) * e->tile_cc.total};
     if (smem[3] > 200 * 1024) smem[3] = 0;
     e->jit_cc = imxjit::get(sp, smem, e->cfg.device);
     if (e->jit_cc) e->jit_cc_state = 1;
@@ -453,10 +492,19 @@ static int select_kernels(imx_env* e) {
         // env-per-thread rollout (imx_rollout_et.cuh): networks up to 8 nodes, lead times up to 4 (registers); IMX_ROLLOUT_ET=0 disables
         const char* re = getenv("IMX_ROLLOUT_ET");
         e->rollout_et = (re && !strcmp(re, "0")) ? 0 : (e->m <= 8 && e->D <= 4 && !e->rollout_cells);
-        e->jit_threads = e->cells ? 32 * e->m : e->tma_threads;
+        // env-per-thread STEP kernels: divergent networks up to 8 nodes (their lane-mapped kernels are issue-bound); IMX_STEP_ET=0/1
+        const char* se = getenv("IMX_STEP_ET");
+        const bool et_ok = e->m <= 8 && e->D <= 4 && e->P <= 2 && !e->cells;
+        // default: divergent networks whose node count is not a power of two (the lane mapping pads them: div2 runs 19 of 32 lanes);
+        // div2 262 144 envs 34.9 -> 33.6 us, 1 Mi envs 129 -> 115 us; no gain on the 4-node div1 (profiles/r2_step_et_sweep.txt)
+        const bool non_pow2 = (e->m & (e->m - 1)) != 0;
+        e->step_et = (se && !strcmp(se, "0")) ? 0 : (se && !strcmp(se, "1")) ? et_ok : (et_ok && e->div && non_pow2);
+        const char* st = getenv("IMX_STEP_ET_THREADS");
+        const int et_threads = (st && (atoi(st) == 32 || atoi(st) == 64 || atoi(st) == 128)) ? atoi(st) : 32;
+        e->jit_threads = e->step_et ? et_threads : e->cells ? 32 * e->m : e->tma_threads;
     }
-    compute_tile(e, e->tile_jit, e->step_dense ? e->m : m_pad_of(e), false, e->cells != 0);
-    compute_tile(e, e->tile_cc, e->step_dense ? e->m : m_pad_of(e), true, e->cells != 0);
+    compute_tile(e, e->tile_jit, e->step_dense ? e->m : m_pad_of(e), false, e->cells != 0, e->step_et ? e->jit_threads : 0);
+    compute_tile(e, e->tile_cc, e->step_dense ? e->m : m_pad_of(e), true, e->cells != 0 && !e->step_et);
     if (e->tile.total <= 200 * 1024) {
         IMX_CUDA(raise_dyn_smem_limit((const void*)e->tma_fn, (size_t)e->tile.total));
         if (e->tile.total2 <= 200 * 1024)
@@ -478,9 +526,8 @@ static int select_kernels(imx_env* e) {
         const char* pm = getenv("IMX_PIPE");
         e->pipe_mode = (pm && !strcmp(pm, "1")) ? 1 : (pm && !strcmp(pm, "0")) ? -1 : 0;
         const char* ps = getenv("IMX_PIPE_STAGES");
-        e->pipe_stages = ps ? atoi(ps) : 4;
-        if (e->pipe_stages < 2 || e->pipe_stages > 8) e->pipe_stages = 4;
-        while (e->pipe_stages > 2 && (int64_t)e->pipe_stages * e->tile_jit.total > 200 * 1024) --e->pipe_stages;
+        e->pipe_stages = ps ? atoi(ps) : 0;                 // 0: the measured default of pipe_stages_for()
+        if (e->pipe_stages < 2 || e->pipe_stages > 8) e->pipe_stages = 0;
         const char* pc = getenv("IMX_PIPE_CTAS");
         e->pipe_ctas = pc ? atoi(pc) : 0;
         e->sm_count = dev_sms;
@@ -933,27 +980,28 @@ extern "C" int imx_reset(imx_env* e, const int32_t* demand_dev, const uint8_t* d
     return 0;
 }
 
-// Resident CTAs per SM of the pipelined kernel: bounded by shared memory (S stages per CTA), threads, and a cap that
-// keeps enough tiles per CTA for the ring to overlap anything.
-static int pipe_ctas_per_sm(const imx_env* e) {
-    if (e->pipe_ctas > 0) return e->pipe_ctas;
-    const int by_smem = (int)((227 * 1024) / ((int64_t)e->pipe_stages * e->tile_jit.total + 1024));
-    const int by_thr = 2048 / (e->jit_threads + 32);
-    int c = by_smem < by_thr ? by_smem : by_thr;
-    if (c > 6) c = 6;
-    return c < 1 ? 1 : c;
-}
-// auto policy: the pipeline needs more than one tile per resident CTA to overlap anything
+// auto policy, measured (profiles/r2_pipe_sweep.txt): the pipelined kernel wins at every batch size on the divergent
+// networks (issue-bound kernels: +5-15 %) and on the serial chains while a launch's working set stays within ~1.5 x L2
+// (one-wave regime: -3 % .. -20 % per launch; even with one tile per CTA its compute warps retire early, which lets the
+// next dependent launch in sooner); for larger serial batches the one-tile-per-CTA kernel already runs at the HBM copy peak
+// and the ring's smaller resident tile count costs 5-10 %.
 static bool pipe_pays(const imx_env* e, int n_tiles) {
-    return (int64_t)n_tiles > (int64_t)e->sm_count * pipe_ctas_per_sm(e);
+    (void)n_tiles;
+    const int64_t bytes_per_env = 8 * (int64_t)e->S + 4 * e->R + (int64_t)e->m * (16 + e->O * (e->cfg.obs_f32 ? 4 : 8));
+    if (e->step_et) return bytes_per_env * e->N <= ((int64_t)384 << 20);   // env-per-thread tiles: one-tile kernel from ~0.5 Mi envs (div2: 115 vs 124 us at 1 Mi)
+    if (e->div) return true;
+    return bytes_per_env * e->N <= ((int64_t)192 << 20);
 }
+// CTAs launched per SM by the pipelined kernel (tiles are dealt round-robin over the grid).  Measured per family: 8 for the
+// 64-thread tiles of 4-wide chains, 6 for 8-lane divergent tiles and for the env-per-thread tiles (more CTAs than fit at once:
+// the late ones shorten everybody's tile list, which measured faster than a grid of exactly the resident CTAs), 4 otherwise.
 static int pipe_ctas_for(const imx_env* e, const TileLayout& L) {
     if (e->pipe_ctas > 0) return e->pipe_ctas;
-    const int by_smem = (int)((227 * 1024) / ((int64_t)e->pipe_stages * L.total + 1024));
-    const int by_thr = 2048 / (e->jit_threads + 32);
-    int c = by_smem < by_thr ? by_smem : by_thr;
-    if (c > 6) c = 6;
-    return c < 1 ? 1 : c;
+    const bool is_cc = (&L == &e->tile_cc);
+    if (e->step_et && !is_cc) return 6;
+    if (e->div) return m_pad_of(e) <= 4 ? 4 : 6;
+    if (e->jit_threads == 64) return 8;
+    return 4;
 }
 
 // periods > 1 (imx_step_many): the TMA kernel advances that many periods in one launch with the tiles' state resident
@@ -1028,19 +1076,20 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
             // persistent pipelined kernel (imx_step_pipe.cuh): a resident CTA walks over its tiles through a ring of stages
             PipeArgs PA;
             PA.n_tiles = (int32_t)(n_tma / TL_use.E);
-            PA.stages = e->pipe_stages;
+            PA.stages = pipe_stages_for(e, TL_use);
             const bool pipe = !fused && jk->step_pipe && e->pipe_mode >= 0 && (e->pipe_mode == 1 || pipe_pays(e, PA.n_tiles));
             void* params[] = {(void*)&A, (void*)&TL_use, (void*)&PA};
             CUlaunchConfig lc;
             memset(&lc, 0, sizeof(lc));
             lc.gridDimX = (unsigned)(n_tma / TL_use.E); lc.gridDimY = 1; lc.gridDimZ = 1;
-            lc.blockDimX = (unsigned)e->jit_threads; lc.blockDimY = 1; lc.blockDimZ = 1;
+            const unsigned jthreads = (unsigned)((with_cc && e->step_et) ? e->tma_threads : e->jit_threads);
+            lc.blockDimX = jthreads; lc.blockDimY = 1; lc.blockDimZ = 1;
             lc.sharedMemBytes = tma_smem;
             if (pipe) {
                 const int64_t resident = (int64_t)e->sm_count * pipe_ctas_for(e, TL_use);
                 lc.gridDimX = (unsigned)(PA.n_tiles < resident ? PA.n_tiles : resident);
-                lc.blockDimX = (unsigned)e->jit_threads + 32;
-                lc.sharedMemBytes = (unsigned)(e->pipe_stages * TL_use.total);
+                lc.blockDimX = jthreads + 32;
+                lc.sharedMemBytes = (unsigned)(PA.stages * TL_use.total);
             }
             lc.hStream = (CUstream)s;
             CUlaunchAttribute at[1];
@@ -1451,11 +1500,17 @@ extern "C" int imx_jit_compile_check(const imx_config* cfg, int variant, char* l
         tmp.rollout_cells = (rc && !strcmp(rc, "1")) ? (tmp.m <= 16) : 0;
         const char* re = getenv("IMX_ROLLOUT_ET");
         tmp.rollout_et = (re && !strcmp(re, "0")) ? 0 : (tmp.m <= 8 && tmp.D <= 4 && !tmp.rollout_cells);
-        tmp.jit_threads = tmp.cells ? 32 * tmp.m : tmp.tma_threads;
+        const char* se = getenv("IMX_STEP_ET");
+        const bool et_ok = tmp.m <= 8 && tmp.D <= 4 && tmp.P <= 2 && !tmp.cells;
+        const bool non_pow2 = (tmp.m & (tmp.m - 1)) != 0;
+        tmp.step_et = (se && !strcmp(se, "0")) ? 0 : (se && !strcmp(se, "1")) ? et_ok : (et_ok && tmp.div && non_pow2);
+        const char* st = getenv("IMX_STEP_ET_THREADS");
+        const int et_threads = (st && (atoi(st) == 32 || atoi(st) == 64 || atoi(st) == 128)) ? atoi(st) : 32;
+        tmp.jit_threads = tmp.step_et ? et_threads : tmp.cells ? 32 * tmp.m : tmp.tma_threads;
     }
     compute_tile(&tmp, tmp.tile, m_pad_of(&tmp));
-    compute_tile(&tmp, tmp.tile_jit, m_pad_of(&tmp), false, tmp.cells != 0);
-    compute_tile(&tmp, tmp.tile_cc, m_pad_of(&tmp), true, tmp.cells != 0);
+    compute_tile(&tmp, tmp.tile_jit, m_pad_of(&tmp), false, tmp.cells != 0, tmp.step_et ? tmp.jit_threads : 0);
+    compute_tile(&tmp, tmp.tile_cc, m_pad_of(&tmp), true, tmp.cells != 0 && !tmp.step_et);
     int TL = 0;
     build_tables(&tmp, &TL);
     imxjit::Spec sp;

@@ -11,6 +11,10 @@
 //     the other kernels (tile_period, lanes = stages), fence the async proxy and arrive on `done` (one arrival per warp).
 // Loads of the next tiles, the arithmetic and the stores of the previous tile overlap inside every SM, and no compute
 // warp ever blocks on a store.  Same tile layout, same results bit for bit (tests force both kernels).
+// Tiles are assigned statically (blockIdx.x, + gridDim.x, ...).  A dynamic scheduler (one atomicAdd per tile on a word of the
+// handle, re-zeroed by the last CTA) was built and measured: 40-60 % SLOWER at every size (config 2 at 65 536 envs: 8.1 us
+// against 5.7) — the atomic round trips sit on the producer's critical path and the launch-to-launch differences it was meant to
+// remove turned out to be occupancy, not tile-count quantisation (profiles/r2_pipe_sweep.txt, r2_dynamic_scheduler_sweep.txt).
 #pragma once
 
 #include "imx_step_tma.cuh"
@@ -137,7 +141,9 @@ __global__ void IMX_PIPE_BOUNDS step_kernel_pipe(const __grid_constant__ StepArg
                             st + KT(off_obs), reinterpret_cast<double*>(st + KT(off_rew))};
         const int64_t n0 = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * E;
         mbar_wait(&full[s], (uint32_t)((k / S) & 1));
-#if IMX_USE_CELLS
+#if IMX_USE_STEP_ET
+        tile_period_et<IMX_K_m, DMAX, PMAX, MAXC, DIV>(A, TLY, T, tid, A.t, n0, []() {});
+#elif IMX_USE_CELLS
         tile_period_cells<M_PAD, DMAX, PMAX, MAXC, DIV, false>(A, TLY, T, st, L, tid, CT, A.t, 0, n0, false, []() {});
 #else
         tile_period<M_PAD, DMAX, PMAX, MAXC, DIV, false>(A, TLY, T, L, A.t, 0, n0, false, []() {});

@@ -644,20 +644,41 @@ __device__ __forceinline__ void cc_build_row(const StepArgs& A, const TileSmem& 
     const int m = KF(m), O = KF(O);
     const int W = (m - 1) * (1 + O) + O;
     const int e0 = L.e_loc * m;
-    ObsT* row = reinterpret_cast<ObsT*>(cc_tile) + (size_t)L.cell * W;
-    const ObsT* ob = reinterpret_cast<const ObsT*>(S.obs);
+    constexpr int WPE = sizeof(ObsT) / 4;            // 32-bit words per element: the rows are only 4-byte aligned (W is odd for m = 2)
+    uint32_t* row = reinterpret_cast<uint32_t*>(cc_tile) + (size_t)L.cell * W * WPE;
+    const uint32_t* ob = reinterpret_cast<const uint32_t*>(S.obs);
+    const int row_words = O * WPE;                   // an observation row in words; rows start 16-byte aligned when this is a multiple of 4
     int k = 0;
     for (int j = 0; j < m; ++j) {
         if (j == L.i) continue;
-        row[k++] = A.cc_fill ? (ObsT)fmin(fmax(S.act[e0 + j], A.cc_lo), A.cc_hi) : (ObsT)0;
+        const ObsT v = A.cc_fill ? (ObsT)fmin(fmax(S.act[e0 + j], A.cc_lo), A.cc_hi) : (ObsT)0;
+        if constexpr (WPE == 1) {
+            row[k++] = __float_as_uint((float)v);
+        } else {
+            const unsigned long long u = (unsigned long long)__double_as_longlong((double)v);
+            row[k++] = (uint32_t)u;
+            row[k++] = (uint32_t)(u >> 32);
+        }
     }
+    // observation rows: 16-byte shared-memory loads (one wavefront per quarter-warp instead of the 8-way conflicts of scalar
+    // loads at a row stride of 32 or 64 bytes), scalar stores into the odd-strided critic row (conflict-free)
+    auto copy_row = [&](int cell_src) {
+        const uint32_t* src = ob + (size_t)cell_src * row_words;
+        if ((row_words & 3) == 0) {
+            for (int q = 0; q < row_words / 4; ++q) {
+                const uint4 v = reinterpret_cast<const uint4*>(src)[q];
+                row[k] = v.x; row[k + 1] = v.y; row[k + 2] = v.z; row[k + 3] = v.w;
+                k += 4;
+            }
+        } else {
+            for (int q = 0; q < row_words; ++q) row[k++] = src[q];
+        }
+    };
     for (int j = 0; j < m; ++j) {
         if (j == L.i) continue;
-        const ObsT* src = ob + (size_t)(e0 + j) * O;
-        for (int q = 0; q < O; ++q) row[k++] = src[q];
+        copy_row(e0 + j);
     }
-    const ObsT* own = ob + (size_t)L.cell * O;
-    for (int q = 0; q < O; ++q) row[k++] = own[q];
+    copy_row(L.cell);
 }
 template <int MAXC>
 __device__ __forceinline__ void cc_build(const StepArgs& A, const TileLayout& TLY, const TileSmem& S, unsigned char* tile_base, const LaneCtx<MAXC>& L,
@@ -671,6 +692,168 @@ __device__ __forceinline__ void cc_build(const StepArgs& A, const TileLayout& TL
     if (KF(obs_f32)) cc_build_row<float, MAXC>(A, S, tile_base + KT(off_cc), L);
     else cc_build_row<double, MAXC>(A, S, tile_base + KT(off_cc), L);
 }
+
+
+// Env-per-thread period (runtime-specialised build, -DIMX_STEP_ET=1, networks up to 8 nodes): thread e of the CTA's compute
+// group owns env e of the tile and walks over its m nodes in an unrolled loop — the network is a set of compile-time lists
+// (IMX_L_*), nothing is exchanged between threads, all 32 lanes of every warp are live and the divergent split costs each warp
+// its instruction stream once per 32 envs instead of once per 4.  Same arithmetic, same order, same tile layout as tile_period.
+// Used for the divergent networks, whose lanes = nodes kernels are issue-bound (profiles/r2_ncu_div2_step_kernel_lanes.txt).
+#if defined(IMX_JIT) && defined(IMX_STEP_ET) && IMX_STEP_ET
+#define IMX_USE_STEP_ET 1
+template <int M, int DMAX, int PMAX, int MAXC, bool DIV, typename BeforeStore>
+__device__ __forceinline__ void tile_period_et(const StepArgs& A, const TileLayout& TLY, const TileSmem& S, int e, int t, int64_t n0,
+                                               BeforeStore&& before_store) {
+    constexpr int INV_MAX[M] = {IMX_L_inv_max}, ORDER_MAX[M] = {IMX_L_order_max}, DEMAND_MAX[M] = {IMX_L_demand_max};
+    constexpr int DELAY[M] = {IMX_L_delay}, PIPE_OFF[M] = {IMX_L_pipe_off};
+    constexpr int NCHILD[M] = {IMX_L_nchild}, RETAILER[M] = {IMX_L_retailer_idx}, BT_OFF[M] = {IMX_L_bt_off};
+    constexpr int CHILDREN[M * MAXC] = {IMX_L_children};
+    // float64 cost constants of the nodes as bit patterns (literals: no loads, no registers)
+    constexpr unsigned long long P_BITS[M] = {IMX_L_p_bits}, C_BITS[M] = {IMX_L_c_bits}, H_BITS[M] = {IMX_L_h_bits}, BC_BITS[M] = {IMX_L_bc_bits},
+                                 TG_BITS[M] = {IMX_L_target_bits};
+    const int E = KT(E), O = KF(O);
+    const int es = KF(obs_f32) ? 4 : 8;
+    const int c0 = e * M;                            // first cell of this thread's env
+    int inv[M], bl[M], ou[M], cr[M], pipe[M][DMAX], hd[M][PMAX], ho[M][PMAX], bt[M][MAXC];
+    int order[M], demand[M], acq[M], ship[M], incoming[M];
+    // ---- read the env out of the tile -----------------------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        inv[j] = S.inv[c0 + j]; bl[j] = S.bl[c0 + j]; ou[j] = S.ou[c0 + j];
+        cr[j] = KF(has_carry) ? S.carry[c0 + j] : 0;
+#pragma unroll
+        for (int k = 0; k < DMAX; ++k) pipe[j][k] = (k < DELAY[j]) ? S.pipe[e * KF(L) + PIPE_OFF[j] + k] : 0;
+#pragma unroll
+        for (int q = 0; q < PMAX; ++q) {
+            hd[j][q] = (KF(need_hd) && q < KF(P)) ? S.hd[(c0 + j) * KF(P) + q] : 0;
+            ho[j][q] = (KF(need_ho) && q < KF(P)) ? S.ho[(c0 + j) * KF(P) + q] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) bt[j][k] = (DIV && NCHILD[j] > 1 && k < NCHILD[j]) ? S.bt[e * KF(NB) + BT_OFF[j] + k] : 0;
+        order[j] = decode_order(S.act[c0 + j], (double)ORDER_MAX[j], KF(std_actions) != 0, KF(multi) != 0, A.a, A.bma, A.inv_bma, KBMA_POW2);
+    }
+    // ---- demand propagation, acquisition, shipment ------------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        if (RETAILER[j] >= 0) {
+            demand[j] = min(S.dem[RETAILER[j] * E + e], INV_MAX[j]);
+        } else if (DIV) {
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k)
+                if (k < NCHILD[j]) sum += order[CHILDREN[j * MAXC + k] >= 0 ? CHILDREN[j * MAXC + k] : 0];
+            demand[j] = sum;
+        } else {
+            demand[j] = order[j > 0 ? j - 1 : 0];
+        }
+        int a = cr[j];
+        if (t >= DELAY[j]) a += pipe[j][0];
+        cr[j] = 0;                                   // (replayed noisy delays are served by the ahead-of-time kernels)
+        acq[j] = a;
+        ship[j] = min(bl[j] + demand[j], inv[j] + a);
+    }
+    int err_code = 0;
+    if constexpr (DIV) {
+        incoming[0] = order[0];
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            if (NCHILD[j] == 1) {
+                incoming[CHILDREN[j * MAXC] >= 0 ? CHILDREN[j * MAXC] : 0] = ship[j];
+            } else if (NCHILD[j] > 1) {
+                int od[MAXC], st[MAXC];
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) od[k] = (k < NCHILD[j]) ? order[CHILDREN[j * MAXC + k] >= 0 ? CHILDREN[j * MAXC + k] : 0] : 0;
+                const int code = split_ship<MAXC>(NCHILD[j], ship[j], demand[j], bl[j], DEMAND_MAX[j], KF(wd_mult1), KF(wd_mult), od, bt[j], st);
+                if (code != 0 && err_code == 0) err_code = code;
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k)
+                    if (k < NCHILD[j]) incoming[CHILDREN[j * MAXC + k] >= 0 ? CHILDREN[j * MAXC + k] : 0] = st[k];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < M; ++j) incoming[j] = (j == M - 1) ? order[j] : ship[j + 1 < M ? j + 1 : j];
+    }
+    // ---- state update, profit, reward ---------------------------------------------------------------------------------------
+    double profit[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        int b = bl[j] + demand[j] - ship[j];
+        if (KF(cap_backlog)) b = min(b, DEMAND_MAX[j]);
+        ou[j] = min(max(ou[j] + order[j] - acq[j], 0), INV_MAX[j]);
+        inv[j] = min(max(inv[j] + acq[j] - ship[j], 0), INV_MAX[j]);
+        bl[j] = b;
+#pragma unroll
+        for (int k = 0; k < DMAX; ++k) {
+            const int nxt = (k + 1 < DMAX) ? pipe[j][k + 1] : 0;
+            pipe[j][k] = (k == DELAY[j] - 1) ? incoming[j] : nxt;
+        }
+#pragma unroll
+        for (int q = PMAX - 1; q > 0; --q) { hd[j][q] = hd[j][q - 1]; ho[j][q] = ho[j][q - 1]; }
+        hd[j][0] = demand[j];
+        ho[j][0] = order[j];
+        profit[j] = profit_of(__longlong_as_double((long long)P_BITS[j]), __longlong_as_double((long long)C_BITS[j]),
+                              __longlong_as_double((long long)H_BITS[j]), __longlong_as_double((long long)BC_BITS[j]),
+                              __longlong_as_double((long long)TG_BITS[j]), ship[j], order[j], inv[j], bl[j]);
+    }
+    double reward[M];
+    if (KF(multi)) {
+        if (KF(independent)) {
+#pragma unroll
+            for (int j = 0; j < M; ++j) reward[j] = profit[j];
+        } else {
+            double sum = 0.0;
+#pragma unroll
+            for (int j = 0; j < M; ++j) sum = __dadd_rn(sum, profit[j]);
+            const double r = div_by_m(sum, M, A.inv_m, KM_POW2);
+#pragma unroll
+            for (int j = 0; j < M; ++j) reward[j] = r;
+        }
+    } else {
+        double r;
+        if constexpr (M < 8) {
+            r = 0.0;
+#pragma unroll
+            for (int j = 0; j < M; ++j) r = __dadd_rn(r, profit[j]);
+        } else {
+            r = __dadd_rn(__dadd_rn(__dadd_rn(profit[0], profit[1]), __dadd_rn(profit[2], profit[3])),
+                          __dadd_rn(__dadd_rn(profit[4], profit[5]), __dadd_rn(profit[6], profit[7])));
+        }
+        reward[0] = r;
+    }
+    // ---- write the tile back ----------------------------------------------------------------------------------------------
+    before_store();
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        S.inv[c0 + j] = inv[j]; S.bl[c0 + j] = bl[j]; S.ou[c0 + j] = ou[j];
+        if (KF(has_carry)) S.carry[c0 + j] = cr[j];
+#pragma unroll
+        for (int k = 0; k < DMAX; ++k)
+            if (k < DELAY[j]) S.pipe[e * KF(L) + PIPE_OFF[j] + k] = pipe[j][k];
+#pragma unroll
+        for (int q = 0; q < PMAX; ++q) {
+            if (KF(need_hd) && q < KF(P)) S.hd[(c0 + j) * KF(P) + q] = hd[j][q];
+            if (KF(need_ho) && q < KF(P)) S.ho[(c0 + j) * KF(P) + q] = ho[j][q];
+        }
+        if (DIV && NCHILD[j] > 1) {
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k)
+                if (k < NCHILD[j]) S.bt[e * KF(NB) + BT_OFF[j] + k] = bt[j][k];
+        }
+        if (KF(multi)) S.rew[c0 + j] = reward[j];
+        if (KHAS(obs)) {
+            NodeParams np;                           // the integer maxima write_obs_row scales with (compile-time values)
+            np.inv_max = INV_MAX[j]; np.order_max = ORDER_MAX[j]; np.demand_max = DEMAND_MAX[j];
+            const double* __restrict__ tabrow = KHAS(tab) ? A.tab + (size_t)j * 4 * KF(TL) : nullptr;
+            write_obs_row<DMAX, PMAX>(S.obs + (size_t)(c0 + j) * O * es, A, np, j, tabrow, inv[j], bl[j], ou[j], pipe[j], hd[j], ho[j], DIV);
+        }
+    }
+    if (!KF(multi)) S.rew[e] = reward[0];
+    if (DIV && err_code != 0) A.err[n0 + e] = err_code;
+}
+#else
+#define IMX_USE_STEP_ET 0
+#endif
 
 // MANY = false: one period per launch (the loop below folds away); MANY = true: A.periods periods per launch with the
 // tile's state resident in shared memory (imx_step_many) — separate kernels because the loop costs registers.
@@ -769,7 +952,10 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
             __syncthreads();
         }
     };
-#if IMX_USE_CELLS
+#if IMX_USE_STEP_ET
+    tile_period_et<IMX_K_m, DMAX, PMAX, MAXC, DIV>(A, TLY, S, tid, t, n0, before_store);
+    (void)L; (void)delayed;
+#elif IMX_USE_CELLS
     tile_period_cells<M_PAD, DMAX, PMAX, MAXC, DIV, MANY>(A, TLY, S, smem, L, tid, (int)blockDim.x, t, j, n0, delayed, before_store);
 #else
     tile_period<M_PAD, DMAX, PMAX, MAXC, DIV, MANY>(A, TLY, S, L, t, j, n0, delayed, before_store);
