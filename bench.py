@@ -358,7 +358,8 @@ def config4_episode_loop(name, total_envs, world, rank, dev, torch, dist, peak, 
            "scaling": "strong", "envs_total": total_envs, "envs_per_gpu": N, "agent_steps_per_sec": world * N * m * T * reps / dt,
            "ms_per_episode": dt / reps * 1e3,
            "step_kernel": {"us_per_launch": dts * 1e6, "achieved": B * N / dts / 1e9, "peak": peak, "unit": "GB/s", "frac": B * N / dts / 1e9 / peak,
-                           "algorithmic_bytes_per_env_step": B, "kernel": KERNEL_VARIANTS[variant]},
+                           "algorithmic_bytes_per_env_step": B, "kernel": KERNEL_VARIANTS[variant],
+                           "traffic": ncu_traffic(f"step_kernel_{name}_{N}")[0], "traffic_source": ncu_traffic(f"step_kernel_{name}_{N}")[1]},
            "watchdog_flags": flags, "mean_return": float((stats[1] / stats[0]).item()) if float(stats[0].item()) > 0 else None,
            "cpu_baseline_reference": reference_timing("config4_" + name)}
     del env
