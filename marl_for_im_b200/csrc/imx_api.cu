@@ -129,11 +129,9 @@ struct imx_env {
     int tma_threads = 256;               // CTA size of the TMA kernel (IMX_TMA_THREADS: 64, 128 or 256)
     int use_pdl = 1;                     // chain step launches with programmatic dependent launch (IMX_PDL=0 disables)
     int fuse_periods = 1;                // imx_step_many advances all its periods in one launch (IMX_FUSE_PERIODS=0: K plain launches)
-    int cells = 0;                       // specialised STEP kernels use the cell mapping (thread k = cell k of the [E][m] tile; IMX_CELLS=1)
     int step_et = 0;                     // the specialised STEP kernels use the env-per-thread period (IMX_STEP_ET; default: divergent networks, m <= 8)
     int rollout_et = 0;                  // the specialised ROLLOUT kernel is the env-per-thread one (imx_rollout_et.cuh; IMX_ROLLOUT_ET, default m <= 8)
-    int rollout_cells = 0;               // the specialised ROLLOUT kernel uses the cell mapping (IMX_ROLLOUT_CELLS; default: divergent networks)
-    int jit_threads = 128;               // CTA size (compute threads) of the specialised TMA kernels: tma_threads, or 32 * m with cells
+    int jit_threads = 128;               // CTA size (compute threads) of the specialised TMA kernels: tma_threads, or the env-per-thread group size
     int pipe_mode = 0;                   // persistent pipelined step kernel: 0 auto, 1 always, -1 never (IMX_PIPE)
     int pipe_stages = 0;                 // ring depth of the pipelined kernel (IMX_PIPE_STAGES; 0 = measured default)
     int pipe_ctas = 0;                   // resident CTAs per SM of the pipelined kernel (IMX_PIPE_CTAS; 0 = derived)
@@ -218,10 +216,10 @@ static int m_pad_of(const imx_env* e) {
 }
 
 // shared-memory tile layout of the TMA kernel (regions 128-byte aligned); pure host arithmetic
-static void compute_tile(const imx_env* e, TileLayout& L, int tile_width, bool with_cc = false, bool cells = false, int E_fixed = 0) {
+static void compute_tile(const imx_env* e, TileLayout& L, int tile_width, bool with_cc = false, int E_fixed = 0) {
     const int m = e->m;
-    // cell mapping: 32 envs x m nodes = m full warps; env-per-thread: one env per compute thread (E_fixed)
-    const int E = E_fixed > 0 ? E_fixed : cells ? 32 : (e->tma_threads / 32) * (32 / tile_width);
+    // lanes = nodes: (warps per CTA) x (envs per warp); env-per-thread: one env per compute thread (E_fixed)
+    const int E = E_fixed > 0 ? E_fixed : (e->tma_threads / 32) * (32 / tile_width);
     int off = 0;
     auto take = [&](int bytes) { const int o = off; off += (bytes + 127) & ~127; return o; };
     L.E = E;
@@ -238,7 +236,6 @@ static void compute_tile(const imx_env* e, TileLayout& L, int tile_width, bool w
     L.off_obs = take(E * m * e->O * (e->cfg.obs_f32 ? 4 : 8));
     L.off_rew = take(E * m * 8);
     L.off_cc = with_cc ? take(E * m * ((m - 1) * (1 + e->O) + e->O) * (e->cfg.obs_f32 ? 4 : 8)) : 0;
-    L.off_x = cells ? take(E * m * (8 + 4 * 4)) : 0;
     L.total = off;
     // multi-period launches double-buffer the per-period inputs; the extra regions sit behind the
     // single-period layout so that a plain step launches the same kernel with `total` bytes only
@@ -256,13 +253,6 @@ static int pipe_stages_for(const imx_env* e, const TileLayout& L) {
     int s = e->pipe_stages > 0 ? e->pipe_stages : ((e->step_et && !is_cc) ? 2 : 4);
     while (s > 2 && ((int64_t)s * L.total > 200 * 1024 || (is_cc && (227 * 1024) / ((int64_t)s * L.total + 1024) < 4))) --s;
     return s;
-}
-
-// dynamic shared memory of the cell-mapped rollout kernel (exchange arrays + the tile's Philox demand), 0 = not applicable
-static int rollout_cells_smem(const imx_env* e) {
-    if (!e->rollout_cells) return 0;
-    const int64_t bytes = (int64_t)32 * e->m * (8 + 5 * 4) + (int64_t)32 * e->R * ((e->T + 1) & ~1) * 4;
-    return bytes <= 96 * 1024 ? (int)bytes : 0;
 }
 
 static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1, int has_cc = 0) {
@@ -289,19 +279,11 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
     addt("E", L.E); addt("off_act", L.off_act); addt("off_inv", L.off_inv); addt("off_bl", L.off_bl); addt("off_ou", L.off_ou);
     addt("off_pipe", L.off_pipe); addt("off_hd", L.off_hd); addt("off_ho", L.off_ho); addt("off_carry", L.off_carry);
     addt("off_bt", L.off_bt); addt("off_dem", L.off_dem); addt("off_obs", L.off_obs); addt("off_rew", L.off_rew); addt("total", L.total);
-    addt("off_act2", L.off_act2); addt("off_dem2", L.off_dem2); addt("total2", L.total2); addt("off_cc", L.off_cc); addt("off_x", L.off_x);
-    if (e->cells) defs.push_back("IMX_CELLS=1");
-    if (rollout_cells_smem(e) > 0) defs.push_back("IMX_ROLLOUT_CELLS=1");
-    {
-        int nsplit = 0;
-        if (e->div)
-            for (int i = 0; i < e->m; ++i) nsplit += c.num_children[i] > 1;
-        add("nsplit", nsplit);
-    }
+    addt("off_act2", L.off_act2); addt("off_dem2", L.off_dem2); addt("total2", L.total2); addt("off_cc", L.off_cc);
     {   // register bound of the plain step kernel, measured per family: the divergent kernels (natural 47) gain occupancy at 40
         // (div1 +5 %, div2 +1.5 %), the 2-wide chain is faster unconstrained (+8 % at 64), the others are best at their natural 32
         const char* sr = getenv("IMX_STEP_MAXNREG");
-        const int bound = sr ? atoi(sr) : ((e->cells || e->step_et) ? 0 : e->div ? 40 : (m_pad_of(e) == 2 ? 64 : 0));   // cell-mapped / env-per-thread kernels spill at 40
+        const int bound = sr ? atoi(sr) : (e->step_et ? 0 : e->div ? 40 : (m_pad_of(e) == 2 ? 64 : 0));   // (the env-per-thread kernels spill at 40)
         if (bound > 0) defs.push_back("IMX_STEP_MAXNREG=" + std::to_string(bound));
     }
     {   // register bound of the rollout kernel.  Measured (profiles/r1_other_configs_1gpu.jsonl): the divergent kernel wants
@@ -384,9 +366,7 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
     }
     if (e->rollout_et) {
         sp.name[2] = "imx::rollout_kernel_et<" + std::to_string(e->m) + ", " + std::to_string(e->D) + ", " + std::to_string(maxc) + ", " + dv + ">";
-    } else if (rollout_cells_smem(e) > 0)
-        sp.name[2] = "imx::rollout_kernel_cells<" + std::to_string(e->D) + ", " + std::to_string(e->div ? maxc : 1) + ", " + dv + ">";
-    else
+    } else
         sp.name[2] = "imx::rollout_kernel<" + std::to_string(e->m) + ", " + std::to_string(e->D) + ", " + std::to_string(e->div ? maxc : 1) +
                      ", " + dv + ">";
     sp.name[3] = "";
@@ -402,7 +382,7 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
 static void jit_smem(const imx_env* e, int smem[imxjit::N_KERNELS]) {
     smem[0] = e->tile_jit.total;
     smem[1] = e->tile_jit.total2 <= 200 * 1024 ? e->tile_jit.total2 : e->tile_jit.total;
-    smem[2] = rollout_cells_smem(e);
+    smem[2] = 0;
     smem[3] = pipe_stages_for(e, e->tile_jit) * e->tile_jit.total;
 }
 
@@ -480,31 +460,22 @@ static int select_kernels(imx_env* e) {
     // ranges (e.g. 40 envs x 6 nodes x 4 B = 960 B) straddle 128-byte lines, measured slower at 262144 envs;
     // the issue-bound ROLLOUT kernel is specialised with tile width = m (dense lane packing, +21% on div2)
     {
-        // Cell mapping (thread k = cell k of a [32][m] tile, coupling through shared memory, the split re-packed into tasks).
-        // ROLLOUT kernel: default for divergent networks up to 16 nodes (issue-bound loop: half the instructions).
-        // STEP kernels: opt-in (IMX_CELLS=1) — measured SLOWER than the lane mapping although they execute 36 % fewer
-        // instructions (profiles/r2_ncu_div2_step_kernel_{lanes,cells}.txt): four CTA barriers per period and 6-warp tiles
-        // leave the kernel latency-bound (issue-active 40 %, long-scoreboard + barrier stalls) instead of issue-bound.
-        const char* cm = getenv("IMX_CELLS");
-        e->cells = (cm && !strcmp(cm, "1")) ? (e->m <= 16) : 0;
-        const char* rc = getenv("IMX_ROLLOUT_CELLS");
-        e->rollout_cells = (rc && !strcmp(rc, "1")) ? (e->m <= 16) : 0;      // opt-in: measured no faster than the lane mapping (profiles/r2_rollout_mappings.txt)
         // env-per-thread rollout (imx_rollout_et.cuh): networks up to 8 nodes, lead times up to 4 (registers); IMX_ROLLOUT_ET=0 disables
         const char* re = getenv("IMX_ROLLOUT_ET");
-        e->rollout_et = (re && !strcmp(re, "0")) ? 0 : (e->m <= 8 && e->D <= 4 && !e->rollout_cells);
+        e->rollout_et = (re && !strcmp(re, "0")) ? 0 : (e->m <= 8 && e->D <= 4);
         // env-per-thread STEP kernels: divergent networks up to 8 nodes (their lane-mapped kernels are issue-bound); IMX_STEP_ET=0/1
         const char* se = getenv("IMX_STEP_ET");
-        const bool et_ok = e->m <= 8 && e->D <= 4 && e->P <= 2 && !e->cells;
+        const bool et_ok = e->m <= 8 && e->D <= 4 && e->P <= 2;
         // default: divergent networks whose node count is not a power of two (the lane mapping pads them: div2 runs 19 of 32 lanes);
         // div2 262 144 envs 34.9 -> 33.6 us, 1 Mi envs 129 -> 115 us; no gain on the 4-node div1 (profiles/r2_step_et_sweep.txt)
         const bool non_pow2 = (e->m & (e->m - 1)) != 0;
         e->step_et = (se && !strcmp(se, "0")) ? 0 : (se && !strcmp(se, "1")) ? et_ok : (et_ok && e->div && non_pow2);
         const char* st = getenv("IMX_STEP_ET_THREADS");
         const int et_threads = (st && (atoi(st) == 32 || atoi(st) == 64 || atoi(st) == 128)) ? atoi(st) : 32;
-        e->jit_threads = e->step_et ? et_threads : e->cells ? 32 * e->m : e->tma_threads;
+        e->jit_threads = e->step_et ? et_threads : e->tma_threads;
     }
-    compute_tile(e, e->tile_jit, e->step_dense ? e->m : m_pad_of(e), false, e->cells != 0, e->step_et ? e->jit_threads : 0);
-    compute_tile(e, e->tile_cc, e->step_dense ? e->m : m_pad_of(e), true, e->cells != 0 && !e->step_et);
+    compute_tile(e, e->tile_jit, e->step_dense ? e->m : m_pad_of(e), false, e->step_et ? e->jit_threads : 0);
+    compute_tile(e, e->tile_cc, e->step_dense ? e->m : m_pad_of(e), true);
     if (e->tile.total <= 200 * 1024) {
         IMX_CUDA(raise_dyn_smem_limit((const void*)e->tma_fn, (size_t)e->tile.total));
         if (e->tile.total2 <= 200 * 1024)
@@ -684,10 +655,6 @@ static void fill_args(const imx_env* e, StepArgs& A) {
     A.hist_o = (int32_t*)e->field_ptr[IMX_F_HIST_O];
     A.carry = (int32_t*)e->field_ptr[IMX_F_CARRY];
     A.bt = (int32_t*)e->field_ptr[IMX_F_BACKLOG_TO];
-    A.nsplit = 0;
-    if (e->div)
-        for (int i = 0; i < e->m && A.nsplit < IMX_MAX_NODES / 2; ++i)
-            if (c.num_children[i] > 1) A.split_nodes[A.nsplit++] = (int8_t)i;
     A.err = e->d_err;
     A.demand_T = e->d_demand_T;
     A.mask_T = e->d_mask_T;
@@ -1274,16 +1241,6 @@ extern "C" int imx_rollout_basestock(imx_env* e, const double* z_dev, int z_stri
         if (cr != CUDA_SUCCESS) return fail(-3, "launch of the env-per-thread rollout kernel failed (CUresult %d)", (int)cr);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e->last_variant = 2;
-    } else if (e->jit_state == 1 && e->jit->rollout && rollout_cells_smem(e) > 0) {
-        void* params[] = {(void*)&A, (void*)&Rg};
-        const int64_t n_tiles = (e->N + 31) / 32;
-        const int64_t cap = (int64_t)e->sm_count * 8;
-        Rg.coop_demand = 0;
-        const CUresult cr = imxjit::g_api.LaunchKernel(e->jit->rollout, (unsigned)(n_tiles < cap ? n_tiles : cap), 1, 1, (unsigned)(32 * e->m), 1, 1,
-                                                       (unsigned)rollout_cells_smem(e), (CUstream)s, params, nullptr);
-        if (cr != CUDA_SUCCESS) return fail(-3, "launch of the cell-mapped rollout kernel failed (CUresult %d)", (int)cr);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        e->last_variant = 2;
     } else if (e->jit_state == 1 && e->jit->rollout) {
         void* params[] = {(void*)&A, (void*)&Rg};
         const int epw_j = 32 / e->m;                         // dense packing in the specialised build
@@ -1494,23 +1451,19 @@ extern "C" int imx_jit_compile_check(const imx_config* cfg, int variant, char* l
     if (rc) return rc;
     tmp.tma_threads = choose_tma_threads(&tmp);
     {
-        const char* cm = getenv("IMX_CELLS");
-        tmp.cells = (cm && !strcmp(cm, "1")) ? (tmp.m <= 16) : 0;
-        const char* rc = getenv("IMX_ROLLOUT_CELLS");
-        tmp.rollout_cells = (rc && !strcmp(rc, "1")) ? (tmp.m <= 16) : 0;
         const char* re = getenv("IMX_ROLLOUT_ET");
-        tmp.rollout_et = (re && !strcmp(re, "0")) ? 0 : (tmp.m <= 8 && tmp.D <= 4 && !tmp.rollout_cells);
+        tmp.rollout_et = (re && !strcmp(re, "0")) ? 0 : (tmp.m <= 8 && tmp.D <= 4);
         const char* se = getenv("IMX_STEP_ET");
-        const bool et_ok = tmp.m <= 8 && tmp.D <= 4 && tmp.P <= 2 && !tmp.cells;
+        const bool et_ok = tmp.m <= 8 && tmp.D <= 4 && tmp.P <= 2;
         const bool non_pow2 = (tmp.m & (tmp.m - 1)) != 0;
         tmp.step_et = (se && !strcmp(se, "0")) ? 0 : (se && !strcmp(se, "1")) ? et_ok : (et_ok && tmp.div && non_pow2);
         const char* st = getenv("IMX_STEP_ET_THREADS");
         const int et_threads = (st && (atoi(st) == 32 || atoi(st) == 64 || atoi(st) == 128)) ? atoi(st) : 32;
-        tmp.jit_threads = tmp.step_et ? et_threads : tmp.cells ? 32 * tmp.m : tmp.tma_threads;
+        tmp.jit_threads = tmp.step_et ? et_threads : tmp.tma_threads;
     }
     compute_tile(&tmp, tmp.tile, m_pad_of(&tmp));
-    compute_tile(&tmp, tmp.tile_jit, m_pad_of(&tmp), false, tmp.cells != 0, tmp.step_et ? tmp.jit_threads : 0);
-    compute_tile(&tmp, tmp.tile_cc, m_pad_of(&tmp), true, tmp.cells != 0 && !tmp.step_et);
+    compute_tile(&tmp, tmp.tile_jit, m_pad_of(&tmp), false, tmp.step_et ? tmp.jit_threads : 0);
+    compute_tile(&tmp, tmp.tile_cc, m_pad_of(&tmp), true);
     int TL = 0;
     build_tables(&tmp, &TL);
     imxjit::Spec sp;

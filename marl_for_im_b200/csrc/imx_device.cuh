@@ -41,22 +41,7 @@ typedef unsigned long uintptr_t;
 #define KNOISY_DEMAND(g) ((g).noise_thr > 0.0)
 #endif
 
-// cell mapping of the runtime-specialised kernels: step kernels (see imx_step_tma.cuh) and the fused rollout (imx_rollout.cuh)
-#if defined(IMX_JIT) && defined(IMX_CELLS) && IMX_CELLS
-#define IMX_USE_CELLS 1
-#else
-#define IMX_USE_CELLS 0
-#endif
-#if defined(IMX_JIT) && defined(IMX_ROLLOUT_CELLS) && IMX_ROLLOUT_CELLS
-#define IMX_USE_ROLLOUT_CELLS 1
-#else
-#define IMX_USE_ROLLOUT_CELLS 0
-#endif
-
 namespace imx {
-
-// named barrier of a CTA's compute threads (id 1; bar 0 = __syncthreads stays free for the whole CTA)
-__device__ __forceinline__ void cells_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
 // ------------------------------------------------------------------------------------
 // Per-node constants.  Lives in global memory (one small table per env handle); every thread
@@ -161,8 +146,6 @@ struct StepArgs {
     int64_t rew_stride;                     // doubles between consecutive periods' reward blocks
     // centralised-critic observation emitted by the step itself (imx_step_cc; models/CC_Model.py:165-214): for every agent the
     // row [opponent actions (m-1) | opponent observations (m-1)*O | own observation O], in the observation element type
-    int32_t nsplit;                         // divergent: nodes with more than one child ...
-    int8_t split_nodes[IMX_MAX_NODES / 2];  // ... and their indices (the cell-mapped kernels hand each (env, split node) pair to one thread)
     void* __restrict__ cc;                  // [N][m][W] or nullptr
     int32_t cc_fill;                        // 1: opponent-action slots = clip(this step's actions, cc_lo, cc_hi); 0: zeros
     int32_t cc_W;                           // (m-1)*(1+O) + O

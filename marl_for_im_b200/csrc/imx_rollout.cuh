@@ -225,223 +225,4 @@ __global__ void IMX_ROLLOUT_BOUNDS rollout_kernel(const __grid_constant__ StepAr
 }
 
 
-#if IMX_USE_ROLLOUT_CELLS
-// The cell-mapped rollout (runtime-specialised build, divergent networks): a CTA of 32 * m threads simulates 32 envs, thread
-// k owns cell k (env k / m, node k % m) for the whole episode — its state stays in registers — and every (env, split node)
-// pair is one TASK owned by one of the first 32 * nsplit threads, whose ledger row also stays in registers.  The per-period
-// coupling (orders up, shipments / split inflows down, profits across) goes through five small shared arrays and four named
-// barriers instead of shuffles, so all 32 lanes of every warp are live and the divergent split runs on full warps
-// (the lanes = nodes kernel above: 30 of 32 lanes, the split on 2 lanes of every 6).  Same arithmetic, same results.
-#if defined(IMX_ROLLOUT_CELLS_MAXNREG)
-#define IMX_ROLLOUT_CELLS_BOUNDS __maxnreg__(IMX_ROLLOUT_CELLS_MAXNREG)
-#else
-#define IMX_ROLLOUT_CELLS_BOUNDS __launch_bounds__(32 * IMX_K_m)
-#endif
-template <int DMAX, int MAXC, bool DIV>
-__global__ void IMX_ROLLOUT_CELLS_BOUNDS rollout_kernel_cells(const __grid_constant__ StepArgs A, const __grid_constant__ RolloutArgs Rg) {
-    constexpr int E = 32;
-    constexpr int m = IMX_K_m, T = IMX_K_T, R = IMX_K_R, NS = IMX_K_nsplit;
-    constexpr int CELLS = E * m, CT = CELLS;
-    constexpr int T_even = (T + 1) & ~1;
-    extern __shared__ __align__(16) unsigned char smem_rc[];
-    double* x_profit = reinterpret_cast<double*>(smem_rc);          // [CELLS]
-    int32_t* x_order = reinterpret_cast<int32_t*>(x_profit + CELLS);
-    int32_t* x_ship = x_order + CELLS;
-    int32_t* x_dem = x_ship + CELLS;
-    int32_t* x_inc = x_dem + CELLS;
-    int32_t* x_bl = x_inc + CELLS;
-    int32_t* s_draws = x_bl + CELLS;                                // [E][R][T_even] Philox demand of the tile's episode
-    const int tid = threadIdx.x;
-    const int i = tid % m, e_loc = tid / m, cell = tid, e0 = e_loc * m;
-    const NodeParams np = load_node(A.nodes + i);
-    int child_lane[MAXC];
-#pragma unroll
-    for (int k = 0; k < MAXC; ++k) child_lane[k] = DIV ? child_lane_of(np, k) : -1;
-    const bool is_last = (i == m - 1);
-    const int delay_m1 = np.delay - 1;
-    const double om_d = (double)np.order_max;
-    // split task of this thread (constant over the run)
-    const bool is_task = DIV && NS > 0 && tid < E * NS;
-    const int te = is_task ? tid / (NS > 0 ? NS : 1) : 0;
-    const int tp = is_task ? (int)A.split_nodes[tid % (NS > 0 ? NS : 1)] : 0;
-    const NodeParams pn = load_node(A.nodes + tp);
-    int task_child[MAXC];
-#pragma unroll
-    for (int k = 0; k < MAXC; ++k) task_child[k] = child_lane_of(pn, k);
-
-    const int64_t n_tiles = (A.N + E - 1) / E;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t n = tile * E + e_loc;
-        const bool ok = n < A.N;
-        const int64_t tn = tile * E + te;
-        const bool task_ok = is_task && tn < A.N;
-        const int64_t gcell = n * m + i;
-        int inv = np.init_inv, backlog = 0, order_u = 0, carry = 0;
-        int pipe[DMAX], bt[MAXC];
-#pragma unroll
-        for (int k = 0; k < DMAX; ++k) pipe[k] = 0;
-#pragma unroll
-        for (int k = 0; k < MAXC; ++k) bt[k] = 0;
-        const double z = ok ? Rg.z[Rg.z_stride ? gcell : (int64_t)i] : 0.0;
-        const int32_t* dem_row = (ok && Rg.demand && np.retailer_idx >= 0) ? Rg.demand + (n * R + np.retailer_idx) * T : nullptr;
-        cells_bar(CT);                                   // the previous tile's readers of s_draws / x_* are done
-        if (!Rg.demand) {                                // every thread draws a share of the tile's (env, retailer, period-pair) demands
-            constexpr int PAIRS = E * R * (T_even / 2);
-            for (int q = tid; q < PAIRS; q += CT) {
-                const int e = q / (R * (T_even / 2)), rq = q % (R * (T_even / 2));
-                const int r = rq / (T_even / 2), t2 = (rq % (T_even / 2)) * 2;
-                int d0 = 0, d1 = 0;
-                if (tile * E + e < A.N) draw_demand_pair(Rg.gen, tile * E + e, r, t2, d0, d1);
-                s_draws[(e * R + r) * T_even + t2] = d0;
-                s_draws[(e * R + r) * T_even + t2 + 1] = d1;
-            }
-            cells_bar(CT);
-        }
-        double ret = 0.0;
-        int err_code = 0;
-
-        for (int t = 0; t < T; ++t) {
-            // ---- A: order-up-to policy (base_restock_policy.py:12-20) and order decoding
-            const double raw = __dsub_rn(z, (double)(inv + order_u - backlog));
-            const double act = KF(std_actions) ? (raw < 0.0 ? 0.0 : (raw > om_d ? om_d : raw)) : raw;
-            const int order = ok ? decode_order(act, om_d, KF(std_actions) != 0, KF(multi) != 0, A.a, A.bma, A.inv_bma, KBMA_POW2) : 0;
-            x_order[cell] = order;
-            if (DIV && np.nchild > 1) x_bl[cell] = backlog;
-            cells_bar(CT);
-            // ---- B: demand, acquisition, shipment
-            int demand = 0;
-            if constexpr (DIV) {
-                if (np.retailer_idx >= 0) {
-                    const int cust = ok ? (dem_row ? dem_row[t] : s_draws[(e_loc * R + np.retailer_idx) * T_even + t]) : 0;
-                    demand = min(cust, np.inv_max);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < MAXC; ++k)
-                        if (k < np.nchild) demand += x_order[e0 + child_lane[k]];
-                }
-            } else {
-                if (i == 0) {
-                    const int cust = ok ? (dem_row ? dem_row[t] : s_draws[(e_loc * R) * T_even + t]) : 0;
-                    demand = min(cust, np.inv_max);
-                } else {
-                    demand = x_order[cell - 1];
-                }
-            }
-            int acq = (t >= np.delay) ? pipe[0] : 0;
-            if (KF(has_carry)) {
-                if (Rg.noisy) {
-                    acq += carry;
-                    carry = 0;
-                    if (ok && t >= np.delay && t < T - 1) {
-                        const bool delayed = Rg.mask ? (Rg.mask[(n * T + t) * m + i] != 0)
-                                                     : draw_delay(Rg.gen.seed, Rg.gen.env_offset + n, i, t, Rg.gen.episode, Rg.delay_thr);
-                        if (delayed) { carry = acq; acq = 0; }
-                    }
-                }
-            }
-            const int ship = min(backlog + demand, inv + acq);
-            x_ship[cell] = ship;
-            if (DIV && np.nchild > 1) x_dem[cell] = demand;
-            cells_bar(CT);
-            // ---- C: the divergent split, one task per (env, split node)
-            if constexpr (DIV && NS > 0) {
-                if (is_task) {
-                    const int c0 = te * m;
-                    int od[MAXC], st[MAXC];
-#pragma unroll
-                    for (int k = 0; k < MAXC; ++k) { od[k] = (k < pn.nchild) ? x_order[c0 + task_child[k]] : 0; st[k] = 0; }
-                    const int code = split_ship<MAXC>(pn.nchild, x_ship[c0 + tp], x_dem[c0 + tp], x_bl[c0 + tp], pn.demand_max, KF(wd_mult1), KF(wd_mult), od, bt, st);
-                    if (code != 0 && err_code == 0) err_code = code;
-#pragma unroll
-                    for (int k = 0; k < MAXC; ++k)
-                        if (k < pn.nchild) x_inc[c0 + task_child[k]] = st[k];
-                }
-                cells_bar(CT);
-            }
-            // ---- D: state update, profit, reward
-            int incoming = order;
-            if constexpr (DIV) {
-                if (np.parent >= 0) incoming = (np.parent_nchild > 1) ? x_inc[cell] : x_ship[e0 + np.parent];
-            } else {
-                if (!is_last) incoming = x_ship[cell + 1];
-            }
-            int backlog_new = backlog + demand - ship;
-            if (KF(cap_backlog)) backlog_new = min(backlog_new, np.demand_max);
-            order_u = min(max(order_u + order - acq, 0), np.inv_max);
-            inv = min(max(inv + acq - ship, 0), np.inv_max);
-            backlog = backlog_new;
-#pragma unroll
-            for (int k = 0; k < DMAX; ++k) {
-                const int nxt = (k + 1 < DMAX) ? pipe[k + 1] : 0;
-                pipe[k] = (k == delay_m1) ? incoming : nxt;
-            }
-            const double profit = ok ? profit_of(np.p, np.c, np.h, np.bc, np.target, ship, order, inv, backlog) : 0.0;
-            double r = profit;
-            if (!(KF(multi) && KF(independent))) {
-                x_profit[cell] = profit;
-                cells_bar(CT);
-                const double* row = x_profit + e0;
-                if (KF(multi)) {
-                    double sum = 0.0;
-#pragma unroll
-                    for (int q = 0; q < m; ++q) sum = __dadd_rn(sum, row[q]);
-                    r = div_by_m(sum, m, A.inv_m, KM_POW2);
-                } else {
-                    // np.sum order (numpy pairwise_sum, n <= 128)
-                    if (m < 8) {
-                        double sum = 0.0;
-#pragma unroll
-                        for (int q = 0; q < m; ++q) sum = __dadd_rn(sum, row[q]);
-                        r = sum;
-                    } else {
-                        double acc[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) acc[q] = row[q];
-                        int q = 8;
-                        for (; q < m - (m % 8); q += 8) {
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) acc[u] = __dadd_rn(acc[u], row[q + u]);
-                        }
-                        double sum = __dadd_rn(__dadd_rn(__dadd_rn(acc[0], acc[1]), __dadd_rn(acc[2], acc[3])),
-                                               __dadd_rn(__dadd_rn(acc[4], acc[5]), __dadd_rn(acc[6], acc[7])));
-                        for (; q < m; ++q) sum = __dadd_rn(sum, row[q]);
-                        r = sum;
-                    }
-                }
-            }
-            ret = __dadd_rn(ret, r);
-            if (ok && Rg.step_reward) {
-                if (KF(multi)) Rg.step_reward[(int64_t)t * A.N * m + gcell] = r;
-                else if (i == 0) Rg.step_reward[(int64_t)t * A.N + n] = r;
-            }
-        }
-
-        if (ok) {
-            if (KF(multi)) Rg.ret[gcell] = ret;
-            else if (i == 0) Rg.ret[n] = ret;
-            if (Rg.write_state) {
-                A.inv[gcell] = inv;
-                A.backlog[gcell] = backlog;
-                A.order_u[gcell] = order_u;
-                int32_t* pp = A.pipe + n * KF(L) + np.pipe_off;
-#pragma unroll
-                for (int k = 0; k < DMAX; ++k)
-                    if (k < np.delay) pp[k] = pipe[k];
-                if (KF(has_carry)) A.carry[gcell] = carry;
-            }
-        }
-        if constexpr (DIV) {
-            if (task_ok) {
-                if (Rg.write_state) {
-#pragma unroll
-                    for (int k = 0; k < MAXC; ++k)
-                        if (k < pn.nchild) A.bt[tn * KF(NB) + pn.bt_off + k] = bt[k];
-                }
-                if (err_code != 0) A.err[tn] = err_code;       // (several split nodes of one env may race to store a code: any of them is a valid report)
-            }
-        }
-    }
-}
-#endif  // IMX_USE_ROLLOUT_CELLS
-
 }  // namespace imx

@@ -143,8 +143,6 @@ __global__ void IMX_PIPE_BOUNDS step_kernel_pipe(const __grid_constant__ StepArg
         mbar_wait(&full[s], (uint32_t)((k / S) & 1));
 #if IMX_USE_STEP_ET
         tile_period_et<IMX_K_m, DMAX, PMAX, MAXC, DIV>(A, TLY, T, tid, A.t, n0, []() {});
-#elif IMX_USE_CELLS
-        tile_period_cells<M_PAD, DMAX, PMAX, MAXC, DIV, false>(A, TLY, T, st, L, tid, CT, A.t, 0, n0, false, []() {});
 #else
         tile_period<M_PAD, DMAX, PMAX, MAXC, DIV, false>(A, TLY, T, L, A.t, 0, n0, false, []() {});
 #endif

@@ -37,7 +37,6 @@ struct TileLayout {
     int32_t off_act2, off_dem2;
     int32_t total2;            // dynamic shared memory bytes of a multi-period launch (second buffers sit behind `total`)
     int32_t off_cc;            // centralised-critic rows [E][m][W] (layouts built for imx_step_cc only; inside `total`)
-    int32_t off_x;             // cell-mapped kernels: exchange arrays profit f64 [E*m], then order, ship, demand, inflow i32 [E*m] each
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -140,37 +139,8 @@ struct LaneCtx {
     bool ok, is_last;
 };
 
-// Cell mapping (runtime-specialised build, -DIMX_CELLS=1): thread k of the CTA owns cell k of the [E][m] tile (env k / m,
-// node k % m), so a network whose node count is not a power of two (div2: m = 6) keeps all 32 lanes of every warp busy —
-// the lanes = stages mapping pads each env to 8 lanes and runs 19 of 32 lanes on average
-// (profiles/r1_ncu_div2_step_kernel_final.txt).  An env then straddles warps, so the stage coupling goes through small
-// exchange arrays in the tile (orders, shipments, demands, split inflows, profits) and named CTA barriers instead of
-// shuffles, and the divergent split — the only long divergent stretch — is re-packed: every (env, split node) pair is
-// ONE task, tasks are handed to consecutive threads, so the split runs on full warps instead of 2 lanes of every 8.
-
 template <int M_PAD, int MAXC, bool DIV>
 __device__ __forceinline__ LaneCtx<MAXC> make_lane_ctx(const StepArgs& A, int tid) {
-#if IMX_USE_CELLS
-    LaneCtx<MAXC> L;
-    const int m = KF(m);
-    L.lane = tid & 31;
-    L.i = tid % m;
-    L.e_loc = tid / m;
-    L.tbase = 0;
-    L.cell = tid;
-    L.ok = tid < KT(E) * m;
-    L.np = load_node(A.nodes + (L.ok ? L.i : 0));
-    if constexpr (DIV) {
-#pragma unroll
-        for (int k = 0; k < MAXC; ++k) L.child_lane[k] = L.ok ? child_lane_of(L.np, k) : -1;
-    } else {
-#pragma unroll
-        for (int k = 0; k < MAXC; ++k) L.child_lane[k] = -1;
-    }
-    L.is_last = (L.i == m - 1);
-    L.tabrow = KHAS(tab) ? A.tab + (size_t)(L.ok ? L.i : 0) * 4 * KF(TL) : nullptr;
-    return L;
-#else
     constexpr int EPW = 32 / M_PAD;
     LaneCtx<MAXC> L;
     L.lane = tid & 31;
@@ -192,229 +162,8 @@ __device__ __forceinline__ LaneCtx<MAXC> make_lane_ctx(const StepArgs& A, int ti
     L.is_last = (L.i == m - 1);
     L.tabrow = KHAS(tab) ? A.tab + (size_t)(L.ok ? L.i : 0) * 4 * KF(TL) : nullptr;
     return L;
-#endif
 }
 
-#if IMX_USE_CELLS
-// np.sum order (numpy pairwise_sum for n <= 128) over the env's m profits in shared memory — IM_env.py:372, IM_div_env.py:561
-__device__ __forceinline__ double cells_np_sum(const double* row, int m) {
-    if (m < 8) {
-        double s = 0.0;
-        for (int j = 0; j < m; ++j) s = __dadd_rn(s, row[j]);
-        return s;
-    }
-    double r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = row[j];
-    int q = 8;
-    for (; q < m - (m % 8); q += 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], row[q + j]);
-    }
-    double s = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-    for (; q < m; ++q) s = __dadd_rn(s, row[q]);
-    return s;
-}
-
-// The cell-mapped period: same arithmetic and results as tile_period below, coupling through the tile's exchange arrays.
-// Every thread of the CTA's compute group (nthreads = E * m rounded up to whole warps) calls it; four named barriers.
-template <int M_PAD, int DMAX, int PMAX, int MAXC, bool DIV, bool MANY, typename BeforeStore>
-__device__ __forceinline__ void tile_period_cells(const StepArgs& A, const TileLayout& TLY, const TileSmem& S, unsigned char* tile_base,
-                                                  const LaneCtx<MAXC>& L, int tid, int nthreads, int t, int j, int64_t n0, bool delayed,
-                                                  BeforeStore&& before_store) {
-    const NodeParams& np = L.np;
-    const int lane = L.lane, i = L.i, e_loc = L.e_loc, cell = L.cell;
-    const bool ok = L.ok, is_last = L.is_last;
-    const int m = KF(m), O = KF(O), E = KT(E);
-    const int es = KF(obs_f32) ? 4 : 8;
-    const int cells = E * m;
-    const int e0 = e_loc * m;                        // first cell of this thread's env
-    const int delay_m1 = np.delay - 1;
-    const double om_d = (double)np.order_max;
-    const double* __restrict__ tabrow = L.tabrow;
-    double* x_profit = reinterpret_cast<double*>(tile_base + KT(off_x));
-    int32_t* x_order = reinterpret_cast<int32_t*>(x_profit + cells);
-    int32_t* x_ship = x_order + cells;
-    int32_t* x_dem = x_ship + cells;
-    int32_t* x_inc = x_dem + cells;
-    int32_t* my_pipe = S.pipe + e_loc * KF(L) + np.pipe_off;
-    (void)lane; (void)O; (void)es;
-
-    // ---- phase A: read the cell, decode the order --------------------------------------------------------------------
-    double act = 0.0;
-    int inv = 0, backlog = 0, order_u = 0, carry = 0, cust = 0;
-    int pipe[DMAX], hd[PMAX], ho[PMAX];
-#pragma unroll
-    for (int k = 0; k < DMAX; ++k) pipe[k] = 0;
-#pragma unroll
-    for (int jj = 0; jj < PMAX; ++jj) { hd[jj] = 0; ho[jj] = 0; }
-    if (ok) {
-        act = S.act[cell];
-        inv = S.inv[cell];
-        backlog = S.bl[cell];
-        order_u = S.ou[cell];
-#pragma unroll
-        for (int k = 0; k < DMAX; ++k)
-            if (k < np.delay) pipe[k] = my_pipe[k];
-        if (KF(need_hd)) {
-#pragma unroll
-            for (int jj = 0; jj < PMAX; ++jj)
-                if (jj < KF(P)) hd[jj] = S.hd[cell * KF(P) + jj];
-        }
-        if (KF(need_ho)) {
-#pragma unroll
-            for (int jj = 0; jj < PMAX; ++jj)
-                if (jj < KF(P)) ho[jj] = S.ho[cell * KF(P) + jj];
-        }
-        if (np.retailer_idx >= 0) cust = S.dem[np.retailer_idx * E + e_loc];
-        if (KF(has_carry)) carry = S.carry[cell];
-    }
-    const int order = ok ? decode_order(act, om_d, KF(std_actions) != 0, KF(multi) != 0, A.a, A.bma, A.inv_bma, KBMA_POW2) : 0;
-    if (ok) x_order[cell] = order;
-    cells_bar(nthreads);
-
-    // ---- phase B: demand propagation, acquisition, shipment ----------------------------------------------------------
-    int demand = 0;
-    if (ok) {
-        if constexpr (DIV) {
-            if (np.retailer_idx >= 0) {
-                demand = min(cust, np.inv_max);
-            } else {
-#pragma unroll
-                for (int k = 0; k < MAXC; ++k)
-                    if (k < np.nchild) demand += x_order[e0 + L.child_lane[k]];
-            }
-        } else {
-            demand = (i == 0) ? min(cust, np.inv_max) : x_order[cell - 1];
-        }
-    }
-    int acq = carry;
-    int carry_new = 0;
-    if (t >= np.delay) {
-        acq += pipe[0];
-        if (delayed && t < KF(T) - 1) { carry_new = acq; acq = 0; }
-    }
-    const int ship = min(backlog + demand, inv + acq);
-    if (ok) {
-        x_ship[cell] = ship;
-        if (DIV && np.nchild > 1) x_dem[cell] = demand;
-    }
-    cells_bar(nthreads);
-
-    // ---- phase C: the divergent split, one (env, split node) task per thread — MAIM_div_env.py:476-579 ------------------
-    if constexpr (DIV) {
-        if (KF(nsplit) > 0) {
-            const int ns = KF(nsplit);
-            if (tid < E * ns) {
-                const int te = tid / ns, p = (int)A.split_nodes[tid % ns];
-                const NodeParams pn = load_node(A.nodes + p);
-                const int c0 = te * m;
-                int od[MAXC], bt[MAXC], st[MAXC];
-#pragma unroll
-                for (int k = 0; k < MAXC; ++k) {
-                    const int cl = child_lane_of(pn, k);
-                    od[k] = (k < pn.nchild) ? x_order[c0 + cl] : 0;
-                    bt[k] = (k < pn.nchild) ? S.bt[te * KF(NB) + pn.bt_off + k] : 0;
-                    st[k] = 0;
-                }
-                const int code = split_ship<MAXC>(pn.nchild, x_ship[c0 + p], x_dem[c0 + p], S.bl[c0 + p], pn.demand_max, KF(wd_mult1), KF(wd_mult), od, bt, st);
-#pragma unroll
-                for (int k = 0; k < MAXC; ++k) {
-                    if (k < pn.nchild) {
-                        x_inc[c0 + child_lane_of(pn, k)] = st[k];
-                        S.bt[te * KF(NB) + pn.bt_off + k] = bt[k];
-                    }
-                }
-                if (code != 0) A.err[n0 + te] = code;
-            }
-            cells_bar(nthreads);
-        }
-    }
-
-    // ---- phase D: state update, profit -----------------------------------------------------------------------------------
-    int incoming = order;                            // root / factory: its own production order
-    if (ok) {
-        if constexpr (DIV) {
-            if (np.parent >= 0) incoming = (np.parent_nchild > 1) ? x_inc[cell] : x_ship[e0 + np.parent];
-        } else {
-            if (!is_last) incoming = x_ship[cell + 1];
-        }
-    }
-    int backlog_new = backlog + demand - ship;
-    if (KF(cap_backlog)) backlog_new = min(backlog_new, np.demand_max);
-    const int order_u_new = min(max(order_u + order - acq, 0), np.inv_max);
-    const int inv_new = min(max(inv + acq - ship, 0), np.inv_max);
-#pragma unroll
-    for (int k = 0; k < DMAX; ++k) {
-        const int nxt = (k + 1 < DMAX) ? pipe[k + 1] : 0;
-        pipe[k] = (k == delay_m1) ? incoming : nxt;
-    }
-#pragma unroll
-    for (int jj = PMAX - 1; jj > 0; --jj) { hd[jj] = hd[jj - 1]; ho[jj] = ho[jj - 1]; }
-    hd[0] = demand;
-    ho[0] = order;
-    const double profit = ok ? profit_of(np.p, np.c, np.h, np.bc, np.target, ship, order, inv_new, backlog_new) : 0.0;
-    double reward_out = profit;
-    if (!(KF(multi) && KF(independent))) {
-        if (ok) x_profit[cell] = profit;
-        cells_bar(nthreads);
-        if (ok) {
-            const double* row = x_profit + e0;
-            if (KF(multi)) {                         // reward_sum starts at 0 and adds in stage order (MAIM_env.py:418-426), then / m
-                double sum = 0.0;
-                for (int q = 0; q < m; ++q) sum = __dadd_rn(sum, row[q]);
-                reward_out = div_by_m(sum, m, A.inv_m, KM_POW2);
-            } else {
-                reward_out = cells_np_sum(row, m);
-            }
-        }
-    }
-
-    // ---- write the tile back (in place) ----------------------------------------------------------------------------------
-    before_store();
-    if (ok) {
-        S.inv[cell] = inv_new;
-        S.bl[cell] = backlog_new;
-        S.ou[cell] = order_u_new;
-#pragma unroll
-        for (int k = 0; k < DMAX; ++k)
-            if (k < np.delay) my_pipe[k] = pipe[k];
-        if (KF(need_hd)) {
-#pragma unroll
-            for (int jj = 0; jj < PMAX; ++jj)
-                if (jj < KF(P)) S.hd[cell * KF(P) + jj] = hd[jj];
-        }
-        if (KF(need_ho)) {
-#pragma unroll
-            for (int jj = 0; jj < PMAX; ++jj)
-                if (jj < KF(P)) S.ho[cell * KF(P) + jj] = ho[jj];
-        }
-        if (KF(has_carry)) S.carry[cell] = carry_new;
-        if (KF(multi)) S.rew[cell] = reward_out;
-        else if (i == 0) S.rew[e_loc] = reward_out;
-#ifdef IMX_OBS_ROTATE
-        if (KHAS(obs)) {
-            unsigned long long w[OBS_ROW_BYTES / 8];
-            if (KF(obs_f32)) {
-                float rowf[IMX_K_O];
-                write_obs_row<DMAX, PMAX>(rowf, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
-#pragma unroll
-                for (int k = 0; k < OBS_ROW_BYTES / 8; ++k)
-                    w[k] = (unsigned long long)__float_as_uint(rowf[2 * k]) | ((unsigned long long)__float_as_uint(rowf[2 * k + 1]) << 32);
-            } else {
-                double rowd[IMX_K_O];
-                write_obs_row<DMAX, PMAX>(rowd, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
-#pragma unroll
-                for (int k = 0; k < OBS_ROW_BYTES / 8; ++k) w[k] = (unsigned long long)__double_as_longlong(rowd[k]);
-            }
-            store_row_rotated(S.obs + (size_t)cell * OBS_ROW_BYTES, w, lane);
-        }
-#else
-        if (KHAS(obs)) write_obs_row<DMAX, PMAX>(S.obs + (size_t)cell * O * es, A, np, i, tabrow, inv_new, backlog_new, order_u_new, pipe, hd, ho, DIV);
-#endif
-    }
-}
-#endif  // IMX_USE_CELLS
 
 // ONE period of ONE tile out of shared memory: read the lane's cell, the period's arithmetic (identical to step_kernel),
 // write the new state in place and the observation / reward tiles.  `before_store` runs between the arithmetic and the
@@ -683,12 +432,8 @@ __device__ __forceinline__ void cc_build_row(const StepArgs& A, const TileSmem& 
 template <int MAXC>
 __device__ __forceinline__ void cc_build(const StepArgs& A, const TileLayout& TLY, const TileSmem& S, unsigned char* tile_base, const LaneCtx<MAXC>& L,
                                          int nthreads) {
-#if IMX_USE_CELLS
-    cells_bar(nthreads);                             // an env's rows are written by threads of different warps
-#else
     (void)nthreads;
     __syncwarp();                                    // the env's m observation rows are complete
-#endif
     if (KF(obs_f32)) cc_build_row<float, MAXC>(A, S, tile_base + KT(off_cc), L);
     else cc_build_row<double, MAXC>(A, S, tile_base + KT(off_cc), L);
 }
@@ -955,8 +700,6 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
 #if IMX_USE_STEP_ET
     tile_period_et<IMX_K_m, DMAX, PMAX, MAXC, DIV>(A, TLY, S, tid, t, n0, before_store);
     (void)L; (void)delayed;
-#elif IMX_USE_CELLS
-    tile_period_cells<M_PAD, DMAX, PMAX, MAXC, DIV, MANY>(A, TLY, S, smem, L, tid, (int)blockDim.x, t, j, n0, delayed, before_store);
 #else
     tile_period<M_PAD, DMAX, PMAX, MAXC, DIV, MANY>(A, TLY, S, L, t, j, n0, delayed, before_store);
 #endif

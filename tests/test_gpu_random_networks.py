@@ -1,6 +1,6 @@
-"""Cell-mapped kernels (thread k = cell k of the [32][m] tile; IMX_CELLS): step, step_many, pipelined step and the fused rollout
-against the C oracle on every env, on the shipped divergent networks, random trees with up to 5 children per node, and (forced)
-serial chains whose length is not a power of two; plus cell-mapped == lane-mapped on Philox demand."""
+"""Specialised kernels on networks beyond the shipped presets: step, step_many, the pipelined step and the fused rollout against
+the C oracle on every env — random trees with up to 12 nodes and 5 children per node (lane mapping, more than 8 nodes: the lanes
+rollout), serial chains whose length is not a power of two, and lanes == env-per-thread rollouts on Philox demand."""
 import numpy as np
 import pytest
 import torch
@@ -30,9 +30,8 @@ CFGS = _cfgs()
 
 @pytest.mark.parametrize("case", range(len(CFGS)))
 @pytest.mark.parametrize("pipe", ["0", "1"])
-def test_cells_step_matches_c_oracle(case, pipe, monkeypatch):
+def test_step_on_random_networks_matches_c_oracle(case, pipe, monkeypatch):
     kind, cfg = CFGS[case]
-    monkeypatch.setenv("IMX_CELLS", "1")
     monkeypatch.setenv("IMX_PIPE", pipe)
     monkeypatch.setenv("IMX_PIPE_CTAS", "1")
     N = 2048 + 64 * case + (4 if case % 2 else 0)            # whole tiles (32 envs) plus, for odd cases, a tail for the direct kernel
@@ -62,12 +61,11 @@ def test_cells_step_matches_c_oracle(case, pipe, monkeypatch):
 
 
 @pytest.mark.parametrize("case", range(len(CFGS)))
-def test_cells_rollout_matches_c_oracle(case, monkeypatch):
+def test_rollout_on_random_networks_matches_c_oracle(case, monkeypatch):
     kind, cfg = CFGS[case]
     cfg = dict(cfg, time_dependency=False, prev_demand=False, prev_actions=False)
     if kind == "IM_div":
         cfg.update(standardise_state=False, standardise_actions=False)
-    monkeypatch.setenv("IMX_ROLLOUT_CELLS", "1")
     N = 2048 + 32 * case + (7 if case % 2 else 0)
     env = ENV_CLASSES[kind](dict(cfg, num_envs=N))
     m, T, R = env.num_nodes, env.num_periods, len(env._retailers)
@@ -90,8 +88,7 @@ def test_cells_rollout_matches_c_oracle(case, monkeypatch):
                                                     price=np.array([4, 3, 2, 1]), stock_cost=np.array([0.35, 0.3, 0.4]),
                                                     backlog_cost=np.array([0.5, 0.7, 0.6]), delay=np.array([1, 2, 3]))),
                                       ("IM", presets.serial8(prev_actions=True)), ("MAIM", presets.serial4(independent=True))])
-def test_cells_forced_on_serial_chains(kind, cfg, monkeypatch):
-    monkeypatch.setenv("IMX_CELLS", "1")
+def test_serial_chains_of_odd_length(kind, cfg, monkeypatch):
     N = 4096 + 32
     env = ENV_CLASSES[kind](dict(cfg, num_envs=N))
     m, T = env.num_nodes, env.num_periods
@@ -111,12 +108,12 @@ def test_cells_forced_on_serial_chains(kind, cfg, monkeypatch):
     np.testing.assert_array_equal(env.state_dict()["pipe"].cpu().numpy(), want["pipe"])
 
 
-def test_cells_and_lanes_rollouts_agree_on_philox_demand(monkeypatch):
+def test_et_and_lanes_rollouts_agree_on_philox_demand(monkeypatch):
     cfg = presets.div2(time_dependency=False, prev_demand=False)
     cfg.update(demand_dist="poisson", mu=5)
     outs = []
-    for cells in ("0", "1"):
-        monkeypatch.setenv("IMX_ROLLOUT_CELLS", cells)
+    for et in ("0", "1"):
+        monkeypatch.setenv("IMX_ROLLOUT_ET", et)
         env = ENV_CLASSES["MAIM_div"](dict(cfg, num_envs=5000, seed=7))
         env._episode = 41
         outs.append(env.rollout_basestock(np.full(6, 0.2))["returns"].clone())
