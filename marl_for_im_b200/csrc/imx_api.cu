@@ -266,7 +266,10 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
     add("std_actions", always_std ? 1 : (c.standardise_actions != 0)); add("cap_backlog", always_std ? 1 : std_state);
     add("independent", c.independent != 0); add("share_network", (c.kind == IMX_KIND_MAIM_DIV && c.share_network) ? 1 : 0);
     add("td", c.time_dependency != 0); add("pd", c.prev_demand != 0); add("pa", c.prev_actions != 0);
-    add("write_hd", e->write_hd); add("noisy", 0); add("has_carry", e->has_carry); add("need_hd", e->need_hd);
+    add("write_hd", e->write_hd); add("has_carry", e->has_carry); add("need_hd", e->need_hd);
+    // noisy delays: a handle without the carry state never has them (literal 0); one with it decides per episode (reset(noisy=...)),
+    // so the specialised kernels of such a handle read the flag from the argument block
+    defs.push_back(e->has_carry ? "IMX_K_noisy=(A.noisy)" : "IMX_K_noisy=0");
     add("need_ho", e->need_ho); add("wd_mult1", e->multi ? 2 : 4); add("wd_mult", e->multi ? 1 : 2); add("TL", TL);
     add("noisy_demand", (e->div && c.noisy_demand_threshold > 0.0) ? 1 : 0); add("has_info", 0); add("has_obs", has_obs); add("has_tab", TL > 0); add("obs_f32", c.obs_f32 != 0);
     int ex = 0;
@@ -1004,7 +1007,7 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
     const imxjit::Kernels* jk = nullptr;
     bool with_cc = false;
     if (cc_fused) *cc_fused = false;
-    if (cc && tma_legal && !A.has_info && !A.noisy && obs_dev && aligned16(cc->dev)) {
+    if (cc && tma_legal && !A.has_info && obs_dev && aligned16(cc->dev)) {
         if (e->jit_cc_state == 0 && !stream_is_capturing(s)) ensure_jit_cc(e);
         const int64_t whole = (e->N / e->tile_cc.E) * e->tile_cc.E;
         if (e->jit_cc_state == 1 && whole == e->N) {       // fused only when every env sits in a whole tile (else: unfused fallback)
@@ -1015,7 +1018,7 @@ static int launch_step(imx_env* e, const double* actions_dev, double* obs_dev, d
             if (cc_fused) *cc_fused = true;
         }
     }
-    if (!with_cc && tma_legal && !A.has_info && !A.noisy) {
+    if (!with_cc && tma_legal && !A.has_info) {
         // the specialised kernels were loaded by imx_create() / imx_prepare(); the obs-less variant may still be
         // compiled here on first use, but never while the stream is being captured (module loads are not capturable)
         if (obs_dev) { if (e->jit_state == 1) jk = e->jit; }

@@ -144,7 +144,9 @@ __global__ void IMX_PIPE_BOUNDS step_kernel_pipe(const __grid_constant__ StepArg
 #if IMX_USE_STEP_ET
         tile_period_et<IMX_K_m, DMAX, PMAX, MAXC, DIV>(A, TLY, T, tid, A.t, n0, []() {});
 #else
-        tile_period<M_PAD, DMAX, PMAX, MAXC, DIV, false>(A, TLY, T, L, A.t, 0, n0, false, []() {});
+        // replayed / Philox noisy-delay outcome of this lane's (env, stage) for this period (written by reset(), long complete)
+        const bool delayed = (KF(noisy) && L.ok) ? (A.mask_T[((int64_t)A.t * A.N + n0 + L.e_loc) * m + L.i] != 0) : false;
+        tile_period<M_PAD, DMAX, PMAX, MAXC, DIV, false>(A, TLY, T, L, A.t, 0, n0, delayed, []() {});
 #endif
         if (KHAS(cc)) cc_build<MAXC>(A, TLY, T, st, L, CT);
         fence_proxy_async_smem();                    // this thread's tile writes, before the bulk engine reads them

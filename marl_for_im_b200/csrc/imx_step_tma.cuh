@@ -492,8 +492,13 @@ __device__ __forceinline__ void tile_period_et(const StepArgs& A, const TileLayo
             demand[j] = order[j > 0 ? j - 1 : 0];
         }
         int a = cr[j];
-        if (t >= DELAY[j]) a += pipe[j][0];
-        cr[j] = 0;                                   // (replayed noisy delays are served by the ahead-of-time kernels)
+        cr[j] = 0;
+        if (t >= DELAY[j]) {
+            a += pipe[j][0];
+            if (KF(noisy)) {                         // noisy delay (MAIM_env.py:449-457): hold this period's arrival back by one period
+                if (t < KF(T) - 1 && A.mask_T[((int64_t)t * A.N + n0 + e) * M + j] != 0) { cr[j] = a; a = 0; }
+            }
+        }
         acq[j] = a;
         ship[j] = min(bl[j] + demand[j], inv[j] + a);
     }

@@ -125,3 +125,39 @@ def test_pipe_and_plain_kernels_agree_under_graph_replay(monkeypatch):
         outs[mode] = (obs.clone(), rew.clone(), env.state_dict()["pipe"].clone())
     for a, b in zip(outs["0"], outs["1"]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("pipe", ["0", "1"])
+@pytest.mark.parametrize("kind,preset,N", [("MAIM", "serial4", 4096), ("IM", "serial8", 3072 + 32), ("MAIM_div", "div2", 4096 + 64), ("IM_div", "div1", 2048)])
+def test_noisy_delays_through_the_specialised_kernels(kind, preset, N, pipe, monkeypatch):
+    """Episodes with noisy delays (replayed masks) are served by the runtime-specialised kernels too — one tile per CTA, pipelined,
+    env-per-thread (div2) and multi-period — and match the C oracle on every env; an episode without noise on the same handle
+    (the flag is per episode) still matches."""
+    monkeypatch.setenv("IMX_PIPE", pipe)
+    monkeypatch.setenv("IMX_PIPE_CTAS", "2")
+    cfg = presets.PRESETS[preset]()
+    rng = np.random.default_rng(N)
+    env = ENV_CLASSES[kind](dict(cfg, num_envs=N))
+    m, T, R = env.num_nodes, env.num_periods, len(env._retailers)
+    co = c_oracle.COracle(kind, cfg)
+    for noisy in (True, False, True):
+        demand = rng.poisson(5, size=(N, R, T)).astype(np.int32)
+        actions = np.clip(rng.normal(-0.3, 0.6, size=(T, N, m)), -1.2, 1.2)
+        mask = (rng.uniform(size=(N, T, m)) <= 0.3) if noisy else None
+        env.reset(customer_demand=demand, delay_mask=mask)
+        a_dev = torch.as_tensor(actions, device="cuda:0")
+        rews, variants = [], set()
+        half = T // 2
+        for t in range(half):
+            o, r, done, _ = env.step(a_dev[t])
+            variants.add(env._lib.imx_kernel_variant(env._handle))
+            rews.append(torch.stack([r[n] for n in env.agent_names], dim=1) if env.MULTI else r[:, None])
+        obs_many, rew_many, done = env.step_many(a_dev[half:])
+        assert variants == {3 if pipe == "1" else 2}, variants
+        want = co.run(demand, actions, mask)
+        got = torch.cat([torch.stack(rews), rew_many.reshape(T - half, N, -1)]).cpu().numpy()
+        np.testing.assert_array_equal(got, want["reward"])
+        np.testing.assert_array_equal(obs_many[-1].cpu().numpy(), want["obs_last"])
+        st = {k: v.cpu().numpy() for k, v in env.state_dict().items()}
+        for k in ("inv", "backlog", "order_u", "pipe"):
+            np.testing.assert_array_equal(st[k], want[k], err_msg=k)
