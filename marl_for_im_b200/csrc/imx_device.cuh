@@ -175,9 +175,13 @@ __device__ __forceinline__ int decode_order(double x, double om, bool std_action
     }
     // round-half-to-even then clip (MAIM) and clip then round (IM) give the same integer for an integral order_max
     // (rounding is monotone and fixes 0 and order_max), so one saturating convert + an integer clamp replaces the float64
-    // rint / fmin / fmax sequence (19 instructions per lane in the rollout loop); NaN converts to 0 like fmax(NaN, 0) did
-    (void)multi;
-    return min(max(__double2int_rn(x), 0), (int)om);
+    // rint / fmin / fmax sequence (19 instructions per lane in the rollout loop); NaN converts to 0.
+    // Non-finite / huge actions: the MAIM kinds round and convert BEFORE clipping (MAIM_env.py:344-347), and on the reference's
+    // x86-64 the float64 -> int64 conversion of anything >= 2^63 (and of NaN, +-inf) yields INT64_MIN, which then clips to 0 —
+    // so an order >= 2^63 (high word >= 0x43E00000: also +inf and positive NaN) is 0 there, not order_max.  The IM kinds clip
+    // first (IM_env.py:300-302), so +inf saturates to order_max like any large value.
+    const int v = min(max(__double2int_rn(x), 0), (int)om);
+    return (multi && __double2hiint(x) >= 0x43E00000) ? 0 : v;
 }
 // Rescaled observation value.  The integer domain of every scaled field is bounded (inventory and
 // unfulfilled orders by inv_max, capped backlog and demand by demand_max, pipeline entries by

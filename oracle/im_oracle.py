@@ -312,9 +312,18 @@ class OracleEnv:
             if self.std_actions:
                 x = rev_scale(x, om, self.a, self.b)
             if self.multi:
-                x = min(max(_rint(x), 0.0), om)          # round, then clip
+                # round, .astype(int), then clip (MAIM_env.py:344-347).  The reference runs on x86-64, where the float64 ->
+                # int64 conversion of NaN, +-inf and anything outside [-2^63, 2^63) yields INT64_MIN, which then clips to 0
+                x = _rint(x)
+                if not (-9.223372036854775808e18 <= x < 9.223372036854775808e18):
+                    x = -9.223372036854775808e18
+                x = min(max(x, 0.0), om)
             else:
-                x = _rint(min(max(x, 0.0), om))          # clip, then round
+                # clip, then round, then .astype(int) (IM_env.py:300-302): +-inf clip like any value; a NaN survives the clip
+                # and becomes an order of INT64_MIN that corrupts the reference's float state — outside the parity domain
+                if x != x:
+                    raise ValueError("NaN action on a single-agent env: the reference's state becomes INT64_MIN garbage (IM_env.py:300)")
+                x = _rint(min(max(x, 0.0), om))
             out.append(int(x))
         return out
 

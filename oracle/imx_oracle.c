@@ -131,7 +131,13 @@ static void observe(const orc_cfg* c, const orc_state* s, int t, double* obs /* 
 static int decode_order(const orc_cfg* c, int i, double x) {
     const double om = c->order_max[i];
     if (c->std_actions) x = rev_scale(x, om, c->a, c->b);
-    if (c->multi) { x = rint(x); x = x < 0.0 ? 0.0 : x; x = x > om ? om : x; }
+    if (c->multi) {
+        /* round, .astype(int), clip (MAIM_env.py:344-347): on the reference's x86-64 the float64 -> int64 conversion of NaN,
+         * +-inf and anything outside [-2^63, 2^63) yields INT64_MIN, which the clip turns into 0 */
+        x = rint(x);
+        if (!(x >= -9223372036854775808.0 && x < 9223372036854775808.0)) x = -9223372036854775808.0;
+        x = x < 0.0 ? 0.0 : x; x = x > om ? om : x;
+    }
     else { x = x < 0.0 ? 0.0 : x; x = x > om ? om : x; x = rint(x); }
     return (int)x;
 }

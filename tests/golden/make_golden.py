@@ -36,8 +36,22 @@ def cfg_to_json(cfg):
 CASES = []
 
 
-def add(name, kind, preset, mu=5, amode="uniform", noisy=False, hetero=False, **kw):
-    CASES.append(dict(name=name, kind=kind, preset=preset, mu=mu, amode=amode, noisy=noisy, hetero=hetero, kw=kw))
+def add(name, kind, preset, mu=5, amode="uniform", noisy=False, hetero=False, nonfinite=False, **kw):
+    CASES.append(dict(name=name, kind=kind, preset=preset, mu=mu, amode=amode, noisy=noisy, hetero=hetero, nonfinite=nonfinite, kw=kw))
+
+
+def inject_nonfinite(actions, kind, rng):
+    """Overwrites ~15 % of the action trace with +-inf, huge finite values either side of 2^63 and (MAIM kinds only) NaN.
+    The MAIM kinds round and .astype(int) before clipping (MAIM_env.py:344-347): on x86-64 everything outside [-2^63, 2^63)
+    and NaN converts to INT64_MIN and clips to order 0.  The IM kinds clip first (IM_env.py:300-302); a NaN there turns the
+    reference's state into INT64_MIN garbage, so it is left out."""
+    specials = [np.inf, -np.inf, 1e19, -1e19, 3e9, -3e9, 1e300, 9.3e18, 9.2e18, 2.0 ** 63, np.nextafter(2.0 ** 63, 0), 6.2e17, 1e18]
+    if kind.startswith("MAIM"):
+        specials += [np.nan, -np.nan]
+    a = np.array(actions, dtype=np.float64, copy=True)
+    hit = rng.uniform(size=a.shape) < 0.15
+    a[hit] = rng.choice(np.array(specials), size=int(hit.sum()))
+    return a
 
 
 # config 2 of BASELINE.json (MA_6 mode) and its siblings
@@ -65,6 +79,12 @@ add("maimdiv2_noisy", "MAIM_div", "div2", noisy=True, amode="near_eq")
 add("imdiv1_ttt", "IM_div", "div1", prev_actions=True)
 add("imdiv2_fff", "IM_div", "div2", time_dependency=False, prev_demand=False, amode="near_eq")
 add("imdiv2_tft_hetero", "IM_div", "div2", prev_demand=False, prev_actions=True, hetero=True, mu=9)
+# non-finite and out-of-range actions (appended last: the generator stream of the cases above is unchanged)
+add("maim4_nonfinite", "MAIM", "serial4", nonfinite=True)
+add("maim4_nonfinite_raw", "MAIM", "serial4", nonfinite=True, standardise_actions=False, prev_actions=True)
+add("maimdiv2_nonfinite", "MAIM_div", "div2", nonfinite=True, amode="near_eq")
+add("im4_nonfinite", "IM", "serial4", nonfinite=True, prev_actions=True)
+add("imdiv1_nonfinite", "IM_div", "div1", nonfinite=True)
 
 
 def main():
@@ -76,6 +96,8 @@ def main():
             cfg["inv_max"] = np.array([30, 25, 40, 35, 30, 45, 20, 30][:m], dtype=float)
             cfg["inv_target"] = np.array([0, 3, 5.5, 1, 0, 2, 4, 0][:m], dtype=float)
         demand, actions = random_case(c["kind"], cfg, rng, mu=c["mu"], action_mode=c["amode"])
+        if c["nonfinite"]:
+            actions = inject_nonfinite(actions, c["kind"], rng)
         mask = make_delay_mask(c["kind"], cfg["delay"], cfg["num_periods"], 0.3, rng) if c["noisy"] else None
         out = run_reference(c["kind"], cfg, demand, actions, mask)
         np.savez_compressed(
