@@ -104,7 +104,6 @@ struct imx_env {
     uint16_t* d_guide = nullptr;         // cutpoint table of the Poisson inversion
     int cdf_len = 0;
     double* d_stats_partial = nullptr;   // [max(2 + 2m, 2(4 + m))][STATS_BLOCKS] scratch of imx_return_stats / imx_eval_stats
-    double* d_returns = nullptr;         // [N][cols] scratch of imx_episode_stats
     double* d_dfo_rewards = nullptr;     // [T][N] scratch of the dfo objective (allocated on first use / imx_prepare)
     double* d_tab = nullptr;             // [m][4][TL] rescale tables
     int TL = 0;
@@ -615,7 +614,7 @@ static int derive(imx_env* e) {
     return 0;
 }
 
-static void launch_reset_kernel(imx_env* e, double* obs_dev, cudaStream_t s);
+static void launch_reset_kernel(imx_env* e, double* obs_dev, cudaStream_t s, const int32_t* demand_in = nullptr);
 
 static void fill_args(const imx_env* e, StepArgs& A) {
     const imx_config& c = e->cfg;
@@ -814,8 +813,12 @@ extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
             IMX_CREATE_CUDA(cudaMemcpy(e->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
         }
     }
-    IMX_CREATE_CUDA(cudaMalloc(&e->d_stats_partial, (size_t)(2 * EVAL_FIXED + 2 + 2 * IMX_MAX_NODES) * STATS_BLOCKS * sizeof(double)));
-    IMX_CREATE_CUDA(cudaMalloc(&e->d_returns, (size_t)N * m * sizeof(double)));
+    {   // partial sums of the two-stage statistics: [statistic][slice] (imx_stats.cuh) or [2 x column][STATS_BLOCKS] (imx_eval.cuh)
+        const int cols = e->multi ? m : 1;
+        const int64_t nslices = (N + stats_envs_per_block(cols) - 1) / stats_envs_per_block(cols);
+        const size_t a = (size_t)(2 + 2 * cols) * (size_t)nslices, b = (size_t)(2 * EVAL_FIXED + 2 + 2 * IMX_MAX_NODES) * STATS_BLOCKS;
+        IMX_CREATE_CUDA(cudaMalloc(&e->d_stats_partial, (a > b ? a : b) * sizeof(double)));
+    }
     // reset state with an all-zero demand trace (the reference constructors end with self.reset())
     IMX_CREATE_CUDA(cudaMemset(e->d_demand_T, 0, dem_bytes));
     {
@@ -836,7 +839,7 @@ extern "C" int imx_destroy(imx_env* e) {
     cudaSetDevice(e->cfg.device);
     if (e->hstream) { cudaStreamSynchronize(e->hstream); cudaStreamDestroy(e->hstream); }
     cudaFree(e->d_nodes); cudaFree(e->d_state); cudaFree(e->d_err);
-    cudaFree(e->d_demand_T); cudaFree(e->d_mask_T); cudaFree(e->d_cdf); cudaFree(e->d_guide); cudaFree(e->d_tab); cudaFree(e->d_stats_partial); cudaFree(e->d_returns);
+    cudaFree(e->d_demand_T); cudaFree(e->d_mask_T); cudaFree(e->d_cdf); cudaFree(e->d_guide); cudaFree(e->d_tab); cudaFree(e->d_stats_partial);
     cudaFree(e->d_dfo_rewards); cudaFree(e->d_obs_scratch);
     cudaFree(e->d_act_h); cudaFree(e->d_obs_h); cudaFree(e->d_rew_h); cudaFree(e->d_dem_h); cudaFree(e->d_mask_h);
     delete e;
@@ -885,7 +888,7 @@ extern "C" int imx_set_period(imx_env* e, int t) {
 // reset / step
 // --------------------------------------------------------------------------------------
 // launches the reset fill kernel (state zero + inv init + optional t = 0 observation)
-static void launch_reset_kernel(imx_env* e, double* obs_dev, cudaStream_t s) {
+static void launch_reset_kernel(imx_env* e, double* obs_dev, cudaStream_t s, const int32_t* demand_in) {
     StepArgs A;
     fill_args(e, A);
     A.obs = obs_dev;
@@ -893,6 +896,9 @@ static void launch_reset_kernel(imx_env* e, double* obs_dev, cudaStream_t s) {
     Z.zero_base = e->d_state;
     Z.zero_words = (int64_t)(e->state_bytes / sizeof(int32_t));
     Z.err = e->d_err;
+    Z.demand_in = demand_in;                               // replayed trace [N][R][T]: transposed to [T][R][N] by the same launch
+    Z.demand_T = e->d_demand_T;
+    Z.R = e->R; Z.T = e->T;
     const int64_t work = (obs_dev ? e->N * e->m * e->O : 0) > Z.zero_words / 4 ? e->N * e->m * e->O : Z.zero_words / 4;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device);
@@ -900,7 +906,16 @@ static void launch_reset_kernel(imx_env* e, double* obs_dev, cudaStream_t s) {
     if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
     if (blocks < 1) blocks = 1;
     const size_t smem = (size_t)e->m * e->O * sizeof(double) + (size_t)e->m * sizeof(int32_t);   // template sized for float64
-    e->reset_fn<<<(unsigned)blocks, 256, smem, s>>>(A, Z, e->div ? 1 : 0);
+    // a programmatic dependent of whatever is in front of it on the stream (the kernel starts with griddepcontrol.wait)
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)blocks); lc.blockDim = dim3(256); lc.dynamicSmemBytes = smem; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = e->use_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&lc, e->reset_fn, A, Z, e->div ? 1 : 0);
 }
 
 static DemandGen make_gen(const imx_env* e, uint64_t episode) {
@@ -923,10 +938,7 @@ extern "C" int imx_reset(imx_env* e, const int32_t* demand_dev, const uint8_t* d
         return fail(-1, "reset() without a demand trace needs demand_dist poisson or uniform");
     const int64_t N = e->N;
     const unsigned gb = (unsigned)((N * e->R + 255) / 256);
-    if (demand_dev) {
-        demand_transpose_kernel<<<gb, 256, 0, s>>>(demand_dev, e->d_demand_T, N, e->R, e->T);
-        IMX_CHECK_LAUNCH("demand_transpose_kernel");
-    } else {
+    if (!demand_dev) {                                       // (a replayed trace is transposed by the reset kernel itself)
         demand_generate_kernel<<<gb, 256, 0, s>>>(e->d_demand_T, N, e->R, e->T, make_gen(e, episode));
         IMX_CHECK_LAUNCH("demand_generate_kernel");
     }
@@ -945,7 +957,7 @@ extern "C" int imx_reset(imx_env* e, const int32_t* demand_dev, const uint8_t* d
     }
     e->t = 0;
     e->episode = episode;
-    launch_reset_kernel(e, (double*)obs_dev, s);
+    launch_reset_kernel(e, (double*)obs_dev, s, demand_dev);
     IMX_CHECK_LAUNCH("reset_kernel");
     return 0;
 }
@@ -1271,16 +1283,47 @@ extern "C" int imx_rollout_basestock(imx_env* e, const double* z_dev, int z_stri
     return 0;
 }
 
+// launches `kern` as a programmatic dependent of the kernel in front of it on the stream (the kernel itself starts with
+// griddepcontrol.wait): its launch latency overlaps the predecessor's tail
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_dependent(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, bool pdl, Args... args) {
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = 0; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&lc, kern, KArgs(args)...);
+}
+
+// stage 1 (one block per slice of envs; FUSED adds the step rewards first) + stage 2 of the return statistics
+static int launch_return_stats(imx_env* e, const double* src, int periods, bool fused, double* ret_out, double* stats_dev, int accumulate,
+                               cudaStream_t s) {
+    const int cols = e->multi ? e->m : 1;
+    const int per_agent = e->multi ? 1 : 0;
+    const int nstat = per_agent ? 2 + 2 * cols : 2;
+    const int epb = stats_envs_per_block(cols);
+    const int nslices = (int)((e->N + epb - 1) / epb);
+    const bool pdl = e->use_pdl != 0;
+    if (fused)
+        IMX_CUDA(launch_dependent(stats_slice_kernel<true>, dim3((unsigned)nslices), dim3(STATS_THREADS), s, pdl, src, ret_out, e->d_stats_partial,
+                                  e->N, cols, per_agent, periods, epb, nslices));
+    else
+        IMX_CUDA(launch_dependent(stats_slice_kernel<false>, dim3((unsigned)nslices), dim3(STATS_THREADS), s, pdl, src, (double*)nullptr,
+                                  e->d_stats_partial, e->N, cols, per_agent, 1, epb, nslices));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    IMX_CUDA(launch_dependent(stats_final_kernel, dim3((unsigned)nstat), dim3(STATS_THREADS), s, pdl, (const double*)e->d_stats_partial, stats_dev,
+                              e->N, nslices, accumulate));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
 extern "C" int imx_return_stats(imx_env* e, const double* return_dev, double* stats_dev, void* stream) {
     if (!e || !return_dev || !stats_dev) return fail(-1, "null argument");
     IMX_CUDA(cudaSetDevice(e->cfg.device));
-    const int cols = e->multi ? e->m : 1;
-    const int nstat = e->multi ? 2 + 2 * cols : 2;
-    return_stats_partial_kernel<<<dim3(STATS_BLOCKS, nstat), STATS_THREADS, 0, (cudaStream_t)stream>>>(return_dev, e->d_stats_partial, e->N, cols);
-    IMX_CHECK_LAUNCH("return_stats_partial_kernel");
-    return_stats_final_kernel<<<nstat, 32, 0, (cudaStream_t)stream>>>(e->d_stats_partial, stats_dev, e->N, nstat, 0);
-    IMX_CHECK_LAUNCH("return_stats_final_kernel");
-    return 0;
+    return launch_return_stats(e, return_dev, 1, false, nullptr, stats_dev, 0, (cudaStream_t)stream);
 }
 
 extern "C" int imx_episode_stats(imx_env* e, const double* step_reward_dev, int periods, double* return_dev, double* stats_dev,
@@ -1290,18 +1333,8 @@ extern "C" int imx_episode_stats(imx_env* e, const double* step_reward_dev, int 
     if (!e || !step_reward_dev || !stats_dev) return fail(-1, "null argument");
     if (periods < 1) return fail(-1, "periods must be >= 1");
     IMX_CUDA(cudaSetDevice(e->cfg.device));
-    const int cols = e->multi ? e->m : 1;
-    const int nstat = e->multi ? 2 + 2 * cols : 2;
-    const int64_t cells = e->N * cols;
-    double* ret = return_dev ? return_dev : e->d_returns;
-    cudaStream_t s = (cudaStream_t)stream;
-    episode_return_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(step_reward_dev, ret, cells, periods);
-    IMX_CHECK_LAUNCH("episode_return_kernel");
-    return_stats_partial_kernel<<<dim3(STATS_BLOCKS, nstat), STATS_THREADS, 0, s>>>(ret, e->d_stats_partial, e->N, cols);
-    IMX_CHECK_LAUNCH("return_stats_partial_kernel");
-    return_stats_final_kernel<<<nstat, 32, 0, s>>>(e->d_stats_partial, stats_dev, e->N, nstat, accumulate);
-    IMX_CHECK_LAUNCH("return_stats_final_kernel");
-    return 0;
+    // the episode returns are only written when the caller asks for them (the statistics are built from shared memory)
+    return launch_return_stats(e, step_reward_dev, periods, true, return_dev, stats_dev, accumulate, (cudaStream_t)stream);
 }
 
 // --------------------------------------------------------------------------------------
@@ -1331,8 +1364,8 @@ extern "C" int imx_eval_stats(imx_env* e, const double* acc_dev, double* stats_d
     const int W = EVAL_FIXED + e->m;
     column_stats_partial_kernel<<<dim3(STATS_BLOCKS, 2 * W), STATS_THREADS, 0, (cudaStream_t)stream>>>(acc_dev, e->d_stats_partial, e->N, W);
     IMX_CHECK_LAUNCH("column_stats_partial_kernel");
-    return_stats_final_kernel<<<2 * W, 32, 0, (cudaStream_t)stream>>>(e->d_stats_partial, stats_dev, e->N, 2 * W, accumulate);
-    IMX_CHECK_LAUNCH("return_stats_final_kernel");
+    stats_final_kernel<<<2 * W, STATS_THREADS, 0, (cudaStream_t)stream>>>(e->d_stats_partial, stats_dev, e->N, STATS_BLOCKS, accumulate);
+    IMX_CHECK_LAUNCH("stats_final_kernel");
     return 0;
 }
 

@@ -17,7 +17,11 @@ struct ResetArgs {
     int32_t* zero_base;        // the state block (all fields back to back) ...
     int64_t zero_words;        // ... and its length in int32 words
     int32_t* err;              // [N] watchdog flags, cleared
+    const int32_t* demand_in;  // replayed demand trace [N][R][T] of the new episode, or NULL (drawn by demand_generate_kernel)
+    int32_t* demand_T;         // [T][R][N]: the trace period-major
+    int32_t R, T;
 };
+constexpr int RESET_T_CHUNK = 8;   // periods one thread transposes
 
 template <int DMAX, int PMAX>
 __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ ResetArgs Z, int div) {
@@ -25,6 +29,9 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
     const int m = A.m, O = A.O;
     const int es = A.obs_f32 ? 4 : 8;
     int32_t* s_init = reinterpret_cast<int32_t*>(s_tmpl + m * O);
+    // everything this kernel writes may still be read by the kernel in front of it (it is launched as a programmatic dependent)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if ((int)threadIdx.x < m) {
         const int i = threadIdx.x;
         const NodeParams np = load_node(A.nodes + i);
@@ -80,6 +87,28 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
             }
         }
     }
+    if (Z.demand_in) {
+        // demand [N][R][T] -> [T][R][N]: one thread per (chunk of RESET_T_CHUNK periods, retailer row, env), env fastest, so the
+        // stores of a warp are 32 consecutive words per period and the loads of a thread are one short run of its env's row
+        const int R = Z.R, T = Z.T;
+        const int chunks = (T + RESET_T_CHUNK - 1) / RESET_T_CHUNK;
+        const int64_t rows = A.N * R;
+        const int64_t items = rows * chunks;
+        for (int64_t k = gtid; k < items; k += stride) {
+            const int ch = (int)(k / rows);
+            const int64_t idx = k - (int64_t)ch * rows;
+            const int r = (int)(idx / A.N);
+            const int64_t n = idx - (int64_t)r * A.N;
+            const int32_t* src = Z.demand_in + (n * R + r) * T;
+            const int t0 = ch * RESET_T_CHUNK;
+            int v[RESET_T_CHUNK];
+#pragma unroll
+            for (int u = 0; u < RESET_T_CHUNK; ++u) v[u] = (t0 + u < T) ? src[t0 + u] : 0;
+#pragma unroll
+            for (int u = 0; u < RESET_T_CHUNK; ++u)
+                if (t0 + u < T) Z.demand_T[((int64_t)(t0 + u) * R + r) * A.N + n] = v[u];
+        }
+    }
     // inv lives inside the zeroed block: a grid-wide ordering is needed between the zero fill and the
     // init fill of the same words, so the init fill is done by the thread that zeroed the word:
     // inv is the FIRST field of the block (offset 0), words [0, N*m)
@@ -93,18 +122,6 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
             if (++rem == m) rem = 0;
         }
     }
-}
-
-// Initial observation only (used when obs is requested separately from the state reset).
-// demand [N][R][T] -> [T][R][N]; one thread per (retailer row, env), env fastest.
-__global__ void __launch_bounds__(256) demand_transpose_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
-                                                               int64_t N, int R, int T) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= N * R) return;
-    const int r = (int)(idx / N);
-    const int64_t n = idx % N;
-    const int32_t* src = in + (n * R + r) * T;
-    for (int t = 0; t < T; ++t) out[((int64_t)t * R + r) * N + n] = src[t];
 }
 
 // Philox demand: customer_demand ~ Poisson(mu) / randint(low, high) per (env, retailer, period)

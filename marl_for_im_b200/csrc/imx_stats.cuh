@@ -79,69 +79,109 @@ __global__ void __launch_bounds__(128) dfo_objective_kernel(const double* __rest
 }
 
 // Episode statistics [n, Σ total, Σ total², then per agent (Σ, Σ²)] in a fixed, deterministic
-// order (the payload of the single cross-GPU all-reduce).  Two stages: STATS_BLOCKS x nstat blocks
-// each reduce one statistic over a fixed slice of the envs (strided threads + shared-memory tree),
-// then one block per statistic adds the STATS_BLOCKS partials in index order.  The grid is a
-// constant, so the result depends only on N, never on the device.  The per-env total of a MAIM kind
-// is the sum over agents in agent order.
-constexpr int STATS_BLOCKS = 128;
+// order (the payload of the single cross-GPU all-reduce).  Two stages, both of a shape that depends only on N and m:
+//   1. stats_slice_kernel: one block per slice of `epb` consecutive envs (stats_envs_per_block: as many whole envs as fit in
+//      256 cells, at least 32), one thread per cell.  FUSED: the thread first adds the step rewards of its cell in period
+//      order ("reward += r", inv_management.py:223-231; one coalesced row of step_reward [T][cells] per period), writes the
+//      episode return and leaves it in shared memory — no second pass over the returns; otherwise it loads the return.
+//      Thread e < epb then owns env e of the slice: per-env total = sum over agents in agent order, and every statistic is
+//      reduced over the block (warp shuffles, then the warps in order).
+//   2. stats_final_kernel: one block per statistic adds the slices' partials (strided threads + a fixed tree).
+// Both are programmatic dependent launches (griddepcontrol.wait), so their launch latency hides behind the kernel in front.
 constexpr int STATS_THREADS = 256;
+constexpr int STATS_BLOCKS = 128;                              // slices of the column statistics (imx_eval.cuh)
+constexpr int STATS_MAX_STAT = 2 + 2 * IMX_MAX_NODES;
 
-__device__ __forceinline__ double stats_value(const double* __restrict__ ret, int64_t n, int cols, int q) {
-    double v;
-    if (q < 2) {
-        v = 0.0;
-        for (int c = 0; c < cols; ++c) v += ret[n * cols + c];
-    } else {
-        v = ret[n * cols + (q - 2) / 2];
-    }
-    return (q & 1) ? v * v : v;
+static inline int stats_envs_per_block(int cols) { const int e = STATS_THREADS / cols; return e < 32 ? 32 : e; }
+
+__device__ __forceinline__ double warp_sum_fixed(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, off));   // (explicit roundings: never contracted)
+    return v;
 }
 
-__global__ void __launch_bounds__(STATS_THREADS) return_stats_partial_kernel(const double* __restrict__ ret, double* __restrict__ partial,
-                                                                             int64_t N, int cols) {
+template <bool FUSED>
+__global__ void __launch_bounds__(STATS_THREADS) stats_slice_kernel(const double* __restrict__ src, double* __restrict__ ret_out,
+                                                                    double* __restrict__ partial, int64_t N, int cols, int per_agent, int T,
+                                                                    int epb, int nslices) {
+    __shared__ double s_ret[32 * IMX_MAX_NODES > STATS_THREADS ? 32 * IMX_MAX_NODES : STATS_THREADS];   // [epb][cols] returns of the slice
+    __shared__ double s_part[STATS_MAX_STAT * (STATS_THREADS / 32)];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t env0 = (int64_t)blockIdx.x * epb;
+    const int64_t cells = N * cols;
+    const int64_t cell0 = env0 * cols;
+    const int my_cells = epb * cols;
+    asm volatile("griddepcontrol.wait;" ::: "memory");         // (returns at once unless launched as a programmatic dependent)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the final kernel may take its seat; it waits for this grid to complete
+    for (int j = tid; j < my_cells; j += STATS_THREADS) {
+        const int64_t c = cell0 + j;
+        double acc = 0.0;
+        if (c < cells) {
+            if (FUSED) {
+                int t = 0;
+                for (; t + 10 <= T; t += 10) {                 // ten independent loads in flight, added in period order
+                    double r[10];
+#pragma unroll
+                    for (int u = 0; u < 10; ++u) r[u] = src[(int64_t)(t + u) * cells + c];
+#pragma unroll
+                    for (int u = 0; u < 10; ++u) acc += r[u];
+                }
+                for (; t < T; ++t) acc += src[(int64_t)t * cells + c];
+                if (ret_out) ret_out[c] = acc;
+            } else {
+                acc = src[c];
+            }
+        }
+        s_ret[j] = acc;
+    }
+    __syncthreads();
+    const int nstat = per_agent ? 2 + 2 * cols : 2;
+    const bool live = tid < epb && env0 + tid < N;
+    double tot = 0.0;
+    if (live)
+        for (int c = 0; c < cols; ++c) tot += s_ret[tid * cols + c];
+    {
+        const double a = warp_sum_fixed(tot), b = warp_sum_fixed(__dmul_rn(tot, tot));
+        if (lane == 0) { s_part[0 * 8 + warp] = a; s_part[1 * 8 + warp] = b; }
+    }
+    if (per_agent) {
+        for (int c = 0; c < cols; ++c) {
+            const double v = live ? s_ret[tid * cols + c] : 0.0;
+            const double a = warp_sum_fixed(v), b = warp_sum_fixed(__dmul_rn(v, v));
+            if (lane == 0) { s_part[(2 + 2 * c) * 8 + warp] = a; s_part[(3 + 2 * c) * 8 + warp] = b; }
+        }
+    }
+    __syncthreads();
+    if (tid < nstat) {
+        double acc = 0.0;
+#pragma unroll
+        for (int w = 0; w < STATS_THREADS / 32; ++w) acc += s_part[tid * 8 + w];
+        partial[(int64_t)tid * nslices + blockIdx.x] = acc;
+    }
+}
+
+// One block per statistic: strided threads over the slices' partials, then a fixed shared-memory tree (deterministic).
+// accumulate != 0: stats += result (statistics of an evaluation batch build up on the device).
+__global__ void __launch_bounds__(STATS_THREADS) stats_final_kernel(const double* __restrict__ partial, double* __restrict__ stats, int64_t N,
+                                                                   int nslices, int accumulate) {
     __shared__ double red[STATS_THREADS];
-    const int q = blockIdx.y;
-    const int64_t per_block = (N + STATS_BLOCKS - 1) / STATS_BLOCKS;
-    const int64_t lo = (int64_t)blockIdx.x * per_block;
-    const int64_t hi = lo + per_block < N ? lo + per_block : N;
+    const int q = blockIdx.x;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     double acc = 0.0;
-    for (int64_t n = lo + threadIdx.x; n < hi; n += STATS_THREADS) acc += stats_value(ret, n, cols, q);
+    for (int b = threadIdx.x; b < nslices; b += STATS_THREADS) acc += partial[(int64_t)q * nslices + b];
     red[threadIdx.x] = acc;
     __syncthreads();
-    for (int s = STATS_THREADS / 2; s > 0; s >>= 1) {
+    for (int s = STATS_THREADS / 2; s >= 32; s >>= 1) {
         if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) partial[q * STATS_BLOCKS + blockIdx.x] = red[0];
-}
-
-// One warp per statistic: fixed-shape tree over the STATS_BLOCKS partials (deterministic).
-// accumulate != 0: stats += result (statistics of an evaluation batch build up on the device).
-__global__ void __launch_bounds__(32) return_stats_final_kernel(const double* __restrict__ partial, double* __restrict__ stats, int64_t N,
-                                                                int nstat, int accumulate) {
-    const int q = blockIdx.x;
-    const int lane = threadIdx.x;
-    double acc = 0.0;
-    for (int b = lane; b < STATS_BLOCKS; b += 32) acc += partial[q * STATS_BLOCKS + b];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-    if (lane == 0) {
-        stats[1 + q] = accumulate ? stats[1 + q] + acc : acc;
-        if (q == 0) stats[0] = accumulate ? stats[0] + (double)N : (double)N;
+    if (threadIdx.x < 32) {
+        const double v = warp_sum_fixed(red[threadIdx.x]);
+        if (threadIdx.x == 0) {
+            stats[1 + q] = accumulate ? stats[1 + q] + v : v;
+            if (q == 0) stats[0] = accumulate ? stats[0] + (double)N : (double)N;
+        }
     }
-}
-
-// Episode return per (env, agent) = sum over periods of the step rewards, added in period order like
-// the host loops of the reference ("reward += r", inv_management.py:223-231).  One thread per cell;
-// each period is one coalesced row of step_reward [T][cells].
-__global__ void __launch_bounds__(256) episode_return_kernel(const double* __restrict__ step_reward, double* __restrict__ ret, int64_t cells,
-                                                             int T) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cells) return;
-    double acc = 0.0;
-    for (int t = 0; t < T; ++t) acc += step_reward[(int64_t)t * cells + c];
-    ret[c] = acc;
 }
 
 }  // namespace imx
