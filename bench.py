@@ -379,7 +379,6 @@ def config3_fused_rollout(total_envs, world, rank, dev, torch, dist, reps):
     m, T = env.num_nodes, env.num_periods
     z = torch.full((m,), 25.0, dtype=torch.float64, device=dev)
     ret = torch.empty((N, m), dtype=torch.float64, device=dev)
-    st_one = torch.zeros(3 + 2 * m, dtype=torch.float64, device=dev)
     stats = torch.zeros(3 + 2 * m, dtype=torch.float64, device=dev)
     lib, h = env._lib, env._handle
     s = torch.cuda.current_stream().cuda_stream
@@ -389,8 +388,8 @@ def config3_fused_rollout(total_envs, world, rank, dev, torch, dist, reps):
         ep[0] += 1                                          # a new episode id = new Philox draws
         _lib.check(lib.imx_rollout_basestock(h, C.c_void_p(z.data_ptr()), 0, None, None, 0, ep[0], None, C.c_void_p(ret.data_ptr()), None, None, 0,
                                              C.c_void_p(s)))
-        _lib.check(lib.imx_return_stats(h, C.c_void_p(ret.data_ptr()), C.c_void_p(st_one.data_ptr()), C.c_void_p(s)))
-        stats.add_(st_one)
+        # statistics of the batch added into `stats` on the device (imx_episode_stats over ONE row of returns, accumulate = 1)
+        _lib.check(lib.imx_episode_stats(h, C.c_void_p(ret.data_ptr()), 1, None, C.c_void_p(stats.data_ptr()), 1, C.c_void_p(s)))
 
     for _ in range(3):
         batch()

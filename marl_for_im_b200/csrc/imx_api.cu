@@ -648,6 +648,7 @@ static void fill_args(const imx_env* e, StepArgs& A) {
     }
     A.TL = e->TL;
     A.tab = e->d_tab;
+    A.tabf = e->d_tab ? reinterpret_cast<const float*>(e->d_tab + (size_t)e->m * 4 * e->TL) : nullptr;   // float32 copy behind the float64 table
     A.nodes = e->d_nodes;
     A.inv = (int32_t*)e->field_ptr[IMX_F_INV];
     A.backlog = (int32_t*)e->field_ptr[IMX_F_BACKLOG];
@@ -809,8 +810,12 @@ extern "C" int imx_create(const imx_config* cfg, imx_env** out) {
     {
         std::vector<double> tab = build_tables(e, &e->TL);
         if (e->TL > 0) {
-            IMX_CREATE_CUDA(cudaMalloc(&e->d_tab, tab.size() * sizeof(double)));
+            // [m][4][TL] float64, then the same entries rounded to float32 (what an obs_f32 kernel stores: np.float32(obs64))
+            std::vector<float> tabf(tab.size());
+            for (size_t k = 0; k < tab.size(); ++k) tabf[k] = (float)tab[k];
+            IMX_CREATE_CUDA(cudaMalloc(&e->d_tab, tab.size() * (sizeof(double) + sizeof(float))));
             IMX_CREATE_CUDA(cudaMemcpy(e->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+            IMX_CREATE_CUDA(cudaMemcpy(e->d_tab + tab.size(), tabf.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
         }
     }
     {   // partial sums of the two-stage statistics: [statistic][slice] (imx_stats.cuh) or [2 x column][STATS_BLOCKS] (imx_eval.cuh)

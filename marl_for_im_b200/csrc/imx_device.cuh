@@ -119,6 +119,7 @@ struct StepArgs {
     int32_t TL;                // entries per rescale table row (0: no tables, compute)
     int32_t pad_tl;
     const double* __restrict__ tab;         // [m][4][TL] exact rescale results, see build_tables() in imx_api.cu
+    const float* __restrict__ tabf;         // the same table rounded to float32 (obs_f32: the value is stored as loaded, no conversion in the kernel)
     const NodeParams* __restrict__ nodes;   // [m]
     // state (SoA, int32)
     int32_t* __restrict__ inv;
@@ -217,11 +218,34 @@ __device__ __forceinline__ double div_by_m(double s, int m, double inv_m, bool m
     const double rem = __fma_rn(-q0, (double)m, s);
     return __fma_rn(rem, inv_m, q0);
 }
+// float32 observations: the table entry rounded once on the host ((float)tab[v] == np.float32(obs64)) — one 4-byte load and no
+// F2F.F32.F64 in the kernel (conversions run at a fraction of the FP64 rate; 7 per lane made the float32 step of config 2
+// SLOWER than the float64 one although it writes 112 fewer bytes per env)
+__device__ __forceinline__ float scaled_f32(const float* __restrict__ tabrow_f, int TL, int which, int v) {
+#ifdef IMX_DEBUG_BOUNDS
+    if ((unsigned)v >= (unsigned)TL) __trap();
+#endif
+    return __ldg(tabrow_f + which * TL + (int)min((unsigned)v, (unsigned)(TL - 1)));
+}
 // One observation element.  `row` addresses the agent's vector in the output element type.
 #define OBS_PUT(row, k, v)                                                           \
     do {                                                                             \
         if (KF(obs_f32)) reinterpret_cast<float*>(row)[k] = (float)(v);              \
         else reinterpret_cast<double*>(row)[k] = (v);                                \
+    } while (0)
+
+// A rescaled element (scaled() above) and a raw integer element: for float32 rows the float table / the int -> float
+// conversion give the bits of np.float32(float64 value) directly ((float)(double)i == (float)i for every int).
+#define OBS_PUT_SCALED(row, k, CHECKED_, tabrow, tabrow_f, TL, which, v, vmax, a, bma)                                   \
+    do {                                                                                                                 \
+        if (KF(obs_f32) && KHAS(tab) && (!(CHECKED_) || (unsigned)(v) < (unsigned)(TL)))                                  \
+            reinterpret_cast<float*>(row)[k] = scaled_f32(tabrow_f, TL, which, v);                                        \
+        else OBS_PUT(row, k, scaled<CHECKED_>(KHAS(tab), tabrow, TL, which, v, vmax, a, bma));                            \
+    } while (0)
+#define OBS_PUT_INT(row, k, v)                                                       \
+    do {                                                                             \
+        if (KF(obs_f32)) reinterpret_cast<float*>(row)[k] = (float)(v);              \
+        else reinterpret_cast<double*>(row)[k] = (double)(v);                        \
     } while (0)
 
 // profit = p*ship - c*order - h*|inv' - target| - bc*backlog'           MAIM_env.py:421-424

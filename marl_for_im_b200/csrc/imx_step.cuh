@@ -220,14 +220,15 @@ __device__ __forceinline__ void write_obs_row(void* row, const StepArgs& A, cons
     const double inv_max = (double)np.inv_max, order_max = (double)np.order_max;
     const double dem_max = (double)np.demand_max;
     const double ou_max = KF(multi) ? order_max : inv_max;   // MAIM_env.py:300 vs IM_env.py:265
+    const float* __restrict__ tabrow_f = (KF(obs_f32) && KHAS(tab)) ? A.tabf + (size_t)node_idx * 4 * TL : nullptr;
     if (KF(std_state)) {
-        OBS_PUT(row, 0, scaled<CHECKED>(KHAS(tab), tabrow, TL, TAB_INV, inv, inv_max, a, bma));
-        OBS_PUT(row, 1, scaled<CHECKED>(KHAS(tab), tabrow, TL, TAB_DEM, backlog, dem_max, a, bma));
-        OBS_PUT(row, 2, scaled<CHECKED>(KHAS(tab), tabrow, TL, KF(multi) ? TAB_ORD : TAB_INV, order_u, ou_max, a, bma));
+        OBS_PUT_SCALED(row, 0, CHECKED, tabrow, tabrow_f, TL, TAB_INV, inv, inv_max, a, bma);
+        OBS_PUT_SCALED(row, 1, CHECKED, tabrow, tabrow_f, TL, TAB_DEM, backlog, dem_max, a, bma);
+        OBS_PUT_SCALED(row, 2, CHECKED, tabrow, tabrow_f, TL, KF(multi) ? TAB_ORD : TAB_INV, order_u, ou_max, a, bma);
     } else {
-        OBS_PUT(row, 0, (double)inv);
-        OBS_PUT(row, 1, (double)backlog);
-        OBS_PUT(row, 2, (double)order_u);
+        OBS_PUT_INT(row, 0, inv);
+        OBS_PUT_INT(row, 1, backlog);
+        OBS_PUT_INT(row, 2, order_u);
     }
     if (KF(multi) && !KF(std_state)) {
         // MAIM_env.py:319-324 (quirk 13): raw pipeline at [3:3+D] whatever the history offsets, rest stays 0
@@ -235,7 +236,7 @@ __device__ __forceinline__ void write_obs_row(void* row, const StepArgs& A, cons
         if (KF(td)) {
 #pragma unroll
             for (int k = 0; k < DMAX; ++k)
-                if (k < KF(D)) OBS_PUT(row, 3 + k, (double)pipe[k]);
+                if (k < KF(D)) OBS_PUT_INT(row, 3 + k, pipe[k]);
         }
         return;
     }
@@ -243,24 +244,25 @@ __device__ __forceinline__ void write_obs_row(void* row, const StepArgs& A, cons
     if (KF(pd)) {
 #pragma unroll
         for (int j = 0; j < PMAX; ++j)
-            if (j < KF(P)) OBS_PUT(row, k0 + j, KF(write_hd) ? scaled<CHECKED>(KHAS(tab), tabrow, TL, TAB_DEM, hd[j], dem_max, a, bma) : 0.0);   // quirk 2
+            if (j < KF(P)) {
+                if (KF(write_hd)) OBS_PUT_SCALED(row, k0 + j, CHECKED, tabrow, tabrow_f, TL, TAB_DEM, hd[j], dem_max, a, bma);
+                else OBS_PUT(row, k0 + j, 0.0);             // quirk 2
+            }
         k0 += KF(P);
     }
     if (KF(pa)) {
 #pragma unroll
         for (int j = 0; j < PMAX; ++j)
-            if (j < KF(P)) OBS_PUT(row, k0 + j, scaled<CHECKED>(KHAS(tab), tabrow, TL, TAB_ORD, ho[j], order_max, a, bma));
+            if (j < KF(P)) OBS_PUT_SCALED(row, k0 + j, CHECKED, tabrow, tabrow_f, TL, TAB_ORD, ho[j], order_max, a, bma);
         k0 += KF(P);
     }
     if (KF(td)) {
 #pragma unroll
         for (int k = 0; k < DMAX; ++k) {
             if (k < KF(D)) {
-                double v;
-                if (!KF(std_state)) v = (double)pipe[k];                                    // IM kinds, raw
-                else if (div && KF(multi)) v = scaled<CHECKED>(KHAS(tab), tabrow, TL, TAB_PIPE2, min(pipe[k], 2 * np.inv_max), 2.0 * inv_max, a, bma);   // MAIM_div_env.py:408-411
-                else v = scaled<CHECKED>(KHAS(tab), tabrow, TL, TAB_INV, pipe[k], inv_max, a, bma);
-                OBS_PUT(row, k0 + k, v);
+                if (!KF(std_state)) OBS_PUT_INT(row, k0 + k, pipe[k]);                      // IM kinds, raw
+                else if (div && KF(multi)) OBS_PUT_SCALED(row, k0 + k, CHECKED, tabrow, tabrow_f, TL, TAB_PIPE2, min(pipe[k], 2 * np.inv_max), 2.0 * inv_max, a, bma);   // MAIM_div_env.py:408-411
+                else OBS_PUT_SCALED(row, k0 + k, CHECKED, tabrow, tabrow_f, TL, TAB_INV, pipe[k], inv_max, a, bma);
             }
         }
         k0 += KF(D);

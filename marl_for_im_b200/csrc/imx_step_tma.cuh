@@ -397,9 +397,12 @@ __device__ __forceinline__ void cc_build_row(const StepArgs& A, const TileSmem& 
     uint32_t* row = reinterpret_cast<uint32_t*>(cc_tile) + (size_t)L.cell * W * WPE;
     const uint32_t* ob = reinterpret_cast<const uint32_t*>(S.obs);
     const int row_words = O * WPE;                   // an observation row in words; rows start 16-byte aligned when this is a multiple of 4
+    // opponents in agent order without a divergent branch: the q-th opponent of agent i is j = q + (q >= i), so every lane of
+    // the warp runs the same instruction stream and (specialised build: m is a literal) the loops unroll into static offsets
     int k = 0;
-    for (int j = 0; j < m; ++j) {
-        if (j == L.i) continue;
+#pragma unroll
+    for (int q = 0; q < m - 1; ++q) {
+        const int j = q + (q >= L.i ? 1 : 0);
         const ObsT v = A.cc_fill ? (ObsT)fmin(fmax(S.act[e0 + j], A.cc_lo), A.cc_hi) : (ObsT)0;
         if constexpr (WPE == 1) {
             row[k++] = __float_as_uint((float)v);
@@ -414,19 +417,19 @@ __device__ __forceinline__ void cc_build_row(const StepArgs& A, const TileSmem& 
     auto copy_row = [&](int cell_src) {
         const uint32_t* src = ob + (size_t)cell_src * row_words;
         if ((row_words & 3) == 0) {
+#pragma unroll
             for (int q = 0; q < row_words / 4; ++q) {
                 const uint4 v = reinterpret_cast<const uint4*>(src)[q];
                 row[k] = v.x; row[k + 1] = v.y; row[k + 2] = v.z; row[k + 3] = v.w;
                 k += 4;
             }
         } else {
+#pragma unroll
             for (int q = 0; q < row_words; ++q) row[k++] = src[q];
         }
     };
-    for (int j = 0; j < m; ++j) {
-        if (j == L.i) continue;
-        copy_row(e0 + j);
-    }
+#pragma unroll
+    for (int q = 0; q < m - 1; ++q) copy_row(e0 + q + (q >= L.i ? 1 : 0));
     copy_row(L.cell);
 }
 template <int MAXC>
