@@ -983,12 +983,19 @@ static bool pipe_pays(const imx_env* e, int n_tiles) {
 // 64-thread tiles of 4-wide chains, 6 for 8-lane divergent tiles and for the env-per-thread tiles (more CTAs than fit at once:
 // the late ones shorten everybody's tile list, which measured faster than a grid of exactly the resident CTAs), 4 otherwise.
 static int pipe_ctas_for(const imx_env* e, const TileLayout& L) {
-    if (e->pipe_ctas > 0) return e->pipe_ctas;
     const bool is_cc = (&L == &e->tile_cc);
-    if (e->step_et && !is_cc) return 6;
-    if (e->div) return m_pad_of(e) <= 4 ? 4 : 6;
-    if (e->jit_threads == 64) return 8;
-    return 4;
+    int want = 4;
+    if (e->pipe_ctas > 0) want = e->pipe_ctas;
+    else if (e->step_et && !is_cc) want = 6;
+    else if (e->div) want = m_pad_of(e) <= 4 ? 4 : 6;
+    else if (e->jit_threads == 64) want = 8;
+    // never more than shared memory lets in (228 KB per SM, 1 KB reserved per CTA + the barriers): the tiles are assigned
+    // statically, so CTAs that only become resident in a second wave would serialise the launch (float64 critic rows of the
+    // 2-stage chain: 3 CTAs fit, a grid of 4 per SM took 11.0 us instead of 6)
+    const int64_t per_cta = (int64_t)pipe_stages_for(e, L) * L.total + 1024 + 256;
+    const int fit = (int)((228 * 1024) / per_cta);
+    if (want > fit) want = fit;
+    return want < 1 ? 1 : want;
 }
 
 // periods > 1 (imx_step_many): the TMA kernel advances that many periods in one launch with the tiles' state resident
@@ -1312,6 +1319,8 @@ static int launch_return_stats(imx_env* e, const double* src, int periods, bool 
     const int epb = stats_envs_per_block(cols);
     const int nslices = (int)((e->N + epb - 1) / epb);
     const bool pdl = e->use_pdl != 0;
+    // one row of "step rewards" whose sum nobody asked for IS the returns: the plain kernel keeps four loads per thread in flight
+    if (fused && periods == 1 && !ret_out) fused = false;
     if (fused)
         IMX_CUDA(launch_dependent(stats_slice_kernel<true>, dim3((unsigned)nslices), dim3(STATS_THREADS), s, pdl, src, ret_out, e->d_stats_partial,
                                   e->N, cols, per_agent, periods, epb, nslices));

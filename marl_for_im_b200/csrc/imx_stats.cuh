@@ -90,9 +90,14 @@ __global__ void __launch_bounds__(128) dfo_objective_kernel(const double* __rest
 // Both are programmatic dependent launches (griddepcontrol.wait), so their launch latency hides behind the kernel in front.
 constexpr int STATS_THREADS = 256;
 constexpr int STATS_BLOCKS = 128;                              // slices of the column statistics (imx_eval.cuh)
-constexpr int STATS_MAX_STAT = 2 + 2 * IMX_MAX_NODES;
 
-static inline int stats_envs_per_block(int cols) { const int e = STATS_THREADS / cols; return e < 32 ? 32 : e; }
+constexpr int STATS_SLICE_CELLS = 1024;                        // returns one block keeps in shared memory
+// envs per slice: as many as fit (whole warps of envs, at most one per thread, at least 32)
+static inline int stats_envs_per_block(int cols) {
+    int e = (STATS_SLICE_CELLS / cols) & ~31;
+    if (e > STATS_THREADS) e = STATS_THREADS;
+    return e < 32 ? 32 : e;
+}
 
 __device__ __forceinline__ double warp_sum_fixed(double v) {
 #pragma unroll
@@ -104,19 +109,24 @@ template <bool FUSED>
 __global__ void __launch_bounds__(STATS_THREADS) stats_slice_kernel(const double* __restrict__ src, double* __restrict__ ret_out,
                                                                     double* __restrict__ partial, int64_t N, int cols, int per_agent, int T,
                                                                     int epb, int nslices) {
-    __shared__ double s_ret[32 * IMX_MAX_NODES > STATS_THREADS ? 32 * IMX_MAX_NODES : STATS_THREADS];   // [epb][cols] returns of the slice
-    __shared__ double s_part[STATS_MAX_STAT * (STATS_THREADS / 32)];
+    // [epb][stride] returns of the slice; the row stride is odd so that the lanes of phase 2 (one env each) hit distinct banks
+    __shared__ double s_ret[STATS_SLICE_CELLS + STATS_THREADS];
+    constexpr int MAXK = STATS_SLICE_CELLS / STATS_THREADS;    // cells per thread
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int stride = cols | 1;
     const int64_t env0 = (int64_t)blockIdx.x * epb;
     const int64_t cells = N * cols;
     const int64_t cell0 = env0 * cols;
     const int my_cells = epb * cols;
     asm volatile("griddepcontrol.wait;" ::: "memory");         // (returns at once unless launched as a programmatic dependent)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the final kernel may take its seat; it waits for this grid to complete
-    for (int j = tid; j < my_cells; j += STATS_THREADS) {
+    double acc[MAXK];
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k) {                           // (unrolled: the loads of a thread's cells are all in flight together)
+        const int j = tid + k * STATS_THREADS;
         const int64_t c = cell0 + j;
-        double acc = 0.0;
-        if (c < cells) {
+        acc[k] = 0.0;
+        if (j < my_cells && c < cells) {
             if (FUSED) {
                 int t = 0;
                 for (; t + 10 <= T; t += 10) {                 // ten independent loads in flight, added in period order
@@ -124,39 +134,45 @@ __global__ void __launch_bounds__(STATS_THREADS) stats_slice_kernel(const double
 #pragma unroll
                     for (int u = 0; u < 10; ++u) r[u] = src[(int64_t)(t + u) * cells + c];
 #pragma unroll
-                    for (int u = 0; u < 10; ++u) acc += r[u];
+                    for (int u = 0; u < 10; ++u) acc[k] = __dadd_rn(acc[k], r[u]);
                 }
-                for (; t < T; ++t) acc += src[(int64_t)t * cells + c];
-                if (ret_out) ret_out[c] = acc;
+                for (; t < T; ++t) acc[k] = __dadd_rn(acc[k], src[(int64_t)t * cells + c]);
+                if (ret_out) ret_out[c] = acc[k];
             } else {
-                acc = src[c];
+                acc[k] = src[c];
             }
         }
-        s_ret[j] = acc;
     }
-    __syncthreads();
-    const int nstat = per_agent ? 2 + 2 * cols : 2;
-    const bool live = tid < epb && env0 + tid < N;
-    double tot = 0.0;
-    if (live)
-        for (int c = 0; c < cols; ++c) tot += s_ret[tid * cols + c];
-    {
-        const double a = warp_sum_fixed(tot), b = warp_sum_fixed(__dmul_rn(tot, tot));
-        if (lane == 0) { s_part[0 * 8 + warp] = a; s_part[1 * 8 + warp] = b; }
-    }
-    if (per_agent) {
-        for (int c = 0; c < cols; ++c) {
-            const double v = live ? s_ret[tid * cols + c] : 0.0;
-            const double a = warp_sum_fixed(v), b = warp_sum_fixed(__dmul_rn(v, v));
-            if (lane == 0) { s_part[(2 + 2 * c) * 8 + warp] = a; s_part[(3 + 2 * c) * 8 + warp] = b; }
-        }
-    }
-    __syncthreads();
-    if (tid < nstat) {
-        double acc = 0.0;
 #pragma unroll
-        for (int w = 0; w < STATS_THREADS / 32; ++w) acc += s_part[tid * 8 + w];
-        partial[(int64_t)tid * nslices + blockIdx.x] = acc;
+    for (int k = 0; k < MAXK; ++k) {
+        const int j = tid + k * STATS_THREADS;
+        if (j < my_cells) s_ret[(j / cols) * stride + (j % cols)] = acc[k];
+    }
+    __syncthreads();
+    // one warp per task: task c < cols = (Σ, Σ²) of agent c's returns, task cols = (Σ, Σ²) of the per-env totals (sum over agents
+    // in agent order).  Lane g adds the envs g, g + 32, ... of the slice in that order, then the lanes are added in a fixed tree.
+    const int live = (int)(N - env0 < epb ? N - env0 : epb);   // envs of this slice that exist
+    for (int task = warp; task <= cols; task += STATS_THREADS / 32) {
+        if (task < cols && !per_agent) continue;
+        double sum = 0.0, sq = 0.0;
+        for (int e = lane; e < live; e += 32) {
+            double v;
+            if (task < cols) {
+                v = s_ret[e * stride + task];
+            } else {
+                v = 0.0;
+                for (int c = 0; c < cols; ++c) v = __dadd_rn(v, s_ret[e * stride + c]);
+            }
+            sum = __dadd_rn(sum, v);
+            sq = __dadd_rn(sq, __dmul_rn(v, v));
+        }
+        sum = warp_sum_fixed(sum);
+        sq = warp_sum_fixed(sq);
+        if (lane == 0) {
+            const int q = task < cols ? 2 + 2 * task : 0;
+            partial[(int64_t)q * nslices + blockIdx.x] = sum;
+            partial[(int64_t)(q + 1) * nslices + blockIdx.x] = sq;
+        }
     }
 }
 

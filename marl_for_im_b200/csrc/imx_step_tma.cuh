@@ -387,16 +387,20 @@ __device__ __forceinline__ void tile_period(const StepArgs& A, const TileLayout&
 // from the observation tile the step has just written (all m rows of an env are written by lanes of ONE warp: the caller
 // separates the two phases with __syncwarp) and from the action tile of this period (FillInActions :165-193 /
 // CC_inv_management.py:516-528: opponent actions clipped to [lo, hi]; zeros at sampling time).  Opponents in agent order.
+template <int BYTES> struct CcWord { typedef uint32_t type; };
+template <> struct CcWord<8> { typedef unsigned long long type; };
 template <typename ObsT, int MAXC>
 __device__ __forceinline__ void cc_build_row(const StepArgs& A, const TileSmem& S, unsigned char* cc_tile, const LaneCtx<MAXC>& L) {
     if (!L.ok) return;
     const int m = KF(m), O = KF(O);
     const int W = (m - 1) * (1 + O) + O;
     const int e0 = L.e_loc * m;
-    constexpr int WPE = sizeof(ObsT) / 4;            // 32-bit words per element: the rows are only 4-byte aligned (W is odd for m = 2)
-    uint32_t* row = reinterpret_cast<uint32_t*>(cc_tile) + (size_t)L.cell * W * WPE;
-    const uint32_t* ob = reinterpret_cast<const uint32_t*>(S.obs);
-    const int row_words = O * WPE;                   // an observation row in words; rows start 16-byte aligned when this is a multiple of 4
+    // a row is copied in units of its element type (4-byte words for float32 rows, which are only 4-byte aligned — W is odd
+    // for m = 2; 8-byte words for float64 rows: 17 STS.64 instead of 34 STS.32 per lane, conflict-free at a stride of 2 W words)
+    using WordT = typename CcWord<sizeof(ObsT)>::type;
+    WordT* row = reinterpret_cast<WordT*>(cc_tile) + (size_t)L.cell * W;
+    const WordT* ob = reinterpret_cast<const WordT*>(S.obs);
+    constexpr int VEC = 16 / sizeof(ObsT);           // elements per 16-byte shared-memory load
     // opponents in agent order without a divergent branch: the q-th opponent of agent i is j = q + (q >= i), so every lane of
     // the warp runs the same instruction stream and (specialised build: m is a literal) the loops unroll into static offsets
     int k = 0;
@@ -404,28 +408,28 @@ __device__ __forceinline__ void cc_build_row(const StepArgs& A, const TileSmem& 
     for (int q = 0; q < m - 1; ++q) {
         const int j = q + (q >= L.i ? 1 : 0);
         const ObsT v = A.cc_fill ? (ObsT)fmin(fmax(S.act[e0 + j], A.cc_lo), A.cc_hi) : (ObsT)0;
-        if constexpr (WPE == 1) {
-            row[k++] = __float_as_uint((float)v);
-        } else {
-            const unsigned long long u = (unsigned long long)__double_as_longlong((double)v);
-            row[k++] = (uint32_t)u;
-            row[k++] = (uint32_t)(u >> 32);
-        }
+        if constexpr (sizeof(ObsT) == 4) row[k++] = __float_as_uint((float)v);
+        else row[k++] = (unsigned long long)__double_as_longlong((double)v);
     }
-    // observation rows: 16-byte shared-memory loads (one wavefront per quarter-warp instead of the 8-way conflicts of scalar
-    // loads at a row stride of 32 or 64 bytes), scalar stores into the odd-strided critic row (conflict-free)
+    // observation rows: 16-byte shared-memory loads where the rows are 16-byte multiples (one wavefront per quarter-warp instead
+    // of the 8-way conflicts of scalar loads at a row stride of 32 or 64 bytes), element-wise stores into the critic row
     auto copy_row = [&](int cell_src) {
-        const uint32_t* src = ob + (size_t)cell_src * row_words;
-        if ((row_words & 3) == 0) {
+        const WordT* src = ob + (size_t)cell_src * O;
+        if (O % VEC == 0) {
 #pragma unroll
-            for (int q = 0; q < row_words / 4; ++q) {
-                const uint4 v = reinterpret_cast<const uint4*>(src)[q];
-                row[k] = v.x; row[k + 1] = v.y; row[k + 2] = v.z; row[k + 3] = v.w;
-                k += 4;
+            for (int q = 0; q < O / VEC; ++q) {
+                if constexpr (sizeof(ObsT) == 4) {
+                    const uint4 v = reinterpret_cast<const uint4*>(src)[q];
+                    row[k] = v.x; row[k + 1] = v.y; row[k + 2] = v.z; row[k + 3] = v.w;
+                } else {
+                    const ulonglong2 v = reinterpret_cast<const ulonglong2*>(src)[q];
+                    row[k] = v.x; row[k + 1] = v.y;
+                }
+                k += VEC;
             }
         } else {
 #pragma unroll
-            for (int q = 0; q < row_words; ++q) row[k++] = src[q];
+            for (int q = 0; q < O; ++q) row[k++] = src[q];
         }
     };
 #pragma unroll
