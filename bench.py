@@ -351,6 +351,27 @@ def config4_episode_loop(name, total_envs, world, rank, dev, torch, dist, peak, 
     dt = _timed_region(g_ep.replay, reps, torch, dist, world, dev, post=(lambda: dist.all_reduce(stats)) if world > 1 else None)
     timed_replays(g_st, 3, torch)
     dts = timed_replays(g_st, max(reps, 10), torch) / (max(reps, 10) * T)
+    # the same episode with the 30 periods as ONE imx_step_many launch (the pre-staged actions are a stored plan): no per-period
+    # launch floor, which is what bounds the strong-scaling curve of the per-step loop at 32 768 envs per GPU
+    fused = None
+    if True:
+        obs_all = torch.empty((T, N, m, O), dtype=torch.float64, device=dev)    # (at most 2.3 GB: div2, 262 144 envs)
+
+        def episode_many(stream):
+            _lib.check(lib.imx_reset(h, C.c_void_p(demand.data_ptr()), None, 0, 1, None, C.c_void_p(stream)))
+            _lib.check(lib.imx_step_many(h, C.c_void_p(actions.data_ptr()), T, C.c_void_p(obs_all.data_ptr()), C.c_void_p(rew.data_ptr()), None,
+                                         C.c_void_p(stream)))
+            _lib.check(lib.imx_episode_stats(h, C.c_void_p(rew.data_ptr()), T, None, C.c_void_p(stats.data_ptr()), 1, C.c_void_p(stream)))
+
+        g_many = capture(episode_many, torch)
+        for _ in range(3):
+            g_many.replay()
+        keep = stats.clone()
+        dtm = _timed_region(g_many.replay, reps, torch, dist, world, dev)
+        stats.copy_(keep)
+        fused = {"agent_steps_per_sec": world * N * m * T * reps / dtm, "ms_per_episode": dtm / reps * 1e3,
+                 "api": "imx_reset + imx_step_many(K=30) + imx_episode_stats per episode (one CUDA graph)"}
+        del obs_all
     B = algorithmic_bytes_per_env_step(env)
     flags = int(env.error_flags.abs().sum())
     out = {"workload": f"MAIM_div_env {name}, MA_6 obs mode, {total_envs} envs in total over {world} GPU(s) = {N} per GPU (strong scaling), "
@@ -360,6 +381,7 @@ def config4_episode_loop(name, total_envs, world, rank, dev, torch, dist, peak, 
            "step_kernel": {"us_per_launch": dts * 1e6, "achieved": B * N / dts / 1e9, "peak": peak, "unit": "GB/s", "frac": B * N / dts / 1e9 / peak,
                            "algorithmic_bytes_per_env_step": B, "kernel": KERNEL_VARIANTS[variant],
                            "traffic": ncu_traffic(f"step_kernel_{name}_{N}")[0], "traffic_source": ncu_traffic(f"step_kernel_{name}_{N}")[1]},
+           "replay_fused": fused,
            "watchdog_flags": flags, "mean_return": float((stats[1] / stats[0]).item()) if float(stats[0].item()) > 0 else None,
            "cpu_baseline_reference": reference_timing("config4_" + name)}
     del env

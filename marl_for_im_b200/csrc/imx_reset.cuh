@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
                                       ho, div != 0);
         }
     }
-    __syncthreads();
+    // (the fills that do not read the template run while the first m threads are still building it: the barrier sits behind them)
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // zero the whole state block (16 bytes per store), then overwrite inv with init_inv
@@ -55,6 +55,29 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
     for (int64_t k = gtid; k < n4; k += stride) z4[k] = make_int4(0, 0, 0, 0);
     for (int64_t k = n4 * 4 + gtid; k < Z.zero_words; k += stride) Z.zero_base[k] = 0;
     for (int64_t k = gtid; k < A.N; k += stride) Z.err[k] = 0;
+    if (Z.demand_in) {
+        // demand [N][R][T] -> [T][R][N]: one thread per (chunk of RESET_T_CHUNK periods, retailer row, env), env fastest, so the
+        // stores of a warp are 32 consecutive words per period and the loads of a thread are one short run of its env's row
+        const int R = Z.R, T = Z.T;
+        const int chunks = (T + RESET_T_CHUNK - 1) / RESET_T_CHUNK;
+        const int64_t rows = A.N * R;
+        const int64_t items = rows * chunks;
+        for (int64_t k = gtid; k < items; k += stride) {
+            const int ch = (int)(k / rows);
+            const int64_t idx = k - (int64_t)ch * rows;
+            const int r = (int)(idx / A.N);
+            const int64_t n = idx - (int64_t)r * A.N;
+            const int32_t* src = Z.demand_in + (n * R + r) * T;
+            const int t0 = ch * RESET_T_CHUNK;
+            int v[RESET_T_CHUNK];
+#pragma unroll
+            for (int u = 0; u < RESET_T_CHUNK; ++u) v[u] = (t0 + u < T) ? src[t0 + u] : 0;
+#pragma unroll
+            for (int u = 0; u < RESET_T_CHUNK; ++u)
+                if (t0 + u < T) Z.demand_T[((int64_t)(t0 + u) * R + r) * A.N + n] = v[u];
+        }
+    }
+    __syncthreads();                                 // the observation template and init_inv are complete
     if (A.obs) {
         // every env's initial observation is the same m*O-element template: 16-byte stores where the template
         // length allows it, and the position inside the template advances by (stride mod len) per iteration
@@ -85,28 +108,6 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
                 rem += step;
                 if (rem >= len) rem -= len;
             }
-        }
-    }
-    if (Z.demand_in) {
-        // demand [N][R][T] -> [T][R][N]: one thread per (chunk of RESET_T_CHUNK periods, retailer row, env), env fastest, so the
-        // stores of a warp are 32 consecutive words per period and the loads of a thread are one short run of its env's row
-        const int R = Z.R, T = Z.T;
-        const int chunks = (T + RESET_T_CHUNK - 1) / RESET_T_CHUNK;
-        const int64_t rows = A.N * R;
-        const int64_t items = rows * chunks;
-        for (int64_t k = gtid; k < items; k += stride) {
-            const int ch = (int)(k / rows);
-            const int64_t idx = k - (int64_t)ch * rows;
-            const int r = (int)(idx / A.N);
-            const int64_t n = idx - (int64_t)r * A.N;
-            const int32_t* src = Z.demand_in + (n * R + r) * T;
-            const int t0 = ch * RESET_T_CHUNK;
-            int v[RESET_T_CHUNK];
-#pragma unroll
-            for (int u = 0; u < RESET_T_CHUNK; ++u) v[u] = (t0 + u < T) ? src[t0 + u] : 0;
-#pragma unroll
-            for (int u = 0; u < RESET_T_CHUNK; ++u)
-                if (t0 + u < T) Z.demand_T[((int64_t)(t0 + u) * R + r) * A.N + n] = v[u];
         }
     }
     // inv lives inside the zeroed block: a grid-wide ordering is needed between the zero fill and the
