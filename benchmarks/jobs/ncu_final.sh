@@ -15,3 +15,5 @@ cap rollout_et_serial8 rollout_kernel_et 1 python benchmarks/one_step.py --confi
 cap rollout_et_div2 rollout_kernel_et 1 python benchmarks/one_step.py --config div2 --envs 262144 --rollout --steps 3
 cap many_div2 step_kernel_tma_many 0 python benchmarks/one_step.py --config div2 --envs 262144 --many --steps 30
 ls -la gpurun_out/*.ncu-rep | awk '{print $5, $9}'
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_kernel_pipe -s 3 -c 1 -f -o gpurun_out/r2_cc_pipe_serial2 python benchmarks/cc_sweep.py --one > gpurun_out/r2_ncu_cc.log 2>&1
+ls -la gpurun_out/*.ncu-rep | awk '{print $5, $9}'
