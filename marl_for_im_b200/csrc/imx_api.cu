@@ -282,6 +282,10 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
     addt("off_pipe", L.off_pipe); addt("off_hd", L.off_hd); addt("off_ho", L.off_ho); addt("off_carry", L.off_carry);
     addt("off_bt", L.off_bt); addt("off_dem", L.off_dem); addt("off_obs", L.off_obs); addt("off_rew", L.off_rew); addt("total", L.total);
     addt("off_act2", L.off_act2); addt("off_dem2", L.off_dem2); addt("total2", L.total2); addt("off_cc", L.off_cc);
+    {   // L2 prefetch of the action tiles ahead of griddepcontrol.wait (IMX_ACT_PREFETCH=0 switches it off for A/B runs)
+        const char* ap = getenv("IMX_ACT_PREFETCH");
+        if (ap && !strcmp(ap, "0")) defs.push_back("IMX_NO_ACT_PREFETCH=1");
+    }
     {   // register bound of the plain step kernel, measured per family: the divergent kernels (natural 47) gain occupancy at 40
         // (div1 +5 %, div2 +1.5 %), the 2-wide chain is faster unconstrained (+8 % at 64), the others are best at their natural 32
         const char* sr = getenv("IMX_STEP_MAXNREG");

@@ -70,6 +70,13 @@ __device__ __forceinline__ void bulk_store_only(void* gdst, const void* ssrc, ui
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// L2 prefetch of a global byte range (a hint: it moves no data into the SM and cannot observe a stale value — L2 is the
+// point of coherence, a later write by the kernel in front simply updates the line).  Issued BEFORE griddepcontrol.wait for
+// the one input a step reads that is cold: the caller's action block (in the benchmark loop it comes from HBM every period,
+// while the state was written into L2 by the previous step), so its DRAM latency overlaps the previous launch's drain.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 
 // Programmatic dependent launch (sm_90+): back-to-back step() launches are chained with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so the next grid may start its prologue
@@ -664,6 +671,10 @@ __device__ __forceinline__ void step_tile(const StepArgs& A, const TileLayout& T
     }
     __syncthreads();
     if (tid == 0) {
+#if defined(IMX_JIT) && !defined(IMX_NO_ACT_PREFETCH)
+        bulk_prefetch_l2(A.actions + n0 * m, b_cell8);
+        for (int r = 0; r < KF(R); ++r) bulk_prefetch_l2(A.demand_T + ((int64_t)A.t * KF(R) + r) * A.N + n0, b_dem);
+#endif
         pdl_wait();                                  // state written by the previous step must be complete and visible
         uint32_t bytes = b_in + 3u * b_cell4 + b_pipe;
         if (KF(need_hd)) bytes += b_hist;
