@@ -128,6 +128,7 @@ struct imx_env {
     int tma_threads = 256;               // CTA size of the TMA kernel (IMX_TMA_THREADS: 64, 128 or 256)
     int use_pdl = 1;                     // chain step launches with programmatic dependent launch (IMX_PDL=0 disables)
     int fuse_periods = 1;                // imx_step_many advances all its periods in one launch (IMX_FUSE_PERIODS=0: K plain launches)
+    int l2_hints = 0;                    // L2 eviction priorities on the pipelined kernel's bulk copies (IMX_L2_HINTS; default: see select_kernels)
     int step_et = 0;                     // the specialised STEP kernels use the env-per-thread period (IMX_STEP_ET; default: divergent networks, m <= 8)
     int rollout_et = 0;                  // the specialised ROLLOUT kernel is the env-per-thread one (imx_rollout_et.cuh; IMX_ROLLOUT_ET, default m <= 8)
     int jit_threads = 128;               // CTA size (compute threads) of the specialised TMA kernels: tma_threads, or the env-per-thread group size
@@ -282,6 +283,9 @@ static void jit_spec(const imx_env* e, int TL, imxjit::Spec& sp, int has_obs = 1
     addt("off_pipe", L.off_pipe); addt("off_hd", L.off_hd); addt("off_ho", L.off_ho); addt("off_carry", L.off_carry);
     addt("off_bt", L.off_bt); addt("off_dem", L.off_dem); addt("off_obs", L.off_obs); addt("off_rew", L.off_rew); addt("total", L.total);
     addt("off_act2", L.off_act2); addt("off_dem2", L.off_dem2); addt("total2", L.total2); addt("off_cc", L.off_cc);
+    {   // L2 eviction priorities on the bulk copies (IMX_L2_HINTS=1: observation stream evict_first, state and rewards evict_last)
+        if (e->l2_hints) defs.push_back("IMX_L2_HINTS=1");
+    }
     {   // L2 prefetch of the action tiles ahead of griddepcontrol.wait (IMX_ACT_PREFETCH=0 switches it off for A/B runs)
         const char* ap = getenv("IMX_ACT_PREFETCH");
         if (ap && !strcmp(ap, "0")) defs.push_back("IMX_NO_ACT_PREFETCH=1");
@@ -444,6 +448,17 @@ static bool stream_is_capturing(cudaStream_t s) {
     return st != cudaStreamCaptureStatusNone;
 }
 
+// see the comment at the call in select_kernels(); l2_bytes <= 0: the B200's 126 MB (imx_jit_compile_check runs without a device)
+static int decide_l2_hints(const imx_env* e, int l2_bytes) {
+    if (l2_bytes <= 0) l2_bytes = 126 << 20;
+    const int64_t per_env = 8 * (int64_t)e->S + 4 * e->R + (int64_t)e->m * (16 + e->O * (e->cfg.obs_f32 ? 4 : 8));
+    const int64_t state_bytes = 4 * (int64_t)e->S * e->N;
+    const char* lh = getenv("IMX_L2_HINTS");
+    if (lh && !strcmp(lh, "1")) return 1;
+    if (lh && !strcmp(lh, "0")) return 0;
+    return (per_env * e->N > (int64_t)l2_bytes / 2 && state_bytes <= (int64_t)l2_bytes * 5 / 8) ? 1 : 0;
+}
+
 static int select_kernels(imx_env* e) {
     const int m = e->m;
     pick_kernels(e, m_pad_of(e), e->div);
@@ -508,6 +523,14 @@ static int select_kernels(imx_env* e) {
         const char* pc = getenv("IMX_PIPE_CTAS");
         e->pipe_ctas = pc ? atoi(pc) : 0;
         e->sm_count = dev_sms;
+        // L2 eviction priorities (observation stream evict_first, state + rewards evict_last): they pay exactly where a launch
+        // streams more than about half of L2 while the state itself would still fit — the write-once stream then no longer
+        // pushes the state out between two periods (config 2 at 262 144 envs 20.7 -> 16.6 us = 1.15 of the HBM copy peak, div2
+        // 33.4 -> 27.1 us, 8-stage 49.2 -> 43.0 us); below that everything is L2-resident anyway (-1 %), above it the state does
+        // not fit and the priorities only disturb the replacement (-2 .. -4 %).  profiles/r2_l2_hints_ab.txt
+        int l2_bytes = 0;
+        cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, e->cfg.device);
+        e->l2_hints = decide_l2_hints(e, l2_bytes);
     }
     IMX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)e->rollout_fn, ROLLOUT_THREADS, 0));
     if (occ < 1) return fail(-4, "rollout kernel does not fit on an SM");
@@ -981,6 +1004,7 @@ static bool pipe_pays(const imx_env* e, int n_tiles) {
     const int64_t bytes_per_env = 8 * (int64_t)e->S + 4 * e->R + (int64_t)e->m * (16 + e->O * (e->cfg.obs_f32 ? 4 : 8));
     if (e->step_et) return bytes_per_env * e->N <= ((int64_t)384 << 20);   // env-per-thread tiles: one-tile kernel from ~0.5 Mi envs (div2: 115 vs 124 us at 1 Mi)
     if (e->div) return true;
+    if (e->l2_hints) return true;                          // the priorities live in the pipelined kernel (serial 4-stage at 512 Ki envs: 38.0 vs 41.8 us)
     return bytes_per_env * e->N <= ((int64_t)192 << 20);
 }
 // CTAs launched per SM by the pipelined kernel (tiles are dealt round-robin over the grid).  Measured per family: 8 for the
@@ -1514,6 +1538,7 @@ extern "C" int imx_jit_compile_check(const imx_config* cfg, int variant, char* l
         const char* st = getenv("IMX_STEP_ET_THREADS");
         const int et_threads = (st && (atoi(st) == 32 || atoi(st) == 64 || atoi(st) == 128)) ? atoi(st) : 32;
         tmp.jit_threads = tmp.step_et ? et_threads : tmp.tma_threads;
+        tmp.l2_hints = decide_l2_hints(&tmp, 0);
     }
     compute_tile(&tmp, tmp.tile, m_pad_of(&tmp));
     compute_tile(&tmp, tmp.tile_jit, m_pad_of(&tmp), false, tmp.step_et ? tmp.jit_threads : 0);

@@ -76,39 +76,51 @@ __global__ void IMX_PIPE_BOUNDS step_kernel_pipe(const __grid_constant__ StepArg
         if (KF(has_carry)) b_in += b_cell4;
         if (DIV && KF(NB) > 0) b_in += b_bt;
         auto first_env = [&](int k) { return ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * E; };
+#if defined(IMX_L2_HINTS) && IMX_L2_HINTS
+        const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+#define PIPE_LOAD_STREAM(d, s_, b, bar) bulk_load_hint(d, s_, b, bar, pol_stream)
+#define PIPE_LOAD_KEEP(d, s_, b, bar) bulk_load_hint(d, s_, b, bar, pol_keep)
+#define PIPE_STORE_STREAM(d, s_, b) bulk_store_hint(d, s_, b, pol_stream)
+#define PIPE_STORE_KEEP(d, s_, b) bulk_store_hint(d, s_, b, pol_keep)
+#else
+#define PIPE_LOAD_STREAM(d, s_, b, bar) bulk_load_g2s(d, s_, b, bar)
+#define PIPE_LOAD_KEEP(d, s_, b, bar) bulk_load_g2s(d, s_, b, bar)
+#define PIPE_STORE_STREAM(d, s_, b) bulk_store_only(d, s_, b)
+#define PIPE_STORE_KEEP(d, s_, b) bulk_store_only(d, s_, b)
+#endif
         auto issue_loads = [&](int k) {
             const int s = k % S;
             unsigned char* st = smem + (size_t)s * KT(total);
             const int64_t n0 = first_env(k);
             uint64_t* bar = &full[s];
             mbar_expect_tx(bar, b_in);
-            bulk_load_g2s(st + KT(off_act), A.actions + n0 * m, b_cell8, bar);
+            PIPE_LOAD_STREAM(st + KT(off_act), A.actions + n0 * m, b_cell8, bar);
             for (int r = 0; r < KF(R); ++r)
-                bulk_load_g2s(st + KT(off_dem) + (size_t)r * b_dem, A.demand_T + ((int64_t)A.t * KF(R) + r) * A.N + n0, b_dem, bar);
-            bulk_load_g2s(st + KT(off_inv), A.inv + n0 * m, b_cell4, bar);
-            bulk_load_g2s(st + KT(off_bl), A.backlog + n0 * m, b_cell4, bar);
-            bulk_load_g2s(st + KT(off_ou), A.order_u + n0 * m, b_cell4, bar);
-            bulk_load_g2s(st + KT(off_pipe), A.pipe + n0 * KF(L), b_pipe, bar);
-            if (KF(need_hd)) bulk_load_g2s(st + KT(off_hd), A.hist_d + n0 * m * KF(P), b_hist, bar);
-            if (KF(need_ho)) bulk_load_g2s(st + KT(off_ho), A.hist_o + n0 * m * KF(P), b_hist, bar);
-            if (KF(has_carry)) bulk_load_g2s(st + KT(off_carry), A.carry + n0 * m, b_cell4, bar);
-            if (DIV && KF(NB) > 0) bulk_load_g2s(st + KT(off_bt), A.bt + n0 * KF(NB), b_bt, bar);
+                PIPE_LOAD_STREAM(st + KT(off_dem) + (size_t)r * b_dem, A.demand_T + ((int64_t)A.t * KF(R) + r) * A.N + n0, b_dem, bar);
+            PIPE_LOAD_KEEP(st + KT(off_inv), A.inv + n0 * m, b_cell4, bar);
+            PIPE_LOAD_KEEP(st + KT(off_bl), A.backlog + n0 * m, b_cell4, bar);
+            PIPE_LOAD_KEEP(st + KT(off_ou), A.order_u + n0 * m, b_cell4, bar);
+            PIPE_LOAD_KEEP(st + KT(off_pipe), A.pipe + n0 * KF(L), b_pipe, bar);
+            if (KF(need_hd)) PIPE_LOAD_KEEP(st + KT(off_hd), A.hist_d + n0 * m * KF(P), b_hist, bar);
+            if (KF(need_ho)) PIPE_LOAD_KEEP(st + KT(off_ho), A.hist_o + n0 * m * KF(P), b_hist, bar);
+            if (KF(has_carry)) PIPE_LOAD_KEEP(st + KT(off_carry), A.carry + n0 * m, b_cell4, bar);
+            if (DIV && KF(NB) > 0) PIPE_LOAD_KEEP(st + KT(off_bt), A.bt + n0 * KF(NB), b_bt, bar);
         };
         auto issue_stores = [&](int k) {
             const int s = k % S;
             const unsigned char* st = smem + (size_t)s * KT(total);
             const int64_t n0 = first_env(k);
-            if (KHAS(cc)) bulk_store_only(reinterpret_cast<unsigned char*>(A.cc) + n0 * m * A.cc_W * es, st + KT(off_cc), (uint32_t)E * m * A.cc_W * es);
-            if (KHAS(obs)) bulk_store_only(reinterpret_cast<unsigned char*>(A.obs) + n0 * m * O * es, st + KT(off_obs), (uint32_t)E * m * O * es);
-            bulk_store_only(A.reward + (KF(multi) ? n0 * m : n0), st + KT(off_rew), KF(multi) ? b_cell8 : (uint32_t)E * 8u);
-            bulk_store_only(A.inv + n0 * m, st + KT(off_inv), b_cell4);
-            bulk_store_only(A.backlog + n0 * m, st + KT(off_bl), b_cell4);
-            bulk_store_only(A.order_u + n0 * m, st + KT(off_ou), b_cell4);
-            bulk_store_only(A.pipe + n0 * KF(L), st + KT(off_pipe), b_pipe);
-            if (KF(need_hd)) bulk_store_only(A.hist_d + n0 * m * KF(P), st + KT(off_hd), b_hist);
-            if (KF(need_ho)) bulk_store_only(A.hist_o + n0 * m * KF(P), st + KT(off_ho), b_hist);
-            if (KF(has_carry)) bulk_store_only(A.carry + n0 * m, st + KT(off_carry), b_cell4);
-            if (DIV && KF(NB) > 0) bulk_store_only(A.bt + n0 * KF(NB), st + KT(off_bt), b_bt);
+            if (KHAS(cc)) PIPE_STORE_STREAM(reinterpret_cast<unsigned char*>(A.cc) + n0 * m * A.cc_W * es, st + KT(off_cc), (uint32_t)E * m * A.cc_W * es);
+            if (KHAS(obs)) PIPE_STORE_STREAM(reinterpret_cast<unsigned char*>(A.obs) + n0 * m * O * es, st + KT(off_obs), (uint32_t)E * m * O * es);
+            PIPE_STORE_KEEP(A.reward + (KF(multi) ? n0 * m : n0), st + KT(off_rew), KF(multi) ? b_cell8 : (uint32_t)E * 8u);
+            PIPE_STORE_KEEP(A.inv + n0 * m, st + KT(off_inv), b_cell4);
+            PIPE_STORE_KEEP(A.backlog + n0 * m, st + KT(off_bl), b_cell4);
+            PIPE_STORE_KEEP(A.order_u + n0 * m, st + KT(off_ou), b_cell4);
+            PIPE_STORE_KEEP(A.pipe + n0 * KF(L), st + KT(off_pipe), b_pipe);
+            if (KF(need_hd)) PIPE_STORE_KEEP(A.hist_d + n0 * m * KF(P), st + KT(off_hd), b_hist);
+            if (KF(need_ho)) PIPE_STORE_KEEP(A.hist_o + n0 * m * KF(P), st + KT(off_ho), b_hist);
+            if (KF(has_carry)) PIPE_STORE_KEEP(A.carry + n0 * m, st + KT(off_carry), b_cell4);
+            if (DIV && KF(NB) > 0) PIPE_STORE_KEEP(A.bt + n0 * KF(NB), st + KT(off_bt), b_bt);
             bulk_commit();
         };
         const int pre = n_my < S ? n_my : S;

@@ -70,6 +70,30 @@ __device__ __forceinline__ void bulk_store_only(void* gdst, const void* ssrc, ui
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// L2 eviction priorities for the bulk copies (runtime-specialised build, IMX_L2_HINTS): the observation / critic-row stream is
+// written once and never read by the path (evict_first), the state is read and rewritten every period and the step rewards are
+// read back by the episode statistics (evict_last) — so the write-once stream does not push the re-used lines out of L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_store_hint(void* gdst, const void* ssrc, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+                 "r"(bytes), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load_hint(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
 // L2 prefetch of a global byte range (a hint: it moves no data into the SM and cannot observe a stale value — L2 is the
 // point of coherence, a later write by the kernel in front simply updates the line).  Issued BEFORE griddepcontrol.wait for
 // the one input a step reads that is cold: the caller's action block (in the benchmark loop it comes from HBM every period,
