@@ -78,11 +78,19 @@ __global__ void IMX_PIPE_BOUNDS step_kernel_pipe(const __grid_constant__ StepArg
         auto first_env = [&](int k) { return ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * E; };
 #if defined(IMX_L2_HINTS) && IMX_L2_HINTS
         const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+#if IMX_L2_HINTS == 2   /* outputs only: the observation stream is evict_first, the rewards evict_last; loads and state untouched */
+#define PIPE_LOAD_STREAM(d, s_, b, bar) bulk_load_g2s(d, s_, b, bar)
+#define PIPE_LOAD_KEEP(d, s_, b, bar) bulk_load_g2s(d, s_, b, bar)
+#define PIPE_STORE_STATE(d, s_, b) bulk_store_only(d, s_, b)
+#else
 #define PIPE_LOAD_STREAM(d, s_, b, bar) bulk_load_hint(d, s_, b, bar, pol_stream)
 #define PIPE_LOAD_KEEP(d, s_, b, bar) bulk_load_hint(d, s_, b, bar, pol_keep)
+#define PIPE_STORE_STATE(d, s_, b) bulk_store_hint(d, s_, b, pol_keep)
+#endif
 #define PIPE_STORE_STREAM(d, s_, b) bulk_store_hint(d, s_, b, pol_stream)
 #define PIPE_STORE_KEEP(d, s_, b) bulk_store_hint(d, s_, b, pol_keep)
 #else
+#define PIPE_STORE_STATE(d, s_, b) bulk_store_only(d, s_, b)
 #define PIPE_LOAD_STREAM(d, s_, b, bar) bulk_load_g2s(d, s_, b, bar)
 #define PIPE_LOAD_KEEP(d, s_, b, bar) bulk_load_g2s(d, s_, b, bar)
 #define PIPE_STORE_STREAM(d, s_, b) bulk_store_only(d, s_, b)
@@ -113,14 +121,14 @@ __global__ void IMX_PIPE_BOUNDS step_kernel_pipe(const __grid_constant__ StepArg
             if (KHAS(cc)) PIPE_STORE_STREAM(reinterpret_cast<unsigned char*>(A.cc) + n0 * m * A.cc_W * es, st + KT(off_cc), (uint32_t)E * m * A.cc_W * es);
             if (KHAS(obs)) PIPE_STORE_STREAM(reinterpret_cast<unsigned char*>(A.obs) + n0 * m * O * es, st + KT(off_obs), (uint32_t)E * m * O * es);
             PIPE_STORE_KEEP(A.reward + (KF(multi) ? n0 * m : n0), st + KT(off_rew), KF(multi) ? b_cell8 : (uint32_t)E * 8u);
-            PIPE_STORE_KEEP(A.inv + n0 * m, st + KT(off_inv), b_cell4);
-            PIPE_STORE_KEEP(A.backlog + n0 * m, st + KT(off_bl), b_cell4);
-            PIPE_STORE_KEEP(A.order_u + n0 * m, st + KT(off_ou), b_cell4);
-            PIPE_STORE_KEEP(A.pipe + n0 * KF(L), st + KT(off_pipe), b_pipe);
-            if (KF(need_hd)) PIPE_STORE_KEEP(A.hist_d + n0 * m * KF(P), st + KT(off_hd), b_hist);
-            if (KF(need_ho)) PIPE_STORE_KEEP(A.hist_o + n0 * m * KF(P), st + KT(off_ho), b_hist);
-            if (KF(has_carry)) PIPE_STORE_KEEP(A.carry + n0 * m, st + KT(off_carry), b_cell4);
-            if (DIV && KF(NB) > 0) PIPE_STORE_KEEP(A.bt + n0 * KF(NB), st + KT(off_bt), b_bt);
+            PIPE_STORE_STATE(A.inv + n0 * m, st + KT(off_inv), b_cell4);
+            PIPE_STORE_STATE(A.backlog + n0 * m, st + KT(off_bl), b_cell4);
+            PIPE_STORE_STATE(A.order_u + n0 * m, st + KT(off_ou), b_cell4);
+            PIPE_STORE_STATE(A.pipe + n0 * KF(L), st + KT(off_pipe), b_pipe);
+            if (KF(need_hd)) PIPE_STORE_STATE(A.hist_d + n0 * m * KF(P), st + KT(off_hd), b_hist);
+            if (KF(need_ho)) PIPE_STORE_STATE(A.hist_o + n0 * m * KF(P), st + KT(off_ho), b_hist);
+            if (KF(has_carry)) PIPE_STORE_STATE(A.carry + n0 * m, st + KT(off_carry), b_cell4);
+            if (DIV && KF(NB) > 0) PIPE_STORE_STATE(A.bt + n0 * KF(NB), st + KT(off_bt), b_bt);
             bulk_commit();
         };
         const int pre = n_my < S ? n_my : S;
