@@ -219,8 +219,9 @@ int imx_return_stats(imx_env* env, const double* return_dev, double* stats_dev /
 /* Statistics of one episode from its per-period rewards (the evaluation loops' "reward += r" then
  * np.mean / np.std over episodes): return[n][agent] = sum over periods in period order, then the
  * reduction of imx_return_stats.  step_reward_dev [periods][N][m] (MAIM kinds) / [periods][N];
- * return_dev [N][m] / [N] optional; accumulate != 0 adds into stats_dev (an evaluation batch builds
- * up on the device, reduced across GPUs once).  Three launches, no host work: graph-capturable. */
+ * return_dev [N][m] / [N] optional (only written when given); accumulate != 0 adds into stats_dev (an
+ * evaluation batch builds up on the device, reduced across GPUs once).  Two launches (programmatic
+ * dependents of whatever precedes them on the stream), no host work: graph-capturable. */
 int imx_episode_stats(imx_env* env, const double* step_reward_dev, int periods, double* return_dev, double* stats_dev,
                       int accumulate, void* stream);
 

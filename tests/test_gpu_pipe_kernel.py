@@ -57,6 +57,25 @@ def test_pipe_kernel_matches_c_oracle(kind, preset, N, stages, ctas, monkeypatch
         np.testing.assert_array_equal(st["backlog_to"], want["backlog_to"])
 
 
+@pytest.mark.parametrize("hints,prefetch", [("0", "0"), ("1", "1"), ("2", "1"), ("1", "0")])
+@pytest.mark.parametrize("kind,preset,N", [("MAIM", "serial4", 6148), ("MAIM_div", "div2", 9000), ("IM", "serial8", 3072 + 32)])
+def test_l2_priorities_and_input_prefetch_do_not_change_results(kind, preset, N, hints, prefetch, monkeypatch):
+    """The L2 eviction priorities on the bulk copies (IMX_L2_HINTS = 0 none / 1 all / 2 outputs only) and the L2 prefetch of the
+    action tiles and demand rows ahead of griddepcontrol.wait (IMX_ACT_PREFETCH) are cache hints only: every combination gives the
+    oracle's bits (the library picks them from the batch size; the switches force each variant here)."""
+    monkeypatch.setenv("IMX_PIPE", "1")
+    monkeypatch.setenv("IMX_L2_HINTS", hints)
+    monkeypatch.setenv("IMX_ACT_PREFETCH", prefetch)
+    cfg = presets.PRESETS[preset]()
+    rng = np.random.default_rng(hash((kind, preset, N, hints, prefetch)) % 2 ** 32)
+    obs, rew, st, want, variants = _episode(kind, cfg, N, rng, periods=10)
+    assert 3 in variants, variants
+    np.testing.assert_array_equal(obs, want["obs_last"])
+    np.testing.assert_array_equal(rew, want["reward"])
+    for k in ("inv", "backlog", "order_u", "pipe"):
+        np.testing.assert_array_equal(st[k], want[k], err_msg=k)
+
+
 def test_pipe_kernel_f32_obs_and_no_obs(monkeypatch):
     monkeypatch.setenv("IMX_PIPE", "1")
     monkeypatch.setenv("IMX_PIPE_CTAS", "1")
