@@ -64,20 +64,18 @@ __global__ void IMX_PIPE_BOUNDS step_kernel_pipe(const __grid_constant__ StepArg
     }
     __syncthreads();                                 // the only CTA-wide barrier: the roles part ways here
 
-    if (tid >= CT) {
-        if (tid != CT) return;
-        // ---------------------------------------------------------------- producer ---------------------------------
-        const uint32_t b_cell4 = (uint32_t)E * m * 4u, b_cell8 = (uint32_t)E * m * 8u;
-        const uint32_t b_pipe = (uint32_t)E * KF(L) * 4u, b_hist = b_cell4 * (uint32_t)KF(P);
-        const uint32_t b_bt = (uint32_t)E * KF(NB) * 4u, b_dem = (uint32_t)E * 4u;
-        uint32_t b_in = b_cell8 + (uint32_t)KF(R) * b_dem + 3u * b_cell4 + b_pipe;
-        if (KF(need_hd)) b_in += b_hist;
-        if (KF(need_ho)) b_in += b_hist;
-        if (KF(has_carry)) b_in += b_cell4;
-        if (DIV && KF(NB) > 0) b_in += b_bt;
-        auto first_env = [&](int k) { return ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * E; };
+    // ---- what every role that issues bulk loads needs (the producer, and lane 0 of each compute warp for the first ring fill) ----
+    const uint32_t b_cell4 = (uint32_t)E * m * 4u, b_cell8 = (uint32_t)E * m * 8u;
+    const uint32_t b_pipe = (uint32_t)E * KF(L) * 4u, b_hist = b_cell4 * (uint32_t)KF(P);
+    const uint32_t b_bt = (uint32_t)E * KF(NB) * 4u, b_dem = (uint32_t)E * 4u;
+    uint32_t b_in = b_cell8 + (uint32_t)KF(R) * b_dem + 3u * b_cell4 + b_pipe;
+    if (KF(need_hd)) b_in += b_hist;
+    if (KF(need_ho)) b_in += b_hist;
+    if (KF(has_carry)) b_in += b_cell4;
+    if (DIV && KF(NB) > 0) b_in += b_bt;
+    auto first_env = [&](int k) { return ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * E; };
 #if defined(IMX_L2_HINTS) && IMX_L2_HINTS
-        const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
 #if IMX_L2_HINTS == 2   /* outputs only: the observation stream is evict_first, the rewards evict_last; loads and state untouched */
 #define PIPE_LOAD_STREAM(d, s_, b, bar) bulk_load_g2s(d, s_, b, bar)
 #define PIPE_LOAD_KEEP(d, s_, b, bar) bulk_load_g2s(d, s_, b, bar)
@@ -96,24 +94,42 @@ __global__ void IMX_PIPE_BOUNDS step_kernel_pipe(const __grid_constant__ StepArg
 #define PIPE_STORE_STREAM(d, s_, b) bulk_store_only(d, s_, b)
 #define PIPE_STORE_KEEP(d, s_, b) bulk_store_only(d, s_, b)
 #endif
-        auto issue_loads = [&](int k) {
-            const int s = k % S;
-            unsigned char* st = smem + (size_t)s * KT(total);
-            const int64_t n0 = first_env(k);
-            uint64_t* bar = &full[s];
-            mbar_expect_tx(bar, b_in);
-            PIPE_LOAD_STREAM(st + KT(off_act), A.actions + n0 * m, b_cell8, bar);
-            for (int r = 0; r < KF(R); ++r)
-                PIPE_LOAD_STREAM(st + KT(off_dem) + (size_t)r * b_dem, A.demand_T + ((int64_t)A.t * KF(R) + r) * A.N + n0, b_dem, bar);
-            PIPE_LOAD_KEEP(st + KT(off_inv), A.inv + n0 * m, b_cell4, bar);
-            PIPE_LOAD_KEEP(st + KT(off_bl), A.backlog + n0 * m, b_cell4, bar);
-            PIPE_LOAD_KEEP(st + KT(off_ou), A.order_u + n0 * m, b_cell4, bar);
-            PIPE_LOAD_KEEP(st + KT(off_pipe), A.pipe + n0 * KF(L), b_pipe, bar);
-            if (KF(need_hd)) PIPE_LOAD_KEEP(st + KT(off_hd), A.hist_d + n0 * m * KF(P), b_hist, bar);
-            if (KF(need_ho)) PIPE_LOAD_KEEP(st + KT(off_ho), A.hist_o + n0 * m * KF(P), b_hist, bar);
-            if (KF(has_carry)) PIPE_LOAD_KEEP(st + KT(off_carry), A.carry + n0 * m, b_cell4, bar);
-            if (DIV && KF(NB) > 0) PIPE_LOAD_KEEP(st + KT(off_bt), A.bt + n0 * KF(NB), b_bt, bar);
-        };
+    // the action tile and demand rows of tile k into L2 while the previous launch drains (see bulk_prefetch_l2)
+    auto prefetch_inputs = [&](int k) {
+#if !defined(IMX_NO_ACT_PREFETCH)
+        bulk_prefetch_l2(A.actions + first_env(k) * m, b_cell8);
+        for (int r = 0; r < KF(R); ++r)              // (the demand trace was written at reset() and is long evicted)
+            bulk_prefetch_l2(A.demand_T + ((int64_t)A.t * KF(R) + r) * A.N + first_env(k), b_dem);
+#endif
+    };
+    auto issue_loads = [&](int k) {
+        const int s = k % S;
+        unsigned char* st = smem + (size_t)s * KT(total);
+        const int64_t n0 = first_env(k);
+        uint64_t* bar = &full[s];
+        mbar_expect_tx(bar, b_in);
+        PIPE_LOAD_STREAM(st + KT(off_act), A.actions + n0 * m, b_cell8, bar);
+        for (int r = 0; r < KF(R); ++r)
+            PIPE_LOAD_STREAM(st + KT(off_dem) + (size_t)r * b_dem, A.demand_T + ((int64_t)A.t * KF(R) + r) * A.N + n0, b_dem, bar);
+        PIPE_LOAD_KEEP(st + KT(off_inv), A.inv + n0 * m, b_cell4, bar);
+        PIPE_LOAD_KEEP(st + KT(off_bl), A.backlog + n0 * m, b_cell4, bar);
+        PIPE_LOAD_KEEP(st + KT(off_ou), A.order_u + n0 * m, b_cell4, bar);
+        PIPE_LOAD_KEEP(st + KT(off_pipe), A.pipe + n0 * KF(L), b_pipe, bar);
+        if (KF(need_hd)) PIPE_LOAD_KEEP(st + KT(off_hd), A.hist_d + n0 * m * KF(P), b_hist, bar);
+        if (KF(need_ho)) PIPE_LOAD_KEEP(st + KT(off_ho), A.hist_o + n0 * m * KF(P), b_hist, bar);
+        if (KF(has_carry)) PIPE_LOAD_KEEP(st + KT(off_carry), A.carry + n0 * m, b_cell4, bar);
+        if (DIV && KF(NB) > 0) PIPE_LOAD_KEEP(st + KT(off_bt), A.bt + n0 * KF(NB), b_bt, bar);
+    };
+
+    // The first ring fill is the launch's critical path: one thread issuing S tiles x 7-10 bulk loads one after the other
+    // puts the last tile's loads ~0.5 us behind the first's (each bulk copy is ~10 dependent uniform-datapath instructions).
+    // The compute warps have nothing to do until their first tile lands, so the fill is dealt round-robin over ALL warps:
+    // tile k of the fill is issued by warp k mod NW (0 = producer warp, w + 1 = compute warp w).
+    constexpr int NW = 1 + CT / 32;
+    const int pre = n_my < S ? n_my : S;
+    if (tid >= CT) {
+        if (tid != CT) return;
+        // ---------------------------------------------------------------- producer ---------------------------------
         auto issue_stores = [&](int k) {
             const int s = k % S;
             const unsigned char* st = smem + (size_t)s * KT(total);
@@ -131,17 +147,9 @@ __global__ void IMX_PIPE_BOUNDS step_kernel_pipe(const __grid_constant__ StepArg
             if (DIV && KF(NB) > 0) PIPE_STORE_STATE(A.bt + n0 * KF(NB), st + KT(off_bt), b_bt);
             bulk_commit();
         };
-        const int pre = n_my < S ? n_my : S;
-#if !defined(IMX_NO_ACT_PREFETCH)
-        // the action tiles of the first ring fill into L2 while the previous launch drains (see bulk_prefetch_l2)
-        for (int k = 0; k < pre; ++k) {
-            bulk_prefetch_l2(A.actions + first_env(k) * m, b_cell8);
-            for (int r = 0; r < KF(R); ++r)          // ... and this period's demand rows (written at reset(), long evicted)
-                bulk_prefetch_l2(A.demand_T + ((int64_t)A.t * KF(R) + r) * A.N + first_env(k), b_dem);
-        }
-#endif
+        for (int k = 0; k < pre; k += NW) prefetch_inputs(k);
         pdl_wait();                                  // state written by the previous step must be complete and visible
-        for (int k = 0; k < pre; ++k) issue_loads(k);
+        for (int k = 0; k < pre; k += NW) issue_loads(k);
         for (int k = 0; k < n_my; ++k) {
             mbar_wait(&done[k % S], (uint32_t)((k / S) & 1));
             issue_stores(k);
@@ -158,6 +166,11 @@ __global__ void IMX_PIPE_BOUNDS step_kernel_pipe(const __grid_constant__ StepArg
 
     // -------------------------------------------------------------------- compute warps ------------------------------
     const LaneCtx<MAXC> L = make_lane_ctx<M_PAD, MAXC, DIV>(A, tid);
+    if ((tid & 31) == 0 && (tid >> 5) + 1 < pre) {   // this warp's share of the first ring fill (tiles w + 1, w + 1 + NW, ...)
+        for (int k = (tid >> 5) + 1; k < pre; k += NW) prefetch_inputs(k);
+        pdl_wait();
+        for (int k = (tid >> 5) + 1; k < pre; k += NW) issue_loads(k);
+    }
     // (prefetching the rescale table into L1 here was measured: 5.5 -> 8.3 us per launch at 65 536 envs, profiles/r2_act_prefetch_ab.txt)
     for (int k = 0; k < n_my; ++k) {
         const int s = k % S;
