@@ -205,7 +205,8 @@ static int choose_tma_threads(const imx_env* e) {
     const int64_t bytes_per_env = 8 * (int64_t)e->S + 4 * e->R + (int64_t)e->m * (16 + e->O * (e->cfg.obs_f32 ? 4 : 8));
     const bool small4 = !e->div && m_pad_of(e) == 4 && e->N >= 1024 && bytes_per_env * e->N <= ((int64_t)192 << 20);
     // (512 Ki envs of a 4-wide chain, pipelined with the L2 priorities: 256-thread tiles 35.7 us, 128-thread 38.1, 64-thread 38.9)
-    const int dflt = small4 ? 64 : (m_pad_of(e) <= 4 && e->N >= ((int64_t)1 << 19)) ? 256 : 128;
+    const bool big4 = !e->div && m_pad_of(e) == 4 && e->N >= ((int64_t)1 << 19);
+    const int dflt = small4 ? 64 : (big4 || (m_pad_of(e) <= 4 && e->N >= ((int64_t)1 << 20))) ? 256 : 128;
     const int v = tt ? atoi(tt) : dflt;
     return ((v == 64 || v == 128 || v == 256 || v == 512) && v >= 2 * m_pad_of(e)) ? v : 256;
 }
