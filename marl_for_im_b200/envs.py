@@ -739,14 +739,18 @@ class _ImxEnvBase:
         _lib.check(self._lib.imx_return_stats(self._handle, C.c_void_p(returns.data_ptr()), C.c_void_p(out.data_ptr()), self._stream()))
         return out
 
-    def episode_stats(self, step_rewards, stats=None, accumulate=False):
+    def episode_stats(self, step_rewards, stats=None, accumulate=False, returns=None):
         """step_rewards [T, N, m] (MAIM kinds) or [T, N] float64 on the device → statistics vector (see
-        return_stats); ``accumulate=True`` adds into ``stats`` (evaluation batches, one all-reduce at the end)."""
+        return_stats); ``accumulate=True`` adds into ``stats`` (evaluation batches, one all-reduce at the end);
+        ``returns`` ([N, m] / [N] float64, contiguous) also receives the episode returns (sum over periods in period order)."""
         m = self.num_nodes
         if stats is None:
             stats = torch.zeros(3 + (2 * m if self.MULTI else 0), dtype=torch.float64, device=self.device)
         sr = step_rewards.contiguous()
-        _lib.check(self._lib.imx_episode_stats(self._handle, C.c_void_p(sr.data_ptr()), int(sr.shape[0]), None,
+        if returns is not None and (not returns.is_contiguous() or returns.dtype != torch.float64 or returns.numel() != sr[0].numel()):
+            raise ValueError("returns must be a contiguous float64 tensor of one period's reward shape")
+        _lib.check(self._lib.imx_episode_stats(self._handle, C.c_void_p(sr.data_ptr()), int(sr.shape[0]),
+                                               C.c_void_p(returns.data_ptr()) if returns is not None else None,
                                                C.c_void_p(stats.data_ptr()), int(bool(accumulate)), self._stream()))
         return stats
 

@@ -204,6 +204,36 @@ def test_episode_stats_accumulates_like_the_eval_loops():
     np.testing.assert_allclose(st1, [N, tot.sum().item(), (tot * tot).sum().item()], rtol=1e-12)
 
 
+@pytest.mark.parametrize("kind,preset,N", [("MAIM", "serial2", 257), ("MAIM", "serial8", 4097), ("MAIM_div", "div2", 1000),
+                                           ("MAIM_div", "div1", 33), ("IM", "serial4", 513), ("IM_div", "div2", 70000)])
+def test_episode_statistics_every_slice_shape(kind, preset, N):
+    """The two-stage statistics (one block per slice of envs, one warp per statistic pair) for agent counts 1 / 2 / 4 / 6 / 8 —
+    i.e. 256, 256, 256, 160 and 128 envs per slice — and env counts that end inside a slice: returns = step rewards added in
+    period order (bit for bit), statistics against float64 numpy within summation-order tolerance, and the fused form equal to the
+    plain form on its own returns."""
+    from marl_for_im_b200.envs import ENV_CLASSES
+    env = ENV_CLASSES[kind](dict(presets.PRESETS[preset](), num_envs=N))
+    m, T = env.num_nodes, env.num_periods
+    cols = m if env.MULTI else 1
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(N)
+    sr = torch.randn((T, N, cols) if env.MULTI else (T, N), dtype=torch.float64, device="cuda:0", generator=g) * 50.0
+    ret = torch.empty((N, cols) if env.MULTI else (N,), dtype=torch.float64, device="cuda:0")
+    st = env.episode_stats(sr, returns=ret)
+    want_ret = torch.zeros_like(ret)
+    for t in range(T):
+        want_ret += sr[t]
+    assert torch.equal(ret, want_ret)
+    assert torch.equal(st, env.return_stats(ret))
+    r = want_ret.reshape(N, cols).cpu().numpy()
+    tot = r.sum(axis=1)
+    want = [float(N), tot.sum(), (tot * tot).sum()]
+    if env.MULTI:
+        for c in range(cols):
+            want += [r[:, c].sum(), (r[:, c] ** 2).sum()]
+    np.testing.assert_allclose(st.cpu().numpy(), want, rtol=1e-11, atol=1e-6)
+
+
 def test_dfo_func_batch_matches_single_env_objective():
     from scipy.stats import poisson
     from marl_for_im_b200.base_restock_policy import dfo_func_batch, population_search_inventory_policy
