@@ -80,12 +80,13 @@ __global__ void __launch_bounds__(128) dfo_objective_kernel(const double* __rest
 
 // Episode statistics [n, Σ total, Σ total², then per agent (Σ, Σ²)] in a fixed, deterministic
 // order (the payload of the single cross-GPU all-reduce).  Two stages, both of a shape that depends only on N and m:
-//   1. stats_slice_kernel: one block per slice of `epb` consecutive envs (stats_envs_per_block: as many whole envs as fit in
-//      256 cells, at least 32), one thread per cell.  FUSED: the thread first adds the step rewards of its cell in period
-//      order ("reward += r", inv_management.py:223-231; one coalesced row of step_reward [T][cells] per period), writes the
-//      episode return and leaves it in shared memory — no second pass over the returns; otherwise it loads the return.
-//      Thread e < epb then owns env e of the slice: per-env total = sum over agents in agent order, and every statistic is
-//      reduced over the block (warp shuffles, then the warps in order).
+//   1. stats_slice_kernel: one block per slice of `epb` consecutive envs (stats_envs_per_block: whole warps of envs, up to
+//      1024 returns and at most 256 envs per slice), up to four cells per thread.  FUSED: the thread first adds the step
+//      rewards of its cells in period order ("reward += r", inv_management.py:223-231; one coalesced row of
+//      step_reward [T][cells] per period), writes the episode returns when the caller wants them and leaves them in shared
+//      memory — no second pass over the returns; otherwise it loads the returns.  Then one WARP per statistic pair: warp c
+//      reduces (Σ, Σ²) of agent c's returns, one more the per-env totals (sum over agents in agent order); lane g adds the
+//      envs g, g + 32, ... of the slice in that order and the lanes are added in a fixed shuffle tree.
 //   2. stats_final_kernel: one block per statistic adds the slices' partials (strided threads + a fixed tree).
 // Both are programmatic dependent launches (griddepcontrol.wait), so their launch latency hides behind the kernel in front.
 constexpr int STATS_THREADS = 256;
