@@ -122,6 +122,24 @@ def test_runtime_specialisation_compiles_for_sm100a_without_gpu():
             assert n > 10000, (kind, variant, n, buf.value.decode()[:500], lib.imx_last_error())
 
 
+@pytest.mark.parametrize("hints,prefetch", [("0", "0"), ("1", "1"), ("2", "1")])
+def test_cache_hint_variants_of_the_specialised_kernels_compile(hints, prefetch, monkeypatch):
+    """The L2 eviction-priority modes (IMX_L2_HINTS = none / all / outputs only) and the input prefetch switch select different
+    code in the pipelined kernel (createpolicy + cp.async.bulk ... .L2::cache_hint, cp.async.bulk.prefetch.L2): every variant
+    must build for sm_100a, serial and divergent (env-per-thread) alike."""
+    from marl_for_im_b200 import presets
+    monkeypatch.setenv("IMX_L2_HINTS", hints)
+    monkeypatch.setenv("IMX_ACT_PREFETCH", prefetch)
+    monkeypatch.setenv("IMX_JIT_CACHE", "0")
+    lib = _lib.load()
+    for kind, cfg in (("MAIM", presets.serial4()), ("MAIM_div", presets.div2())):
+        c = _raw_config(kind, cfg)
+        for variant in (0, 2):
+            buf = ctypes.create_string_buffer(8192)
+            n = lib.imx_jit_compile_check(ctypes.byref(c), variant, buf, 8192)
+            assert n > 10000, (kind, variant, hints, n, buf.value.decode()[:500], lib.imx_last_error())
+
+
 def test_header_is_plain_c99_and_links_against_the_library(tmp_path):
     """include/imx_b200.h must be usable from C: compile a C99 translation unit that takes the address of every declared
     entry point with -pedantic -Werror, and link it against libimx_b200.so (no GPU call is made)."""
