@@ -57,6 +57,29 @@ def test_non_standardised(kind, preset):
                         f"{kind} raw {td, pd, pa}")
 
 
+@pytest.mark.parametrize("kind,preset,std", [("MAIM", "serial4", True), ("MAIM", "serial8", False), ("MAIM_div", "div1", True),
+                                             ("MAIM_div", "div2", True), ("IM", "serial4", True), ("IM", "serial4", False),
+                                             ("IM_div", "div2", True)])
+def test_non_finite_and_huge_actions(kind, preset, std):
+    """+-inf, NaN (MAIM kinds) and finite values either side of 2^63: the MAIM kinds convert to int64 BEFORE clipping
+    (MAIM_env.py:344-347), so on the reference's x86-64 everything outside [-2^63, 2^63) becomes INT64_MIN and clips to order 0;
+    the IM kinds clip first (IM_env.py:300-302).  The oracle follows the reference through every special value, live."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import inject_nonfinite
+    rng = np.random.default_rng(hash((kind, preset, std)) % (2 ** 32))
+    for _ in range(4):
+        cfg = presets.PRESETS[preset]()
+        if not std:
+            cfg["standardise_actions"] = False
+        demand, actions = random_case(kind, cfg, rng)
+        actions = inject_nonfinite(actions, kind, rng)
+        with np.errstate(all="ignore"):
+            want = run_reference(kind, cfg, demand, actions, None)
+        got = run_oracle(kind, cfg, demand, actions, None)
+        assert_same(want, got)
+
+
 @pytest.mark.parametrize("kind,preset", [("MAIM", "serial4"), ("IM", "serial8"), ("MAIM_div", "div2"),
                                          ("IM_div", "div1")])
 def test_noisy_delay_replayed(kind, preset):
